@@ -1,0 +1,96 @@
+// The linear-algebra boundary as the host driver sees it.
+//
+// Mirrors the consumer side of the reference's closed engines:
+//   linalg_v3<Coeff,Order>::initialize/reduce  (call sites source/f4.hpp:91-93,
+//     output contract read by source/matrix.hpp:799-895)
+//   linalg<Matrix>::reduce                       (call site source/reduce.hpp:51-52)
+// A step matrix is handed over in Faugere-Lachartre block form:
+//   * rows 0..n_top-1 are the pivot rows A|B, row i has its (unit) lead at column i;
+//   * rows n_top.. are the rows to reduce, C|D, in the driver's order;
+//   * columns 0..n_top-1 are the pivot columns (ascending original order),
+//     columns n_top..n_cols-1 the non-pivot columns in their original order;
+//   * a row's column list is in the polynomial's term order, so entry k pairs
+//     with coefficient k of the row's *shared* coefficient array coeff_id[row].
+// Coefficients are standard residues in [0,p); every row is monic.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace gb {
+
+struct StepMatrix {
+    uint32_t p = 0;
+    uint32_t n_top = 0, n_bot = 0, n_cols = 0;
+    std::vector<uint64_t> row_ptr;      // n_top + n_bot + 1
+    std::vector<uint32_t> col;          // nnz, block-form column numbers
+    std::vector<uint32_t> coeff_id;     // per row, index into cf_ptr / cf_len
+    std::vector<const uint32_t*> cf_ptr;
+    std::vector<uint32_t> cf_len;
+    uint64_t nnz() const { return row_ptr.empty() ? 0 : row_ptr.back(); }
+    uint32_t n_rows() const { return n_top + n_bot; }
+    uint32_t n_nonpiv() const { return n_cols - n_top; }
+};
+
+// Reduced row echelon form of D' = D - C A^-1 B over the non-pivot columns:
+// rows sorted by ascending pivot, monic, fully inter-reduced; col holds
+// *relative* non-pivot column numbers (0..n_nonpiv-1), strictly increasing in
+// a row, pivot entry first.
+struct NewRows {
+    uint32_t n_new = 0;
+    std::vector<uint64_t> row_ptr;  // n_new + 1
+    std::vector<uint32_t> col;
+    std::vector<uint32_t> val;
+    double seconds = 0.0;           // engine time for this step (f4.hpp:93)
+    double kernel_seconds = 0.0;    // device-only part when known
+    uint64_t fma_top = 0;           // oracle only: SURVEY.md §8(d) invariant
+};
+
+struct Engine {
+    virtual ~Engine() = default;
+    virtual const char* name() const = 0;
+    // One F4 step (role of linalg_v3::initialize + reduce).
+    virtual void reduce_step(const StepMatrix& m, NewRows& out) = 0;
+    // Final inter-reduction (role of linalg<M>::reduce): same computation; the
+    // bottom rows have distinct non-pivot leads so n_new == n_bot.
+    virtual void reduce_final(const StepMatrix& m, NewRows& out) { reduce_step(m, out); }
+};
+
+// ---- step-matrix files (tests, bench, kernel development without the driver) --
+
+struct StepFile {
+    StepMatrix m;
+    std::vector<uint32_t> pool;       // backing store for m.cf_ptr
+    std::vector<uint64_t> pool_off;
+};
+
+inline void write_step_file(const std::string& path, const StepMatrix& m) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    uint64_t pool_len = 0;
+    for (auto l : m.cf_len) pool_len += l;
+    uint64_t hdr[8] = {0x3150545342474aull /* "JGBSTP1" */, m.p, m.n_top, m.n_bot, m.n_cols,
+                       m.nnz(), (uint64_t)m.cf_len.size(), pool_len};
+    std::fwrite(hdr, 8, 8, f);
+    std::fwrite(m.row_ptr.data(), 8, m.row_ptr.size(), f);
+    std::fwrite(m.col.data(), 4, m.col.size(), f);
+    std::fwrite(m.coeff_id.data(), 4, m.coeff_id.size(), f);
+    std::fwrite(m.cf_len.data(), 4, m.cf_len.size(), f);
+    for (size_t i = 0; i < m.cf_len.size(); ++i) std::fwrite(m.cf_ptr[i], 4, m.cf_len[i], f);
+    std::fclose(f);
+}
+
+inline void write_rows_file(const std::string& path, const NewRows& r) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    uint64_t hdr[3] = {0x3157524e42474aull /* "JGBNRW1" */, r.n_new, r.row_ptr.empty() ? 0 : r.row_ptr.back()};
+    std::fwrite(hdr, 8, 3, f);
+    std::fwrite(r.row_ptr.data(), 8, r.row_ptr.size(), f);
+    std::fwrite(r.col.data(), 4, r.col.size(), f);
+    std::fwrite(r.val.data(), 4, r.val.size(), f);
+    std::fclose(f);
+}
+
+}  // namespace gb

@@ -1,0 +1,501 @@
+#include "f4.hpp"
+
+#include <algorithm>
+#include <cassert>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+namespace gb {
+
+static inline uint32_t mulmod(uint32_t a, uint32_t b, uint32_t p) { return (uint32_t)((uint64_t)a * b % p); }
+
+F4::F4(const PolySystem& in, const Params& prm, Engine& eng)
+    : in_(in), prm_(prm), eng_(eng), p_(in.p) {
+    if (prm_.num_elim < 0 || (prm_.num_elim != 0 && (size_t)prm_.num_elim >= in.vars.size()))
+        throw std::runtime_error("Elimination block size must be smaller than the number of variables.");
+    cx_.init((int)in.vars.size(), prm_.num_elim, prm_.seed);
+    bt_ = MonoTable(&cx_, 1 << 16);
+    st_ = MonoTable(&cx_, 1 << 16);
+    import_generators();
+}
+
+// Sort terms decreasing, merge equal monomials, drop zeros / zero polynomials,
+// make monic (behaviour of source/basis.hpp:450-509).
+void F4::import_generators() {
+    const int nv = cx_.nv, st = cx_.stride;
+    size_t off = 0;
+    std::vector<uint16_t> e(st);
+    for (size_t g = 0; g < in_.lens.size(); ++g) {
+        std::vector<std::pair<uint32_t, uint32_t>> terms;  // (handle, coeff)
+        for (size_t j = 0; j < in_.lens[g]; ++j) {
+            const uint16_t* ex = &in_.exps[(off + j) * nv];
+            uint32_t d = 0, d1 = 0;
+            for (int k = 0; k < nv; ++k) { e[2 + k] = ex[k]; d += ex[k]; if (k < cx_.nelim) d1 += ex[k]; }
+            if (d >= (1u << 16)) throw std::runtime_error("Monomial degree too large.");
+            e[0] = (uint16_t)d; e[1] = (uint16_t)d1;
+            terms.emplace_back(bt_.insert(e.data(), cx_.hash(e.data())), in_.coeffs[off + j] % p_);
+        }
+        off += in_.lens[g];
+        std::stable_sort(terms.begin(), terms.end(), [&](auto const& a, auto const& b) {
+            return cx_.cmp(bt_.e(a.first), bt_.e(b.first)) > 0;
+        });
+        Poly f;
+        for (size_t j = 0; j < terms.size();) {
+            size_t k = j; uint64_t s = 0;
+            while (k < terms.size() && terms[k].first == terms[j].first) { s += terms[k].second; ++k; }
+            s %= p_;
+            if (s) { f.mon.push_back(terms[j].first); f.cf.push_back((uint32_t)s); }
+            j = k;
+        }
+        if (f.mon.empty()) continue;
+        uint32_t inv = inv_mod(f.cf[0], p_);
+        for (auto& c : f.cf) c = mulmod(c, inv, p_);
+        f.deg = 0;
+        for (auto m : f.mon) f.deg = std::max<uint32_t>(f.deg, bt_.e(m)[0]);
+        f.lm_mask = cx_.divmask(bt_.e(f.mon[0]));
+        if (bt_.e(f.mon[0])[0] == 0) trivial_ = true;
+        G_.push_back(std::move(f));
+    }
+    // generators sorted by increasing leading monomial (ties: input order)
+    std::stable_sort(G_.begin(), G_.end(), [&](Poly const& a, Poly const& b) {
+        return cx_.cmp(bt_.e(a.mon[0]), bt_.e(b.mon[0])) < 0;
+    });
+}
+
+void F4::make_trivial() {
+    trivial_ = true;
+    G_.clear(); P_.clear();
+    std::vector<uint16_t> e(cx_.stride, 0);
+    Poly one;
+    one.mon.push_back(bt_.insert(e.data(), 0));
+    one.cf.push_back(1);
+    one.lm_mask = 0;
+    G_.push_back(std::move(one));
+}
+
+// Gebauer-Moeller installation of generator h (criteria as in
+// source/update.hpp:29-269; independent code).
+void F4::update(uint32_t h) {
+    const int nv = cx_.nv, st = cx_.stride;
+    const uint16_t* eh = bt_.e(G_[h].mon[0]);
+    std::vector<uint16_t> ehv(eh, eh + st);  // bt_ may reallocate below
+    eh = ehv.data();
+    const uint64_t mh = G_[h].lm_mask;
+
+    // B criterion on the old pairs
+    {
+        size_t w = 0;
+        for (size_t k = 0; k < P_.size(); ++k) {
+            const Pair& pr = P_[k];
+            const uint16_t* el = bt_.e(pr.lcm);
+            bool kill = false;
+            if (cx_.divides(eh, el)) {
+                const uint16_t* ei = bt_.e(G_[pr.i].mon[0]);
+                const uint16_t* ej = bt_.e(G_[pr.j].mon[0]);
+                bool eq_i = true, eq_j = true;
+                for (int v = 0; v < nv; ++v) {
+                    if (std::max(ei[2 + v], eh[2 + v]) != el[2 + v]) eq_i = false;
+                    if (std::max(ej[2 + v], eh[2 + v]) != el[2 + v]) eq_j = false;
+                }
+                kill = !eq_i && !eq_j;
+            }
+            if (!kill) P_[w++] = pr; else ++stats.gm_removed;
+        }
+        P_.resize(w);
+    }
+
+    struct NP { uint32_t i, lcm; int32_t deg; uint64_t mask; bool coprime, dead; };
+    std::vector<NP> np;
+    np.reserve(h);
+    std::vector<uint16_t> el(st);
+    for (uint32_t i = 0; i < h; ++i) {
+        if (G_[i].redundant) continue;
+        const uint16_t* ei = bt_.e(G_[i].mon[0]);
+        uint32_t d = 0, d1 = 0; bool cop = true;
+        for (int v = 0; v < nv; ++v) {
+            uint16_t a = ei[2 + v], b = eh[2 + v];
+            if (a && b) cop = false;
+            uint16_t m = std::max(a, b);
+            el[2 + v] = m; d += m; if (v < cx_.nelim) d1 += m;
+        }
+        if (d >= (1u << 16)) throw std::overflow_error("degree overflow");
+        el[0] = (uint16_t)d; el[1] = (uint16_t)d1;
+        uint32_t l = bt_.insert(el.data(), cx_.hash(el.data()));
+        np.push_back({i, l, (int32_t)d, G_[i].lm_mask | mh, cop, false});
+    }
+    // increasing lcm; equal lcm: coprime first, then older generator first
+    std::sort(np.begin(), np.end(), [&](NP const& a, NP const& b) {
+        if (a.lcm != b.lcm) return cx_.cmp(bt_.e(a.lcm), bt_.e(b.lcm)) < 0;
+        if (a.coprime != b.coprime) return a.coprime;
+        return a.i < b.i;
+    });
+    // M criterion: a strictly smaller lcm divides
+    for (size_t a = 0; a < np.size(); ++a) {
+        if (np[a].coprime) continue;
+        const uint16_t* ea = bt_.e(np[a].lcm);
+        const uint64_t nm = ~np[a].mask;
+        for (size_t b = 0; b < a; ++b) {
+            if (np[b].mask & nm) continue;
+            if (np[b].lcm == np[a].lcm) continue;
+            if (cx_.divides(bt_.e(np[b].lcm), ea)) { np[a].dead = true; break; }
+        }
+    }
+    // F criterion: keep the first pair of every run of equal lcm
+    for (size_t a = 1; a < np.size(); ++a) {
+        if (np[a].coprime || np[a].dead) continue;
+        for (size_t b = a; b > 0 && np[b - 1].lcm == np[a].lcm; --b)
+            if (!np[b - 1].dead) { np[a].dead = true; break; }
+    }
+    for (auto const& q : np) {
+        if (q.dead || q.coprime) { ++stats.gm_removed; continue; }
+        P_.push_back({q.i, h, q.lcm, q.deg});
+    }
+    // older generators whose lead is divisible by the new lead become redundant
+    for (uint32_t i = 0; i < h; ++i) {
+        if (G_[i].redundant) continue;
+        if (mh & ~G_[i].lm_mask) continue;
+        if (cx_.divides(eh, bt_.e(G_[i].mon[0]))) G_[i].redundant = true;
+    }
+}
+
+void F4::update_all(size_t from) {
+    double t0 = now_s();
+    for (size_t h = from; h < G_.size(); ++h) update((uint32_t)h);
+    stats.t_update += now_s() - t0;
+}
+
+// Normal strategy: pairs of minimal degree, at most max_spairs of them, in
+// increasing lcm order (source/spair.hpp:190-264).
+long F4::select_pairs(int32_t& deg) {
+    double t0 = now_s();
+    long n;
+    if (prm_.all_pairs) {
+        std::sort(P_.begin(), P_.end(), [&](Pair const& a, Pair const& b) {
+            if (a.lcm == b.lcm) return false;
+            return cx_.cmp(bt_.e(a.lcm), bt_.e(b.lcm)) < 0;
+        });
+        n = (long)P_.size(); deg = 0xffff;
+    } else {
+        std::sort(P_.begin(), P_.end(), [&](Pair const& a, Pair const& b) {
+            if (a.deg != b.deg) return a.deg < b.deg;
+            if (a.lcm == b.lcm) return false;
+            return cx_.cmp(bt_.e(a.lcm), bt_.e(b.lcm)) < 0;
+        });
+        deg = P_[0].deg;
+        long cnt = 0;
+        while ((size_t)cnt < P_.size() && P_[cnt].deg == deg) ++cnt;
+        n = cnt;
+        if (prm_.max_spairs > 0 && n > prm_.max_spairs) n = prm_.max_spairs;
+    }
+    stats.pairs_reduced += n;
+    stats.t_select += now_s() - t0;
+    return n;
+}
+
+void F4::clear_step() {
+    st_.clear();
+    row_mon_.clear(); row_off_.assign(1, 0); row_gen_.clear(); row_top_.clear();
+    has_red_.clear();
+}
+
+void F4::add_row(uint32_t gen, const uint16_t* q, uint32_t hq, bool top) {
+    const Poly& f = G_[gen];
+    const int st = cx_.stride;
+    uint16_t tmp[258];
+    size_t base = row_mon_.size();
+    row_mon_.resize(base + f.mon.size());
+    for (size_t k = 0; k < f.mon.size(); ++k) {
+        const uint16_t* a = bt_.e(f.mon[k]);
+        for (int i = 0; i < st; ++i) tmp[i] = (uint16_t)(a[i] + q[i]);
+        row_mon_[base + k] = st_.insert(tmp, bt_.hv[f.mon[k]] + hq);
+    }
+    row_off_.push_back(row_mon_.size());
+    row_gen_.push_back(gen);
+    row_top_.push_back(top ? 1 : 0);
+    if (has_red_.size() < st_.size()) has_red_.resize(st_.size(), 0);
+    if (top) has_red_[row_mon_[base]] = 1;
+}
+
+// Rows of the selected pairs (source/matrix.hpp:215-347): per distinct lcm the
+// shortest generator gives the pivot row, all others rows to reduce.
+void F4::build_pair_rows(long n_sel) {
+    double t0 = now_s();
+    const int st = cx_.stride;
+    std::vector<uint32_t> gens;
+    std::vector<uint16_t> q(st);
+    for (long a = 0; a < n_sel;) {
+        long b = a; gens.clear();
+        while (b < n_sel && P_[b].lcm == P_[a].lcm) { gens.push_back(P_[b].i); gens.push_back(P_[b].j); ++b; }
+        std::sort(gens.begin(), gens.end());
+        gens.erase(std::unique(gens.begin(), gens.end()), gens.end());
+        size_t best = 0;
+        for (size_t k = 1; k < gens.size(); ++k) {
+            const Poly& x = G_[gens[k]]; const Poly& y = G_[gens[best]];
+            if (x.mon.size() < y.mon.size() || (x.mon.size() == y.mon.size() && x.deg < y.deg)) best = k;
+        }
+        std::swap(gens[0], gens[best]);
+        const uint16_t* el = bt_.e(P_[a].lcm);
+        for (size_t k = 0; k < gens.size(); ++k) {
+            const uint16_t* lm = bt_.e(G_[gens[k]].mon[0]);
+            for (int i = 0; i < st; ++i) q[i] = (uint16_t)(el[i] - lm[i]);
+            add_row(gens[k], q.data(), cx_.hash(q.data()), k == 0);
+        }
+        a = b;
+    }
+    P_.erase(P_.begin(), P_.begin() + n_sel);
+    stats.t_rows += now_s() - t0;
+}
+
+std::vector<uint32_t> F4::nonredundant() const {
+    std::vector<uint32_t> v;
+    for (uint32_t i = 0; i < G_.size(); ++i) if (!G_[i].redundant) v.push_back(i);
+    return v;
+}
+
+// For every monomial of the step without a reducer, pick the first generator
+// (shortest first) whose lead divides it and add the multiplied row as a pivot
+// row (source/matrix.hpp:469-600).
+void F4::symbolic() {
+    double t0 = now_s();
+    const int st = cx_.stride, nv = cx_.nv;
+    std::vector<uint32_t> cand = nonredundant();
+    std::stable_sort(cand.begin(), cand.end(), [&](uint32_t a, uint32_t b) {
+        if (G_[a].mon.size() != G_[b].mon.size()) return G_[a].mon.size() < G_[b].mon.size();
+        return G_[a].deg < G_[b].deg;
+    });
+    const size_t nc = cand.size();
+    std::vector<uint64_t> cmask(nc);
+    std::vector<uint16_t> cexp(nc * nv);
+    for (size_t c = 0; c < nc; ++c) {
+        cmask[c] = G_[cand[c]].lm_mask;
+        std::memcpy(&cexp[c * nv], bt_.e(G_[cand[c]].mon[0]) + 2, nv * sizeof(uint16_t));
+    }
+    std::vector<uint16_t> q(st), em(st);
+    for (uint32_t m = 0; m < st_.size(); ++m) {
+        if (m < has_red_.size() && has_red_[m]) continue;
+        std::memcpy(em.data(), st_.e(m), st * sizeof(uint16_t));
+        const uint64_t nm = ~cx_.divmask(em.data());
+        size_t hit = nc;
+        for (size_t c = 0; c < nc; ++c) {
+            if (cmask[c] & nm) continue;
+            const uint16_t* le = &cexp[c * nv];
+            bool ok = true;
+            for (int v = 0; v < nv; ++v) if (le[v] > em[2 + v]) { ok = false; break; }
+            if (ok) { hit = c; break; }
+        }
+        if (hit == nc) continue;
+        const uint16_t* lm = bt_.e(G_[cand[hit]].mon[0]);
+        for (int i = 0; i < st; ++i) q[i] = (uint16_t)(em[i] - lm[i]);
+        add_row(cand[hit], q.data(), cx_.hash(q.data()), true);
+    }
+    if (has_red_.size() < st_.size()) has_red_.resize(st_.size(), 0);
+    stats.t_symbolic += now_s() - t0;
+}
+
+// Columns = monomials in decreasing order; then block form (engine.hpp):
+// pivot columns first, pivot row i leads at column i, rows to reduce sorted by
+// decreasing lead (source/matrix.hpp:603-673 + the A|B / C|D split of SURVEY §8(b)).
+void F4::convert() {
+    double t0 = now_s();
+    const uint32_t nc = (uint32_t)st_.size();
+    order_.resize(nc);
+    std::iota(order_.begin(), order_.end(), 0u);
+    std::sort(order_.begin(), order_.end(), [&](uint32_t a, uint32_t b) {
+        return cx_.cmp(st_.e(a), st_.e(b)) > 0;
+    });
+    std::vector<uint32_t> colof(nc);
+    for (uint32_t c = 0; c < nc; ++c) colof[order_[c]] = c;
+
+    const size_t nrows = row_gen_.size();
+    std::vector<uint32_t> top, bot;
+    for (uint32_t r = 0; r < nrows; ++r) (row_top_[r] ? top : bot).push_back(r);
+    auto lead = [&](uint32_t r) { return colof[row_mon_[row_off_[r]]]; };
+    std::sort(top.begin(), top.end(), [&](uint32_t a, uint32_t b) { return lead(a) < lead(b); });
+    std::stable_sort(bot.begin(), bot.end(), [&](uint32_t a, uint32_t b) { return lead(a) > lead(b); });
+
+    std::vector<uint8_t> is_piv(nc, 0);
+    for (uint32_t r : top) {
+        if (is_piv[lead(r)]) throw std::logic_error("two pivot rows share a lead column");
+        is_piv[lead(r)] = 1;
+    }
+    std::vector<uint32_t> newcol(nc);
+    nonpiv_col_.clear();
+    uint32_t np = 0, nn = 0;
+    const uint32_t ntop = (uint32_t)top.size();
+    for (uint32_t c = 0; c < nc; ++c) {
+        if (is_piv[c]) newcol[c] = np++;
+        else { newcol[c] = ntop + nn++; nonpiv_col_.push_back(c); }
+    }
+    // handle -> block-form column in one table
+    std::vector<uint32_t> h2c(nc);
+    for (uint32_t h = 0; h < nc; ++h) h2c[h] = newcol[colof[h]];
+
+    M_.p = p_; M_.n_top = ntop; M_.n_bot = (uint32_t)bot.size(); M_.n_cols = nc;
+    M_.row_ptr.assign(1, 0); M_.row_ptr.reserve(nrows + 1);
+    M_.col.resize(row_mon_.size());
+    M_.coeff_id.clear(); M_.cf_ptr.clear(); M_.cf_len.clear();
+    static std::vector<int32_t> gmap;
+    gmap.assign(G_.size(), -1);
+    uint64_t w = 0;
+    auto emit = [&](uint32_t r) {
+        for (uint64_t k = row_off_[r]; k < row_off_[r + 1]; ++k) M_.col[w++] = h2c[row_mon_[k]];
+        M_.row_ptr.push_back(w);
+        uint32_t g = row_gen_[r];
+        if (gmap[g] < 0) {
+            gmap[g] = (int32_t)M_.cf_ptr.size();
+            M_.cf_ptr.push_back(G_[g].cf.data());
+            M_.cf_len.push_back((uint32_t)G_[g].cf.size());
+        }
+        M_.coeff_id.push_back((uint32_t)gmap[g]);
+    };
+    for (uint32_t r : top) emit(r);
+    for (uint32_t r : bot) emit(r);
+    stats.t_convert += now_s() - t0;
+    stats.max_rows = std::max<uint64_t>(stats.max_rows, nrows);
+    stats.max_cols = std::max<uint64_t>(stats.max_cols, nc);
+    stats.max_nnz = std::max<uint64_t>(stats.max_nnz, w);
+}
+
+void F4::dump_step(const char* tag) {
+    if (prm_.dump_dir.empty() || (long)M_.nnz() < prm_.dump_min_nnz) return;
+    char name[64];
+    std::snprintf(name, sizeof name, "/step_%s.bin", tag);
+    write_step_file(prm_.dump_dir + name, M_);
+    std::snprintf(name, sizeof name, "/rows_%s.bin", tag);
+    write_rows_file(prm_.dump_dir + name, R_);
+}
+
+// New pivot rows -> basis elements (source/matrix.hpp:799-895 +
+// source/basis.hpp:697-769): relative non-pivot index -> column -> monomial.
+void F4::insert_new_rows() {
+    double t0 = now_s();
+    for (uint32_t r = 0; r < R_.n_new; ++r) {
+        Poly f;
+        uint64_t a = R_.row_ptr[r], b = R_.row_ptr[r + 1];
+        f.mon.resize(b - a); f.cf.assign(R_.val.begin() + a, R_.val.begin() + b);
+        for (uint64_t k = a; k < b; ++k) {
+            uint32_t h = order_[nonpiv_col_[R_.col[k]]];
+            f.mon[k - a] = bt_.insert(st_.e(h), st_.hv[h]);
+            f.deg = std::max<uint32_t>(f.deg, st_.e(h)[0]);
+        }
+        if (f.cf[0] != 1) throw std::logic_error("engine returned a non-monic row");
+        f.lm_mask = cx_.divmask(bt_.e(f.mon[0]));
+        if (bt_.e(f.mon[0])[0] == 0) { make_trivial(); break; }
+        G_.push_back(std::move(f));
+    }
+    stats.t_insert += now_s() - t0;
+}
+
+void F4::final_reduce() {
+    double t0 = now_s();
+    clear_step();
+    std::vector<uint32_t> nr = nonredundant();
+    std::vector<uint16_t> one(cx_.stride, 0);
+    for (uint32_t g : nr) {
+        add_row(g, one.data(), 0, false);
+        has_red_[row_mon_[row_off_[row_gen_.size() - 1]]] = 1;  // leads need no reducer
+    }
+    symbolic();
+    convert();
+    double t1 = now_s();
+    eng_.reduce_final(M_, R_);
+    stats.t_final_linalg += now_s() - t1;
+    dump_step("final");
+    if (R_.n_new != M_.n_bot) throw std::logic_error("final reduction lost a basis element");
+    std::vector<Poly> out;
+    for (uint32_t r = 0; r < R_.n_new; ++r) {
+        Poly f;
+        uint64_t a = R_.row_ptr[r], b = R_.row_ptr[r + 1];
+        f.mon.resize(b - a); f.cf.assign(R_.val.begin() + a, R_.val.begin() + b);
+        for (uint64_t k = a; k < b; ++k) {
+            uint32_t h = order_[nonpiv_col_[R_.col[k]]];
+            f.mon[k - a] = bt_.insert(st_.e(h), st_.hv[h]);
+        }
+        f.lm_mask = cx_.divmask(bt_.e(f.mon[0]));
+        out.push_back(std::move(f));
+    }
+    G_ = std::move(out);
+    stats.t_final += now_s() - t0;
+}
+
+void F4::run() {
+    double t_start = now_s();
+    const bool rounds = prm_.verbose > 1;
+    if (trivial_) make_trivial();
+    if (!trivial_) update_all(0);
+    if (rounds)
+        std::printf("%4s %4s %14s %22s %8s %9s %10s %10s\n", "step", "deg", "pairs/queue",
+                    "matrix (rows x cols)", "dens %", "new rows", "linalg s", "step s");
+    while (!P_.empty() && !trivial_) {
+        double ts = now_s();
+        size_t prev = G_.size();
+        int32_t deg; size_t queue = P_.size();
+        long nsel = select_pairs(deg);
+        clear_step();
+        build_pair_rows(nsel);
+        symbolic();
+        stats.rows_reduced += std::count(row_top_.begin(), row_top_.end(), 0);
+        convert();
+        double t1 = now_s();
+        eng_.reduce_step(M_, R_);
+        double tl = now_s() - t1;
+        stats.t_linalg += tl; stats.t_linalg_kernel += R_.kernel_seconds;
+        stats.nnz_in += M_.nnz(); stats.fma_top += R_.fma_top;
+        stats.zero_reductions += M_.n_bot - R_.n_new;
+        ++stats.steps;
+        char tag[32]; std::snprintf(tag, sizeof tag, "%04llu", (unsigned long long)stats.steps);
+        dump_step(tag);
+        insert_new_rows();
+        if (!trivial_) update_all(prev);
+        if (rounds) {
+            double dens = 100.0 * (double)M_.nnz() / ((double)M_.n_rows() * (double)M_.n_cols);
+            std::printf("%4llu %4d %7ld/%-6zu %10u x %-9u %8.2f %9u %10.3f %10.3f\n",
+                        (unsigned long long)stats.steps, deg, nsel, queue, M_.n_rows(), M_.n_cols, dens,
+                        R_.n_new, tl, now_s() - ts);
+            std::fflush(stdout);
+        }
+    }
+    // keep only generators whose lead is minimal (source/basis.hpp:822-882)
+    if (!trivial_) {
+        std::vector<uint32_t> nr = nonredundant();
+        for (uint32_t i : nr)
+            for (uint32_t j : nr) {
+                if (i == j || G_[j].redundant) continue;
+                if (G_[j].lm_mask & ~G_[i].lm_mask) continue;
+                if (G_[i].mon[0] != G_[j].mon[0] && cx_.divides(bt_.e(G_[j].mon[0]), bt_.e(G_[i].mon[0]))) {
+                    G_[i].redundant = true; break;
+                }
+            }
+        if (!prm_.no_reduce) final_reduce();
+        else {
+            std::vector<Poly> out;
+            for (uint32_t i : nonredundant()) out.push_back(std::move(G_[i]));
+            G_ = std::move(out);
+        }
+    }
+    stats.t_total = now_s() - t_start;
+}
+
+// Generators in increasing order of leading monomial (source/basis.hpp:923-972).
+void F4::export_basis(PolySystem& out) const {
+    out.vars = in_.vars; out.p = p_;
+    out.lens.clear(); out.coeffs.clear(); out.exps.clear();
+    std::vector<uint32_t> idx(G_.size());
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        return cx_.cmp(bt_.e(G_[a].mon[0]), bt_.e(G_[b].mon[0])) < 0;
+    });
+    for (uint32_t i : idx) {
+        const Poly& f = G_[i];
+        out.lens.push_back((uint32_t)f.mon.size());
+        for (size_t k = 0; k < f.mon.size(); ++k) {
+            out.coeffs.push_back(f.cf[k]);
+            const uint16_t* e = bt_.e(f.mon[k]);
+            out.exps.insert(out.exps.end(), e + 2, e + 2 + cx_.nv);
+        }
+    }
+}
+
+}  // namespace gb
