@@ -1,0 +1,470 @@
+// Host side of the B200 engine and the C ABI of include/gamba_cuda.h.
+//
+// Role of the reference's closed linalg_v3<Coeff,Order> / linalg<Matrix> classes
+// (call sites source/f4.hpp:63-100, source/reduce.hpp:51-52): stage one step matrix
+// in HBM, eliminate C|D by A|B, echelonise D', hand the new rows back.
+// There is no CPU fallback in this file: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gamba_cuda.h"
+#include "field.cuh"
+#include "kernels_echelon.cuh"
+#include "kernels_elim.cuh"
+#include "kernels_prep.cuh"
+#include "layout.cuh"
+
+namespace gcu {
+
+#define GCU_CHECK(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t err__ = (expr);                                                             \
+        if (err__ != cudaSuccess)                                                               \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(err__));    \
+    } while (0)
+
+static thread_local std::string g_last_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) GCU_CHECK(cudaFree(p));
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        GCU_CHECK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) GCU_CHECK(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        GCU_CHECK(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    ~HostBuf() { if (p) cudaFreeHost(p); }
+};
+
+static double wall_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace gcu
+
+struct gamba_cuda_engine {
+    gamba_cuda_config cfg{};
+    gcu::Fp f{};
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6]{};
+    int max_smem_optin = 0;
+    int64_t opt_tile_cols = 0;
+    int64_t opt_ctas_per_sm = 0;
+
+    // staged step
+    bool staged = false;
+    gcu::Layout L{};
+    uint32_t flags = 0;
+    uint64_t nnz = 0;
+    gcu::DevBuf d_row_ptr, d_col, d_coeff_id, d_coeff_off, d_pool;
+    gcu::DevBuf d_seg, d_ent, d_diag, d_first, d_scan_tmp;
+    gcu::HostBuf h_pool, h_off;
+    uint64_t h2d_bytes = 0;
+    double t_stage_wall = 0, t_prep_dev = 0;
+
+    // elimination / echelon state
+    gcu::DevBuf d_dprime, d_row_nz, d_list_k, d_list_m, d_queue_stats;
+    gcu::DevBuf d_lead, d_nz_list, d_piv_row, d_piv_col, d_is_piv, d_counts, d_out_ptr, d_out_col, d_out_val;
+    uint32_t n_local = 0, n_local_max = 0, n_gather_rows = 0;
+    bool eliminated = false;
+    int elim_grid = 0;
+
+    // results (host, engine-owned)
+    std::vector<uint64_t> r_row_ptr;
+    std::vector<uint32_t> r_col, r_piv, r_val32;
+    std::vector<uint16_t> r_val16;
+    std::vector<uint8_t> r_val8;
+    gcu::HostBuf h_out_ptr, h_out_col, h_out_val, h_misc;
+
+    gamba_cuda_allgather_fn gather_fn = nullptr;
+    void* gather_user = nullptr;
+
+    gamba_cuda_counters ctr{};
+    double t_elim_dev = 0, t_ech_dev = 0;
+
+    ~gamba_cuda_engine() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    void choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols);
+    void stage(const gamba_cuda_step_in* in);
+    void eliminate();
+    void exchange();
+    void echelon(gamba_cuda_step_out* out);
+};
+
+using namespace gcu;
+
+void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols) {
+    L = Layout{};
+    L.n_top = n_top; L.n_bot = n_bot; L.n_cols = n_cols; L.n_nonpiv = n_cols - n_top;
+    const uint32_t gran = BUCKET_COLS * ELIM_WARPS;  // 128, also a multiple of WINDOW
+    cudaFuncAttributes fa{};
+    GCU_CHECK(cudaFuncGetAttributes(&fa, elim_kernel<false>));
+    const size_t avail = (size_t)max_smem_optin - fa.sharedSizeBytes - 64;
+    uint32_t tmax = (uint32_t)(avail / sizeof(uint64_t)) / gran * gran;
+    if (opt_tile_cols > 0) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
+    auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
+    // pivot tiles of equal width; the non-pivot range is cut with the same width
+    uint32_t ntp = n_top ? (n_top + tmax - 1) / tmax : 0;
+    uint32_t t = ntp ? up((n_top + ntp - 1) / ntp) : gran;
+    if (L.n_nonpiv > t) {
+        uint32_t ntn = (L.n_nonpiv + tmax - 1) / tmax;
+        t = std::max(t, up((L.n_nonpiv + ntn - 1) / ntn));
+    }
+    t = std::min(t, tmax);
+    L.tile_cols = t;
+    L.n_tiles_piv = (n_top + t - 1) / t;
+    L.n_tiles_nonpiv = (L.n_nonpiv + t - 1) / t;
+    L.n_tiles = L.n_tiles_piv + L.n_tiles_nonpiv;
+    L.n_bins = std::max(1u, L.n_tiles * ELIM_WARPS);
+    L.n_windows = (n_top + WINDOW - 1) / WINDOW;
+    ctr.tile_cols = t; ctr.n_tiles = L.n_tiles; ctr.acc_bits = 64;
+}
+
+void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
+    const double t0 = wall_s();
+    staged = false; eliminated = false;
+    if (in->n_cols < in->n_top) throw std::runtime_error("n_cols < n_top");
+    const uint32_t n_rows = in->n_top + in->n_bot;
+    if (in->row_ptr[n_rows] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
+    if (in->nnz >= (1ull << 32)) throw std::runtime_error("step has >= 2^32 non-zeros");
+    choose_layout(in->n_top, in->n_bot, in->n_cols);
+    flags = in->flags; nnz = in->nnz;
+    if ((uint64_t)n_rows * L.n_bins + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
+    if ((uint64_t)8 * L.n_bins * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
+
+    // shared coefficient arrays -> one u32 pool
+    const uint32_t na = in->n_coeff_arrays;
+    h_off.ensure((na + 1) * sizeof(uint64_t));
+    uint64_t* off = h_off.as<uint64_t>();
+    uint64_t tot = 0;
+    for (uint32_t i = 0; i < na; ++i) { off[i] = tot; tot += in->coeff_len[i]; }
+    off[na] = tot;
+    h_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
+    uint32_t* pool = h_pool.as<uint32_t>();
+    for (uint32_t i = 0; i < na; ++i) {
+        const uint32_t n = in->coeff_len[i];
+        uint32_t* dst = pool + off[i];
+        switch (cfg.coeff_bytes) {
+            case 4: std::memcpy(dst, in->coeff_ptr[i], (size_t)n * 4); break;
+            case 2: { const uint16_t* s = (const uint16_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
+            default: { const uint8_t* s = (const uint8_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
+        }
+    }
+
+    d_row_ptr.ensure((n_rows + 1) * sizeof(uint64_t));
+    d_col.ensure(std::max<uint64_t>(nnz, 1) * sizeof(uint32_t));
+    d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
+    d_coeff_off.ensure((na + 1) * sizeof(uint64_t));
+    d_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
+    GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaMemcpyAsync(d_pool.p, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    h2d_bytes = (n_rows + 1) * 8ull + nnz * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull;
+
+    const uint64_t n_seg = (uint64_t)n_rows * L.n_bins + 1;
+    d_seg.ensure(n_seg * sizeof(uint32_t));
+    d_ent.ensure(std::max<uint64_t>(nnz, 1) * sizeof(uint2));
+    d_diag.ensure(std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1) * sizeof(uint32_t));
+    d_first.ensure(std::max<uint32_t>(L.n_bot, 1) * sizeof(uint32_t));
+    GCU_CHECK(cudaEventRecord(ev[0], stream));
+    GCU_CHECK(cudaMemsetAsync(d_seg.p, 0, n_seg * sizeof(uint32_t), stream));
+    GCU_CHECK(cudaMemsetAsync(d_diag.p, 0, (uint64_t)L.n_windows * WINDOW * WINDOW * sizeof(uint32_t), stream));
+
+    PrepArgs pa{};
+    pa.L = L; pa.f = f;
+    pa.row_ptr = d_row_ptr.as<uint64_t>(); pa.col = d_col.as<uint32_t>(); pa.coeff_id = d_coeff_id.as<uint32_t>();
+    pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
+    pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>(); pa.diag = d_diag.as<uint32_t>();
+    pa.first_piv = d_first.as<uint32_t>();
+    if (n_rows) {
+        const size_t sh = (size_t)8 * L.n_bins * sizeof(uint32_t);
+        if (sh > 48 * 1024) {
+            GCU_CHECK(cudaFuncSetAttribute(prep_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+            GCU_CHECK(cudaFuncSetAttribute(prep_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        }
+        const uint32_t nblk = (n_rows + 7) / 8;
+        prep_count_kernel<<<nblk, 256, sh, stream>>>(pa);
+        GCU_CHECK(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pa.seg, pa.seg, (int64_t)n_seg, stream));
+        d_scan_tmp.ensure(tmp_bytes);
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, pa.seg, pa.seg, (int64_t)n_seg, stream));
+        prep_fill_kernel<<<nblk, 256, sh, stream>>>(pa);
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 3;
+    }
+    GCU_CHECK(cudaEventRecord(ev[1], stream));
+    GCU_CHECK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    GCU_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    t_prep_dev = ms * 1e-3;
+    t_stage_wall = wall_s() - t0;
+    staged = true;
+}
+
+void gamba_cuda_engine::eliminate() {
+    if (!staged) throw std::runtime_error("no staged step");
+    const uint32_t world = std::max(1u, cfg.world_size), rank = cfg.rank;
+    n_local_max = (L.n_bot + world - 1) / world;
+    n_local = L.n_bot > rank ? (L.n_bot - rank + world - 1) / world : 0;
+    n_gather_rows = world > 1 ? n_local_max * world : L.n_bot;
+
+    const size_t smem = (size_t)L.tile_cols * sizeof(uint64_t);
+    auto kern = f.small ? elim_kernel<true> : elim_kernel<false>;
+    GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ELIM_THREADS, smem));
+    if (occ < 1) throw std::runtime_error("elimination kernel does not fit on an SM");
+    if (opt_ctas_per_sm > 0) occ = std::min<int>(occ, (int)opt_ctas_per_sm);
+    elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
+
+    d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.n_nonpiv, 1) * sizeof(uint32_t));
+    d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
+    d_list_k.ensure(std::max<uint64_t>((uint64_t)elim_grid * L.n_top, 1) * sizeof(uint32_t));
+    d_list_m.ensure(std::max<uint64_t>((uint64_t)elim_grid * L.n_top, 1) * sizeof(uint32_t));
+    d_queue_stats.ensure(64);
+    GCU_CHECK(cudaMemsetAsync(d_queue_stats.p, 0, 64, stream));
+    GCU_CHECK(cudaMemsetAsync(d_row_nz.p, 0, std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t), stream));
+
+    // local block of D' sits at its final place inside the gather buffer
+    uint32_t* dloc = d_dprime.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max * L.n_nonpiv : 0);
+    uint32_t* nzloc = d_row_nz.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max : 0);
+
+    ElimArgs ea{};
+    ea.L = L; ea.f = f;
+    ea.seg = d_seg.as<uint32_t>(); ea.ent = d_ent.as<uint2>(); ea.diag = d_diag.as<uint32_t>();
+    ea.first_piv = d_first.as<uint32_t>();
+    ea.dprime = dloc; ea.row_nz = nzloc;
+    ea.list_k = d_list_k.as<uint32_t>(); ea.list_m = d_list_m.as<uint32_t>();
+    ea.queue = d_queue_stats.as<uint32_t>();
+    ea.stats = reinterpret_cast<unsigned long long*>(d_queue_stats.as<char>() + 16);
+    ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
+    GCU_CHECK(cudaEventRecord(ev[2], stream));
+    if (n_local && L.n_nonpiv) {
+        kern<<<elim_grid, ELIM_THREADS, smem, stream>>>(ea);
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 1;
+    }
+    GCU_CHECK(cudaEventRecord(ev[3], stream));
+    eliminated = true;
+}
+
+void gamba_cuda_engine::exchange() {
+    if (cfg.world_size <= 1) return;
+    if (!gather_fn) throw std::runtime_error("world_size > 1 but no all-gather callback set");
+    const size_t bytes_d = (size_t)n_local_max * L.n_nonpiv * sizeof(uint32_t);
+    const size_t bytes_z = (size_t)n_local_max * sizeof(uint32_t);
+    const char* send_d = d_dprime.as<char>() + (size_t)cfg.rank * bytes_d;
+    const char* send_z = d_row_nz.as<char>() + (size_t)cfg.rank * bytes_z;
+    if (bytes_d && gather_fn(gather_user, send_d, d_dprime.p, bytes_d, stream)) throw std::runtime_error("all-gather of D' failed");
+    if (bytes_z && gather_fn(gather_user, send_z, d_row_nz.p, bytes_z, stream)) throw std::runtime_error("all-gather of row flags failed");
+}
+
+void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
+    if (!eliminated) throw std::runtime_error("eliminate() has not run");
+    const uint32_t nr = n_gather_rows, nc = L.n_nonpiv;
+    uint32_t npiv = 0;
+    uint64_t nnz_new = 0;
+    d_counts.ensure(64);
+    GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
+    GCU_CHECK(cudaEventRecord(ev[4], stream));
+    if (nr && nc) {
+        d_lead.ensure((size_t)2 * nr * sizeof(uint32_t));
+        d_nz_list.ensure((size_t)nr * sizeof(uint32_t));
+        d_piv_row.ensure((size_t)nr * sizeof(uint32_t));
+        d_piv_col.ensure((size_t)nr * sizeof(uint32_t));
+        d_is_piv.ensure(nc);
+        d_out_ptr.ensure((size_t)(nr + 1) * sizeof(uint64_t));
+        EchArgs ea{};
+        ea.f = f; ea.n_rows = nr; ea.n_cols = nc;
+        ea.d = d_dprime.as<uint32_t>(); ea.row_nz = d_row_nz.as<uint32_t>();
+        ea.lead = d_lead.as<uint32_t>(); ea.nz_list = d_nz_list.as<uint32_t>();
+        ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
+        ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
+        ea.out_ptr = d_out_ptr.as<uint64_t>();
+        int occ = 0;
+        GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, echelon_kernel, ECH_THREADS, 0));
+        if (occ < 1) throw std::runtime_error("echelon kernel does not fit on an SM");
+        const int grid = prop.multiProcessorCount * std::min(occ, 1);
+        void* args[] = {&ea};
+        GCU_CHECK(cudaLaunchCooperativeKernel((void*)echelon_kernel, dim3(grid), dim3(ECH_THREADS), args, 0, stream));
+        ctr.kernel_launches += 1;
+        h_misc.ensure(64);
+        GCU_CHECK(cudaMemcpyAsync(h_misc.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaStreamSynchronize(stream));
+        npiv = h_misc.as<uint32_t>()[1];
+        if (npiv) {
+            h_out_ptr.ensure((size_t)(npiv + 1) * sizeof(uint64_t));
+            GCU_CHECK(cudaMemcpyAsync(h_out_ptr.p, d_out_ptr.p, (size_t)(npiv + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+            GCU_CHECK(cudaStreamSynchronize(stream));
+            nnz_new = h_out_ptr.as<uint64_t>()[npiv];
+            d_out_col.ensure(nnz_new * sizeof(uint32_t));
+            d_out_val.ensure(nnz_new * sizeof(uint32_t));
+            EmitArgs em{};
+            em.f = f; em.n_cols = nc; em.n_piv = npiv; em.d = d_dprime.as<uint32_t>();
+            em.piv_row = d_piv_row.as<uint32_t>(); em.piv_col = d_piv_col.as<uint32_t>();
+            em.is_piv_col = d_is_piv.as<uint8_t>(); em.out_ptr = d_out_ptr.as<uint64_t>();
+            em.out_col = d_out_col.as<uint32_t>(); em.out_val = d_out_val.as<uint32_t>();
+            emit_kernel<<<npiv, 256, 0, stream>>>(em);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 1;
+        }
+    }
+    GCU_CHECK(cudaEventRecord(ev[5], stream));
+
+    r_row_ptr.assign(npiv + 1, 0);
+    r_col.resize(nnz_new); r_val32.resize(nnz_new); r_piv.resize(npiv);
+    if (npiv) {
+        std::memcpy(r_row_ptr.data(), h_out_ptr.p, (size_t)(npiv + 1) * sizeof(uint64_t));
+        GCU_CHECK(cudaMemcpyAsync(r_col.data(), d_out_col.p, nnz_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaMemcpyAsync(r_val32.data(), d_out_val.p, nnz_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaMemcpyAsync(r_piv.data(), d_piv_col.p, (size_t)npiv * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    }
+    h_misc.ensure(64);
+    GCU_CHECK(cudaMemcpyAsync(h_misc.as<char>() + 16, d_queue_stats.as<char>() + 16, 16, cudaMemcpyDeviceToHost, stream));
+    GCU_CHECK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    GCU_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_elim_dev = ms * 1e-3;
+    GCU_CHECK(cudaEventElapsedTime(&ms, ev[4], ev[5])); t_ech_dev = ms * 1e-3;
+    ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
+    ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
+    ctr.steps += 1;
+
+    if ((flags & GAMBA_CUDA_STEP_FINAL) && npiv != L.n_bot)
+        throw std::runtime_error("final inter-reduction: rank of D' differs from the number of rows");
+
+    out->n_new = npiv; out->n_nonpiv = nc; out->nnz_new = nnz_new;
+    out->row_ptr = r_row_ptr.data(); out->col_rel = r_col.data(); out->piv_rel = r_piv.data();
+    switch (cfg.coeff_bytes) {
+        case 4: out->coeff = r_val32.data(); break;
+        case 2: r_val16.resize(nnz_new); for (uint64_t i = 0; i < nnz_new; ++i) r_val16[i] = (uint16_t)r_val32[i]; out->coeff = r_val16.data(); break;
+        default: r_val8.resize(nnz_new); for (uint64_t i = 0; i < nnz_new; ++i) r_val8[i] = (uint8_t)r_val32[i]; out->coeff = r_val8.data(); break;
+    }
+    out->zero_reductions = L.n_bot - std::min(L.n_bot, npiv);
+    out->seconds_eliminate = t_elim_dev; out->seconds_echelon = t_ech_dev;
+    out->seconds_device = t_prep_dev + t_elim_dev + t_ech_dev;
+    out->h2d_bytes = h2d_bytes;
+    out->d2h_bytes = (npiv + 1) * 8ull + nnz_new * 8ull + npiv * 4ull + 24;
+}
+
+// ------------------------------------------------------------------ C ABI -----
+
+template <class F>
+static int guarded(F&& fn) {
+    try { fn(); return 0; }
+    catch (std::exception const& e) { gcu::g_last_error = e.what(); return 1; }
+    catch (...) { gcu::g_last_error = "unknown error"; return 2; }
+}
+
+extern "C" {
+
+int gamba_cuda_abi_version(void) { return GAMBA_CUDA_ABI_VERSION; }
+const char* gamba_cuda_last_error(void) { return gcu::g_last_error.c_str(); }
+
+int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
+    return guarded([&] {
+        if (!cfg || !out) throw std::runtime_error("null argument");
+        if (cfg->p < 3 || cfg->p > 0x7fffffffu || (cfg->p & 1) == 0) throw std::runtime_error("p must be an odd prime < 2^31");
+        if (cfg->coeff_bytes != 1 && cfg->coeff_bytes != 2 && cfg->coeff_bytes != 4) throw std::runtime_error("coeff_bytes must be 1, 2 or 4");
+        if (cfg->coeff_bytes < 4 && cfg->p >= (1ull << (8 * cfg->coeff_bytes))) throw std::runtime_error("p does not fit coeff_bytes");
+        int ndev = 0;
+        GCU_CHECK(cudaGetDeviceCount(&ndev));
+        if (ndev <= 0 || (int)cfg->device >= ndev) throw std::runtime_error("no such CUDA device");
+        GCU_CHECK(cudaSetDevice((int)cfg->device));
+        auto* e = new gamba_cuda_engine();
+        try {
+            e->cfg = *cfg;
+            if (e->cfg.world_size == 0) e->cfg.world_size = 1;
+            const uint32_t mont = cfg->repr == GAMBA_CUDA_REPR_MONTGOMERY ? (cfg->coeff_bytes == 4 ? 64u : 32u) : 0u;
+            e->f = gcu::fp_make(cfg->p, mont);
+            GCU_CHECK(cudaGetDeviceProperties(&e->prop, (int)cfg->device));
+            if (e->prop.major < 10) throw std::runtime_error("this library is built for sm_100a (B200) only");
+            GCU_CHECK(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)cfg->device));
+            GCU_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+            for (auto& ev : e->ev) GCU_CHECK(cudaEventCreate(&ev));
+            e->ctr.sm_count = (uint32_t)e->prop.multiProcessorCount;
+        } catch (...) { delete e; throw; }
+        *out = e;
+    });
+}
+
+void gamba_cuda_destroy(gamba_cuda_engine* e) { delete e; }
+
+int gamba_cuda_stage(gamba_cuda_engine* e, const gamba_cuda_step_in* in) {
+    return guarded([&] { GCU_CHECK(cudaSetDevice((int)e->cfg.device)); e->stage(in); });
+}
+
+int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out) {
+    return guarded([&] {
+        GCU_CHECK(cudaSetDevice((int)e->cfg.device));
+        const double t0 = gcu::wall_s();
+        e->eliminate();
+        e->exchange();
+        e->echelon(out);
+        out->seconds_total = gcu::wall_s() - t0;
+    });
+}
+
+int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_cuda_step_out* out) {
+    return guarded([&] {
+        GCU_CHECK(cudaSetDevice((int)e->cfg.device));
+        const double t0 = gcu::wall_s();
+        e->stage(in);
+        e->eliminate();
+        e->exchange();
+        e->echelon(out);
+        out->seconds_total = gcu::wall_s() - t0;
+    });
+}
+
+int gamba_cuda_set_allgather(gamba_cuda_engine* e, gamba_cuda_allgather_fn fn, void* user) {
+    return guarded([&] { e->gather_fn = fn; e->gather_user = user; });
+}
+
+int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c) {
+    return guarded([&] { *c = e->ctr; });
+}
+
+int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) {
+    return guarded([&] {
+        const std::string k = key ? key : "";
+        if (k == "tile_cols") e->opt_tile_cols = value;
+        else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
+        else throw std::runtime_error("unknown option " + k);
+    });
+}
+
+}  // extern "C"

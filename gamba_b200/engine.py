@@ -1,0 +1,109 @@
+"""Python mirror of the reference's engine interface on top of the C ABI.
+
+`LinalgEngine(p, seed)` plays `linalg_v3<Coeff,Order>(field, seed)` (source/f4.hpp:66);
+`reduce(step)` plays `initialize(matrix)` + `reduce(params)` (source/f4.hpp:91-93) and returns the
+new rows that `matrix_f4::extract_new_rows` (source/matrix.hpp:799-895) would read;
+`reduce_final(step)` plays `linalg<Matrix>::reduce` (source/reduce.hpp:51-52).
+Everything runs in libgamba_cuda.so on the GPU; errors raise RuntimeError like the
+reference's std::exception path (source/main.cpp:149-160)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .stepfile import Rows, Step
+
+
+class LinalgEngine:
+    def __init__(self, p: int, seed: int = 967557673, device: int = 0, coeff_bytes: int = 4,
+                 repr: int = _lib.REPR_STANDARD, rank: int = 0, world_size: int = 1):
+        self.lib = _lib.load()
+        self.p, self.coeff_bytes = p, coeff_bytes
+        cfg = _lib.Config(p, coeff_bytes, repr, device, seed, rank, world_size)
+        h = C.c_void_p()
+        if self.lib.gamba_cuda_create(C.byref(cfg), C.byref(h)):
+            raise RuntimeError("gamba_cuda_create: " + self.lib.gamba_cuda_last_error().decode())
+        self.h = h
+        self._keep = None
+        self._cb = None
+        self.last = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gamba_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    # -- helpers -----------------------------------------------------------------
+    def _step_in(self, s: Step, flags: int) -> _lib.StepIn:
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.coeff_bytes]
+        pool = np.ascontiguousarray(s.pool.astype(dt, copy=False))
+        off = s.coeff_offsets()
+        ptrs = (pool.ctypes.data + off[:-1] * self.coeff_bytes).astype(np.uint64)
+        row_ptr = np.ascontiguousarray(s.row_ptr, dtype=np.uint64)
+        col = np.ascontiguousarray(s.col, dtype=np.uint32)
+        cid = np.ascontiguousarray(s.coeff_id, dtype=np.uint32)
+        clen = np.ascontiguousarray(s.coeff_len, dtype=np.uint32)
+        self._keep = (pool, ptrs, row_ptr, col, cid, clen)
+        return _lib.StepIn(s.n_top, s.n_bot, s.n_cols, len(clen), s.nnz, row_ptr.ctypes.data, col.ctypes.data,
+                           cid.ctypes.data, ptrs.ctypes.data, clen.ctypes.data, flags)
+
+    def _rows(self, out: _lib.StepOut) -> Rows:
+        n, nnz = out.n_new, out.nnz_new
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.coeff_bytes]
+
+        def arr(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype=dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (count,)).copy()
+        self.last = {k: getattr(out, k) for k, _ in _lib.StepOut._fields_ if not k.endswith(("ptr", "rel", "coeff"))}
+        return Rows(n, arr(out.row_ptr, n + 1, np.uint64), arr(out.col_rel, nnz, np.uint32),
+                    arr(out.coeff, nnz, dt).astype(np.uint32))
+
+    def _check(self, rc: int, what: str):
+        if rc:
+            raise RuntimeError(f"{what}: " + self.lib.gamba_cuda_last_error().decode())
+
+    # -- the reference-facing calls ------------------------------------------------
+    def reduce(self, s: Step, final: bool = False) -> Rows:
+        """Host buffers in, host buffers out (H2D + kernels + D2H)."""
+        sin, out = self._step_in(s, _lib.STEP_FINAL if final else 0), _lib.StepOut()
+        self._check(self.lib.gamba_cuda_reduce(self.h, C.byref(sin), C.byref(out)), "gamba_cuda_reduce")
+        return self._rows(out)
+
+    def reduce_final(self, s: Step) -> Rows:
+        return self.reduce(s, final=True)
+
+    def stage(self, s: Step, final: bool = False) -> None:
+        sin = self._step_in(s, _lib.STEP_FINAL if final else 0)
+        self._check(self.lib.gamba_cuda_stage(self.h, C.byref(sin)), "gamba_cuda_stage")
+
+    def reduce_staged(self) -> Rows:
+        out = _lib.StepOut()
+        self._check(self.lib.gamba_cuda_reduce_staged(self.h, C.byref(out)), "gamba_cuda_reduce_staged")
+        return self._rows(out)
+
+    def counters(self) -> dict:
+        c = _lib.Counters()
+        self._check(self.lib.gamba_cuda_get_counters(self.h, C.byref(c)), "gamba_cuda_get_counters")
+        return {k: getattr(c, k) for k, _ in _lib.Counters._fields_}
+
+    def set_option(self, key: str, value: int) -> None:
+        self._check(self.lib.gamba_cuda_set_option(self.h, key.encode(), int(value)), "gamba_cuda_set_option")
+
+    def set_allgather(self, fn) -> None:
+        """fn(send_ptr, recv_ptr, bytes_per_rank, stream_ptr) -> None; see parallel.py."""
+        def tramp(_user, send, recv, nbytes, stream):
+            try:
+                fn(send, recv, nbytes, stream)
+                return 0
+            except Exception:  # noqa: BLE001 - reported through the C status code
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._cb = _lib.ALLGATHER_FN(tramp)
+        self._check(self.lib.gamba_cuda_set_allgather(self.h, self._cb, None), "gamba_cuda_set_allgather")

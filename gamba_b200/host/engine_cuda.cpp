@@ -1,0 +1,49 @@
+// Adapter: the host driver's Engine interface on top of the C ABI
+// (include/gamba_cuda.h). This is the product path: it has no CPU fallback —
+// if the CUDA engine cannot be created the driver stops with the error.
+#include <stdexcept>
+#include <string>
+
+#include "../../include/gamba_cuda.h"
+#include "f4.hpp"
+
+namespace gb {
+
+class CudaEngine final : public Engine {
+public:
+    CudaEngine(const Params& prm, uint32_t p) {
+        gamba_cuda_config cfg{};
+        cfg.p = p; cfg.coeff_bytes = 4; cfg.repr = GAMBA_CUDA_REPR_STANDARD;
+        cfg.device = 0; cfg.seed = prm.seed; cfg.rank = 0; cfg.world_size = 1;
+        if (gamba_cuda_create(&cfg, &e_)) throw std::runtime_error(std::string("gamba_cuda_create: ") + gamba_cuda_last_error());
+    }
+    ~CudaEngine() override { gamba_cuda_destroy(e_); }
+    const char* name() const override { return "cuda-b200"; }
+    void reduce_step(const StepMatrix& m, NewRows& out) override { run(m, out, 0); }
+    void reduce_final(const StepMatrix& m, NewRows& out) override { run(m, out, GAMBA_CUDA_STEP_FINAL); }
+
+private:
+    gamba_cuda_engine* e_ = nullptr;
+    std::vector<const void*> ptrs_;
+    void run(const StepMatrix& m, NewRows& out, uint32_t flags) {
+        gamba_cuda_step_in in{};
+        in.n_top = m.n_top; in.n_bot = m.n_bot; in.n_cols = m.n_cols;
+        in.n_coeff_arrays = (uint32_t)m.cf_ptr.size(); in.nnz = m.nnz();
+        in.row_ptr = m.row_ptr.data(); in.col_idx = m.col.data(); in.coeff_id = m.coeff_id.data();
+        ptrs_.assign(m.cf_ptr.begin(), m.cf_ptr.end());
+        in.coeff_ptr = ptrs_.data(); in.coeff_len = m.cf_len.data(); in.flags = flags;
+        gamba_cuda_step_out o{};
+        if (gamba_cuda_reduce(e_, &in, &o)) throw std::runtime_error(std::string("gamba_cuda_reduce: ") + gamba_cuda_last_error());
+        out = NewRows{};
+        out.n_new = o.n_new;
+        out.row_ptr.assign(o.row_ptr, o.row_ptr + o.n_new + 1);
+        out.col.assign(o.col_rel, o.col_rel + o.nnz_new);
+        const uint32_t* v = static_cast<const uint32_t*>(o.coeff);
+        out.val.assign(v, v + o.nnz_new);
+        out.seconds = o.seconds_total; out.kernel_seconds = o.seconds_device;
+    }
+};
+
+Engine* gb_make_engine(const Params& prm, uint32_t p) { return new CudaEngine(prm, p); }
+
+}  // namespace gb

@@ -1,0 +1,143 @@
+/*
+ * gamba_cuda.h — C ABI of the B200 linear-algebra engine for GamBa's F4.
+ *
+ * This is the drop-in boundary for the reference's two closed engine classes:
+ *
+ *   linalg_v3<Coeff,Order>(field, seed)     ctor      source/f4.hpp:66
+ *   linalg_v3::initialize(matrix_f4&)                 source/f4.hpp:91
+ *   linalg_v3::reduce(params) -> seconds              source/f4.hpp:93
+ *     (output members read by matrix_f4::extract_new_rows, source/matrix.hpp:799-895)
+ *   linalg<Matrix>(matrix) / ::reduce(matrix,params)  source/reduce.hpp:51-52
+ *
+ * The reference calls C++ templates, not a C ABI; the thin adapter that maps those
+ * class interfaces onto the functions below is shown in INTEGRATION.md. The
+ * north star fixes the name gamba_cuda_reduce; the other names are ours.
+ *
+ * One step matrix is handed over in Faugere-Lachartre block form:
+ *   rows 0 .. n_top-1            pivot rows A|B; row i is monic with its lead at column i
+ *   rows n_top .. n_top+n_bot-1  rows to reduce C|D, in the driver's order
+ *   columns 0 .. n_top-1         pivot columns, in ascending original (= decreasing monomial) order
+ *   columns n_top .. n_cols-1    non-pivot columns, original relative order kept
+ * A row's col_idx list is in the polynomial's term order (lead first), so entry k
+ * pairs with element k of the row's SHARED coefficient array coeff_ptr[coeff_id[row]];
+ * within a row the A-part (< n_top) and the B-part (>= n_top) are each strictly increasing.
+ *
+ * Number representation (create flag): GAMBA_CUDA_REPR_STANDARD = residues in [0,p);
+ * GAMBA_CUDA_REPR_MONTGOMERY = the reference's field_traits form (source/field.hpp:41-51):
+ * x*R mod p with R = 2^32 for 1- and 2-byte coefficients, R = 2^64 for 4-byte ones.
+ * Output uses the same representation and element width as the input.
+ *
+ * Result: the canonical reduced row echelon form of D' = D - C A^-1 B over the
+ * non-pivot columns: rows monic, fully inter-reduced, sorted by ascending pivot
+ * (= decreasing leading monomial, the order source/basis.hpp:725-727 relies on).
+ *
+ * Threading: one handle per host thread; calls on a handle are strictly sequential
+ * (the reference is single-threaded). All functions return 0 on
+ * success and a non-zero code otherwise; gamba_cuda_last_error() gives the message.
+ * There is no CPU fallback: without a usable CUDA device gamba_cuda_create fails.
+ */
+#ifndef GAMBA_CUDA_H
+#define GAMBA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAMBA_CUDA_ABI_VERSION 1
+
+#define GAMBA_CUDA_REPR_STANDARD   0u
+#define GAMBA_CUDA_REPR_MONTGOMERY 1u
+
+/* gamba_cuda_step_in.flags */
+#define GAMBA_CUDA_STEP_FINAL      1u  /* final inter-reduction (linalg<M>::reduce): result rows are
+                                          returned in the order of the bottom rows, columns absolute */
+
+typedef struct gamba_cuda_engine gamba_cuda_engine;
+
+typedef struct gamba_cuda_config {
+    uint32_t p;             /* field characteristic, odd prime < 2^31                          */
+    uint32_t coeff_bytes;   /* element width of coefficient arrays in and out: 1, 2 or 4       */
+    uint32_t repr;          /* GAMBA_CUDA_REPR_*                                                */
+    uint32_t device;        /* CUDA device ordinal                                              */
+    uint64_t seed;          /* seed of the Monte-Carlo combinations (params.seed, params.hpp:47) */
+    /* row-sharding of C|D across ranks (one process per GPU). With world_size > 1 the caller
+       provides the exchange callbacks below (the Python host wires them to torch.distributed /
+       NCCL); with world_size == 1 they are ignored. */
+    uint32_t rank, world_size;
+} gamba_cuda_config;
+
+typedef struct gamba_cuda_step_in {
+    uint32_t n_top, n_bot, n_cols, n_coeff_arrays;
+    uint64_t nnz;
+    const uint64_t* row_ptr;           /* [n_top + n_bot + 1]                                 */
+    const uint32_t* col_idx;           /* [nnz] block-form columns                            */
+    const uint32_t* coeff_id;          /* [n_top + n_bot] -> coefficient array of the row     */
+    const void* const* coeff_ptr;      /* [n_coeff_arrays], elements coeff_bytes wide         */
+    const uint32_t* coeff_len;         /* [n_coeff_arrays]                                    */
+    uint32_t flags;
+} gamba_cuda_step_in;
+
+typedef struct gamba_cuda_step_out {
+    uint32_t n_new;                    /* rank of D' (== n_bot for GAMBA_CUDA_STEP_FINAL)     */
+    uint32_t n_nonpiv;                 /* n_cols - n_top                                      */
+    uint64_t nnz_new;
+    /* engine-owned host buffers, valid until the next call on the handle */
+    const uint64_t* row_ptr;           /* [n_new + 1]                                         */
+    const uint32_t* col_rel;           /* [nnz_new] relative non-pivot columns, pivot first   */
+    const void* coeff;                 /* [nnz_new] coeff_bytes wide, pivot entry == one      */
+    const uint32_t* piv_rel;           /* [n_new] ascending                                   */
+    uint64_t zero_reductions;          /* rows of C|D that reduced to zero (stats.zero_reductions) */
+    double seconds_total;              /* wall time of the call: H2D + kernels + D2H (f4.hpp:93)   */
+    double seconds_device;             /* CUDA-event time of the kernels only                      */
+    double seconds_eliminate;          /* ... of the C|D-by-A|B elimination kernel                 */
+    double seconds_echelon;            /* ... of the D' echelon                                    */
+    uint64_t h2d_bytes, d2h_bytes;
+} gamba_cuda_step_out;
+
+int gamba_cuda_abi_version(void);
+const char* gamba_cuda_last_error(void);
+
+int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out);
+void gamba_cuda_destroy(gamba_cuda_engine* e);
+
+/* One F4 step (or the final inter-reduction): host buffers in, host buffers out. */
+int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_cuda_step_out* out);
+
+/* The same split in two, so a caller (and the benchmark) can keep a step resident in HBM:
+   gamba_cuda_stage copies the step to the device; gamba_cuda_reduce_staged runs the kernels on
+   the staged step (repeatable) and copies the result back. */
+int gamba_cuda_stage(gamba_cuda_engine* e, const gamba_cuda_step_in* in);
+int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out);
+
+/* Row-block sharding. With world_size > 1 every rank stages the same step,
+   eliminates only the rows r with r % world_size == rank, and the reduced rows are exchanged
+   through the caller-provided all-gather (NCCL over NVLink in the Python host; gloo on CPU tests).
+   gather(user, sendbuf_dev, recvbuf_dev, bytes_per_rank, stream) must behave like ncclAllGather
+   on device pointers enqueued on `stream` (a cudaStream_t). */
+typedef int (*gamba_cuda_allgather_fn)(void* user, const void* send_dev, void* recv_dev,
+                                       size_t bytes_per_rank, void* stream);
+int gamba_cuda_set_allgather(gamba_cuda_engine* e, gamba_cuda_allgather_fn fn, void* user);
+
+/* Introspection used by the benchmark and the tests. */
+typedef struct gamba_cuda_counters {
+    uint64_t kernel_launches;          /* kernels of this library launched since create         */
+    uint64_t steps;
+    uint32_t sm_count;
+    uint32_t tile_cols;                /* accumulator tile width used by the last step          */
+    uint32_t n_tiles;
+    uint32_t acc_bits;                 /* 32 or 64                                              */
+    uint64_t pivots_applied;           /* sum over rows of pivot rows applied in the last step  */
+    uint64_t fma_applied;              /* multiply-adds the elimination kernel did, last step   */
+} gamba_cuda_counters;
+int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
+
+/* Tuning knobs (0 = automatic). */
+int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMBA_CUDA_H */
