@@ -271,6 +271,7 @@ void gamba_cuda_engine::eliminate() {
     ea.list_k = d_list_k.as<uint32_t>(); ea.list_m = d_list_m.as<uint32_t>();
     ea.queue = d_queue_stats.as<uint32_t>();
     ea.stats = reinterpret_cast<unsigned long long*>(d_queue_stats.as<char>() + 16);
+    ea.row_ptr = d_row_ptr.as<uint64_t>();
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (n_local && L.n_nonpiv) {
@@ -354,13 +355,14 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         GCU_CHECK(cudaMemcpyAsync(r_piv.data(), d_piv_col.p, (size_t)npiv * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     }
     h_misc.ensure(64);
-    GCU_CHECK(cudaMemcpyAsync(h_misc.as<char>() + 16, d_queue_stats.as<char>() + 16, 16, cudaMemcpyDeviceToHost, stream));
+    GCU_CHECK(cudaMemcpyAsync(h_misc.as<char>() + 16, d_queue_stats.as<char>() + 16, 24, cudaMemcpyDeviceToHost, stream));
     GCU_CHECK(cudaStreamSynchronize(stream));
     float ms = 0;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_elim_dev = ms * 1e-3;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[4], ev[5])); t_ech_dev = ms * 1e-3;
     ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
     ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
+    ctr.fma_top = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[2];
     ctr.steps += 1;
 
     if ((flags & GAMBA_CUDA_STEP_FINAL) && npiv != L.n_bot)

@@ -36,7 +36,8 @@ struct ElimArgs {
     uint32_t* list_m;            // [gridDim][n_top] their multipliers (p - x)
     uint32_t* queue;             // atomic row counter
     uint32_t row_begin, row_step, n_local;  // rows r = row_begin + i * row_step, i < n_local
-    unsigned long long* stats;   // [0] pivot rows applied, [1] multiply-adds
+    const uint64_t* row_ptr;     // block-form CSR row pointers (for the fma_top invariant)
+    unsigned long long* stats;   // [0] pivot rows applied, [1] multiply-adds done, [2] fma_top
 };
 
 template <bool SMALLP>
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(ELIM_THREADS, 1) elim_kernel(ElimArgs a) {
     const uint64_t p2 = a.f.p2;
     uint32_t* lk = a.list_k + (uint64_t)blockIdx.x * L.n_top;
     uint32_t* lm = a.list_m + (uint64_t)blockIdx.x * L.n_top;
-    unsigned long long fma = 0, npiv = 0;
+    unsigned long long fma = 0, npiv = 0, fma_top = 0;
 
     for (;;) {
         if (tid == 0) s_q = atomicAdd(a.queue, 1u);
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(ELIM_THREADS, 1) elim_kernel(ElimArgs a) {
                         if (x) {
                             const uint32_t i = nlist + __popc(nzm & lt);
                             lk[i] = k0 + lane; lm[i] = p - x;
+                            fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
                         }
                     }
                     __syncthreads();
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(ELIM_THREADS, 1) elim_kernel(ElimArgs a) {
         if (fma) atomicAdd(a.stats + 1, fma);
         if (npiv) atomicAdd(a.stats + 0, npiv);
     }
+    if (warp == 0 && fma_top) atomicAdd(a.stats + 2, fma_top);
 }
 
 }  // namespace gcu

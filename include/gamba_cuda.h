@@ -52,8 +52,10 @@ extern "C" {
 #define GAMBA_CUDA_REPR_MONTGOMERY 1u
 
 /* gamba_cuda_step_in.flags */
-#define GAMBA_CUDA_STEP_FINAL      1u  /* final inter-reduction (linalg<M>::reduce): result rows are
-                                          returned in the order of the bottom rows, columns absolute */
+#define GAMBA_CUDA_STEP_FINAL      1u  /* final inter-reduction (linalg<M>::reduce, reduce.hpp:51-52): the rows
+                                          to reduce have distinct non-pivot leads, so the engine checks
+                                          n_new == n_bot; same output form (ascending pivot = the bottom
+                                          rows' order reversed, matrix.hpp:733-739)                    */
 
 typedef struct gamba_cuda_engine gamba_cuda_engine;
 
@@ -131,6 +133,8 @@ typedef struct gamba_cuda_counters {
     uint32_t acc_bits;                 /* 32 or 64                                              */
     uint64_t pivots_applied;           /* sum over rows of pivot rows applied in the last step  */
     uint64_t fma_applied;              /* multiply-adds the elimination kernel did, last step   */
+    uint64_t fma_top;                  /* matrix invariant of SURVEY.md §8(d): sum over pivot hits of
+                                          nnz(pivot row), this rank's rows, last step              */
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
