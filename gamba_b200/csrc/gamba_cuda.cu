@@ -75,9 +75,9 @@ struct gamba_cuda_engine {
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6]{};
-    int max_smem_optin = 0;
+    int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
-    int64_t opt_ctas_per_sm = 0;
+    int64_t opt_warps_per_sm = 0;
 
     // staged step
     bool staged = false;
@@ -85,7 +85,7 @@ struct gamba_cuda_engine {
     uint32_t flags = 0;
     uint64_t nnz = 0;
     gcu::DevBuf d_row_ptr, d_col, d_coeff_id, d_coeff_off, d_pool;
-    gcu::DevBuf d_seg, d_ent, d_diag, d_first, d_scan_tmp;
+    gcu::DevBuf d_cnt, d_seg, d_ent, d_diag, d_dnz, d_first, d_scan_tmp;
     gcu::HostBuf h_pool, h_off;
     uint64_t h2d_bytes = 0;
     double t_stage_wall = 0, t_prep_dev = 0;
@@ -126,12 +126,14 @@ using namespace gcu;
 
 void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols) {
     L = Layout{};
-    L.n_top = n_top; L.n_bot = n_bot; L.n_cols = n_cols; L.n_nonpiv = n_cols - n_top;
-    const uint32_t gran = BUCKET_COLS * ELIM_WARPS;  // 128, also a multiple of WINDOW
-    cudaFuncAttributes fa{};
-    GCU_CHECK(cudaFuncGetAttributes(&fa, elim_kernel<false>));
-    const size_t avail = (size_t)max_smem_optin - fa.sharedSizeBytes - 64;
-    uint32_t tmax = (uint32_t)(avail / sizeof(uint64_t)) / gran * gran;
+    L.n_top = n_top; L.n_bot = n_bot; L.n_cols = n_cols; L.n_nonpiv = n_cols - n_top; L.n_rows = n_top + n_bot;
+    // Tile width from the number of rows (= warps) wanted in flight per SM: the kernel is
+    // latency-bound, shared memory per SM / (warps per SM) is what one accumulator tile gets.
+    const uint32_t gran = WINDOW;
+    const uint32_t want_warps = (uint32_t)std::max<int64_t>(ELIM_CTA_WARPS, opt_warps_per_sm > 0 ? opt_warps_per_sm : 12);
+    const uint32_t ctas = std::max(1u, want_warps / ELIM_CTA_WARPS);
+    const size_t per_cta = ((size_t)smem_per_sm / ctas) - 1024 - 64;   // 1 KB per resident CTA is reserved
+    uint32_t tmax = (uint32_t)(std::min<size_t>(per_cta, (size_t)max_smem_optin - 64) / (ELIM_CTA_WARPS * sizeof(uint64_t))) / gran * gran;
     if (opt_tile_cols > 0) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
     auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
     // pivot tiles of equal width; the non-pivot range is cut with the same width
@@ -145,8 +147,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     L.tile_cols = t;
     L.n_tiles_piv = (n_top + t - 1) / t;
     L.n_tiles_nonpiv = (L.n_nonpiv + t - 1) / t;
-    L.n_tiles = L.n_tiles_piv + L.n_tiles_nonpiv;
-    L.n_bins = std::max(1u, L.n_tiles * ELIM_WARPS);
+    L.n_tiles = std::max(1u, L.n_tiles_piv + L.n_tiles_nonpiv);
     L.n_windows = (n_top + WINDOW - 1) / WINDOW;
     ctr.tile_cols = t; ctr.n_tiles = L.n_tiles; ctr.acc_bits = 64;
 }
@@ -160,8 +161,8 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     if (in->nnz >= (1ull << 32)) throw std::runtime_error("step has >= 2^32 non-zeros");
     choose_layout(in->n_top, in->n_bot, in->n_cols);
     flags = in->flags; nnz = in->nnz;
-    if ((uint64_t)n_rows * L.n_bins + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
-    if ((uint64_t)8 * L.n_bins * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
+    if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
+    if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
 
     // shared coefficient arrays -> one u32 pool
     const uint32_t na = in->n_coeff_arrays;
@@ -194,23 +195,27 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     GCU_CHECK(cudaMemcpyAsync(d_pool.p, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     h2d_bytes = (n_rows + 1) * 8ull + nnz * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull;
 
-    const uint64_t n_seg = (uint64_t)n_rows * L.n_bins + 1;
-    d_seg.ensure(n_seg * sizeof(uint32_t));
+    const uint64_t n_cnt = (uint64_t)n_rows * L.n_tiles + 1;
+    const uint64_t n_diag = std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1);
+    d_cnt.ensure(n_cnt * sizeof(uint32_t));
+    d_seg.ensure(std::max<uint64_t>((uint64_t)(L.n_tiles + 1) * n_rows, 1) * sizeof(uint32_t));
     d_ent.ensure(std::max<uint64_t>(nnz, 1) * sizeof(uint2));
-    d_diag.ensure(std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1) * sizeof(uint32_t));
+    d_diag.ensure(n_diag * sizeof(uint32_t));
+    d_dnz.ensure(std::max<uint32_t>(L.n_windows, 1) * sizeof(uint32_t));
     d_first.ensure(std::max<uint32_t>(L.n_bot, 1) * sizeof(uint32_t));
     GCU_CHECK(cudaEventRecord(ev[0], stream));
-    GCU_CHECK(cudaMemsetAsync(d_seg.p, 0, n_seg * sizeof(uint32_t), stream));
-    GCU_CHECK(cudaMemsetAsync(d_diag.p, 0, (uint64_t)L.n_windows * WINDOW * WINDOW * sizeof(uint32_t), stream));
+    GCU_CHECK(cudaMemsetAsync(d_cnt.p, 0, n_cnt * sizeof(uint32_t), stream));
+    GCU_CHECK(cudaMemsetAsync(d_diag.p, 0, n_diag * sizeof(uint32_t), stream));
 
     PrepArgs pa{};
     pa.L = L; pa.f = f;
     pa.row_ptr = d_row_ptr.as<uint64_t>(); pa.col = d_col.as<uint32_t>(); pa.coeff_id = d_coeff_id.as<uint32_t>();
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
-    pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>(); pa.diag = d_diag.as<uint32_t>();
+    pa.cnt = d_cnt.as<uint32_t>(); pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
+    pa.diag = d_diag.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
     pa.first_piv = d_first.as<uint32_t>();
     if (n_rows) {
-        const size_t sh = (size_t)8 * L.n_bins * sizeof(uint32_t);
+        const size_t sh = (size_t)8 * L.n_tiles * sizeof(uint32_t);
         if (sh > 48 * 1024) {
             GCU_CHECK(cudaFuncSetAttribute(prep_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
             GCU_CHECK(cudaFuncSetAttribute(prep_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
@@ -219,12 +224,17 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         prep_count_kernel<<<nblk, 256, sh, stream>>>(pa);
         GCU_CHECK(cudaGetLastError());
         size_t tmp_bytes = 0;
-        GCU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pa.seg, pa.seg, (int64_t)n_seg, stream));
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pa.cnt, pa.cnt, (int64_t)n_cnt, stream));
         d_scan_tmp.ensure(tmp_bytes);
-        GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, pa.seg, pa.seg, (int64_t)n_seg, stream));
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, pa.cnt, pa.cnt, (int64_t)n_cnt, stream));
         prep_fill_kernel<<<nblk, 256, sh, stream>>>(pa);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 3;
+        if (L.n_windows) {
+            prep_diag_inverse_kernel<<<(L.n_windows + 7) / 8, 256, 0, stream>>>(pa);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 1;
+        }
     }
     GCU_CHECK(cudaEventRecord(ev[1], stream));
     GCU_CHECK(cudaStreamSynchronize(stream));
@@ -242,19 +252,21 @@ void gamba_cuda_engine::eliminate() {
     n_local = L.n_bot > rank ? (L.n_bot - rank + world - 1) / world : 0;
     n_gather_rows = world > 1 ? n_local_max * world : L.n_bot;
 
-    const size_t smem = (size_t)L.tile_cols * sizeof(uint64_t);
+    const size_t smem = (size_t)ELIM_CTA_WARPS * L.tile_cols * sizeof(uint64_t);
     auto kern = f.small ? elim_kernel<true> : elim_kernel<false>;
     GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ELIM_THREADS, smem));
+    GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ELIM_CTA_THREADS, smem));
     if (occ < 1) throw std::runtime_error("elimination kernel does not fit on an SM");
-    if (opt_ctas_per_sm > 0) occ = std::min<int>(occ, (int)opt_ctas_per_sm);
-    elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
+    if (opt_warps_per_sm > 0) occ = std::min<int>(occ, std::max<int>(1, (int)opt_warps_per_sm / ELIM_CTA_WARPS));
+    const int want_ctas = (int)((std::max(1u, n_local) + ELIM_CTA_WARPS - 1) / ELIM_CTA_WARPS);
+    elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, want_ctas));
+    const uint64_t n_slots = (uint64_t)elim_grid * ELIM_CTA_WARPS;
 
     d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.n_nonpiv, 1) * sizeof(uint32_t));
     d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
-    d_list_k.ensure(std::max<uint64_t>((uint64_t)elim_grid * L.n_top, 1) * sizeof(uint32_t));
-    d_list_m.ensure(std::max<uint64_t>((uint64_t)elim_grid * L.n_top, 1) * sizeof(uint32_t));
+    d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
+    d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
     d_queue_stats.ensure(64);
     GCU_CHECK(cudaMemsetAsync(d_queue_stats.p, 0, 64, stream));
     GCU_CHECK(cudaMemsetAsync(d_row_nz.p, 0, std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t), stream));
@@ -266,6 +278,7 @@ void gamba_cuda_engine::eliminate() {
     ElimArgs ea{};
     ea.L = L; ea.f = f;
     ea.seg = d_seg.as<uint32_t>(); ea.ent = d_ent.as<uint2>(); ea.diag = d_diag.as<uint32_t>();
+    ea.dnz = d_dnz.as<uint32_t>();
     ea.first_piv = d_first.as<uint32_t>();
     ea.dprime = dloc; ea.row_nz = nzloc;
     ea.list_k = d_list_k.as<uint32_t>(); ea.list_m = d_list_m.as<uint32_t>();
@@ -275,7 +288,7 @@ void gamba_cuda_engine::eliminate() {
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (n_local && L.n_nonpiv) {
-        kern<<<elim_grid, ELIM_THREADS, smem, stream>>>(ea);
+        kern<<<elim_grid, ELIM_CTA_THREADS, smem, stream>>>(ea);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 1;
     }
@@ -415,6 +428,7 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
             GCU_CHECK(cudaGetDeviceProperties(&e->prop, (int)cfg->device));
             if (e->prop.major < 10) throw std::runtime_error("this library is built for sm_100a (B200) only");
             GCU_CHECK(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)cfg->device));
+            GCU_CHECK(cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, (int)cfg->device));
             GCU_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
             for (auto& ev : e->ev) GCU_CHECK(cudaEventCreate(&ev));
             e->ctr.sm_count = (uint32_t)e->prop.multiProcessorCount;
@@ -464,7 +478,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
     return guarded([&] {
         const std::string k = key ? key : "";
         if (k == "tile_cols") e->opt_tile_cols = value;
-        else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
+        else if (k == "warps_per_sm") e->opt_warps_per_sm = value;
         else throw std::runtime_error("unknown option " + k);
     });
 }

@@ -2,26 +2,31 @@
 // against the pivot rows (role of the reference's closed kernel/reduce_u16|u32,
 // kernel/saxpy, kernel/modular_u16|u32 translation units, CMakeLists.txt:81-90).
 //
-// One persistent CTA per row in flight, rows pulled from an atomic queue
-// (most expensive first). The row's accumulator is a tile of 64-bit lanes in
-// shared memory with delayed reduction (field.cuh). The CTA sweeps the column
-// tiles left to right:
+// ONE WARP PER ROW, rows pulled from an atomic queue (most expensive first), as
+// many warps resident per SM as shared memory allows: the first version of this
+// kernel (one CTA per row, profiles/r01_v1_*) sat at 12 % active warps with 93 %
+// L2 hits — the elimination of one row is a latency chain, so throughput comes
+// from independent rows in flight, not from more threads per row.
+//
+// The row's accumulator is a tile of T 64-bit lanes in shared memory with delayed
+// reduction (field.cuh). The warp sweeps the column tiles left to right:
 //   1. zero the tile, scatter the row's own entries of this tile;
-//   2. DEFERRED pass: apply every pivot row found in earlier tiles
-//      (multiplier list kept per CTA in global memory) restricted to this tile;
-//   3. pivot tiles only: walk the tile in WINDOWS of 32 pivot columns. Warp 0
-//      solves the window against the dense 32x32 diagonal block in registers
-//      (shuffles only; breaks the one-pivot-at-a-time latency chain), publishes
-//      the 32 multipliers, and all warps apply the non-zero pivot rows of the
-//      window to the rest of the tile, each warp to its own column bucket;
+//   2. DEFERRED pass: apply every pivot row found in earlier tiles (multiplier
+//      list kept per warp in global memory) restricted to this tile;
+//   3. pivot tiles only: walk the tile in WINDOWS of 32 pivot columns. The 32
+//      lanes read the window, multiply by the precomputed INVERSE of the 32x32
+//      diagonal block (layout.cuh) — no dependent chain: x = a * (I+N)^-1, only
+//      rows flagged in dnz are touched — and apply the pivot rows with x != 0 to
+//      the rest of the tile, ELIM_DEPTH row segments' loads in flight at a time;
 //   4. non-pivot tiles: reduce the lanes mod p and write the row of D'.
-// Warps never touch each other's buckets, so no atomics and no intra-window
-// barriers are needed; two CTA barriers per window order the window read
-// against the previous window's updates.
+// No CTA barriers, no atomics on the accumulator: a warp owns its tile.
 #pragma once
 #include "layout.cuh"
 
 namespace gcu {
+
+constexpr int ELIM_CTA_WARPS = 4;
+constexpr int ELIM_CTA_THREADS = ELIM_CTA_WARPS * 32;
 
 struct ElimArgs {
     Layout L;
@@ -29,11 +34,12 @@ struct ElimArgs {
     const uint32_t* seg;
     const uint2* ent;
     const uint32_t* diag;
+    const uint32_t* dnz;
     const uint32_t* first_piv;
     uint32_t* dprime;            // [n_local][n_nonpiv] standard residues
     uint32_t* row_nz;            // [n_local] 1 iff the reduced row is non-zero
-    uint32_t* list_k;            // [gridDim][n_top] pivot columns applied so far
-    uint32_t* list_m;            // [gridDim][n_top] their multipliers (p - x)
+    uint32_t* list_k;            // [warps in grid][n_top] pivot columns applied so far
+    uint32_t* list_m;            // [warps in grid][n_top] their multipliers (p - x)
     uint32_t* queue;             // atomic row counter
     uint32_t row_begin, row_step, n_local;  // rows r = row_begin + i * row_step, i < n_local
     const uint64_t* row_ptr;     // block-form CSR row pointers (for the fma_top invariant)
@@ -45,68 +51,75 @@ __device__ __forceinline__ void elim_rmw(uint64_t* acc, uint2 en, uint32_t m, ui
     acc[en.x] = fp_mac<SMALLP>(acc[en.x], m, en.y, p2);
 }
 
-// Apply up to 32 segments (one per lane: [s,e) with multiplier m) to the tile.
-// Loads of four segments are issued before the first read-modify-write so that
-// the L2/HBM latency of short segments overlaps.
+// Apply up to 32 segments (lane i holds segment i: entries [s,e) with multiplier m) to the tile.
+// The segments are cut into CHUNKS of 32 consecutive entries and the chunk stream of the whole
+// batch is software-pipelined: the loads of ELIM_DEPTH chunks are in flight before the first
+// read-modify-write. One chunk = all lanes on consecutive entries of ONE pivot row: coalesced,
+// and conflict-free because a pivot row has distinct columns. (A row's elimination is a chain of
+// L2 round trips; measured variants: 4 segments in flight with unpipelined tails 46 ms,
+// lane-per-segment with __match_any_sync conflict checks 320 ms on kat12-15 step 9.)
+constexpr int ELIM_DEPTH = 8;
+
 template <bool SMALLP>
 __device__ __forceinline__ void elim_apply_batch(uint64_t* acc, const uint2* __restrict__ ent, uint32_t s,
                                                  uint32_t e, uint32_t m, uint32_t lane, uint64_t p2,
                                                  unsigned long long& fma) {
-    uint32_t active = __ballot_sync(0xffffffffu, e > s);
-    while (active) {
-        int idx[4];
-        uint32_t ss[4], ee[4], mm[4];
-        uint2 v[4];
+    const uint32_t len = e - s;
+    fma += len;
+    const uint32_t nch = (len + 31) >> 5;
+    uint32_t inc = nch;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            idx[u] = active ? __ffs(active) - 1 : -1;
-            if (active) active &= active - 1;
-            const int src = idx[u] < 0 ? 0 : idx[u];
-            ss[u] = __shfl_sync(0xffffffffu, s, src);
-            ee[u] = __shfl_sync(0xffffffffu, e, src);
-            mm[u] = __shfl_sync(0xffffffffu, m, src);
-            if (idx[u] < 0) ee[u] = ss[u];
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += y; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t exc = inc - nch;
+    for (uint32_t c0 = 0; c0 < total; c0 += ELIM_DEPTH) {
+        uint2 v[ELIM_DEPTH];
+        uint32_t mm[ELIM_DEPTH];
+        bool ok[ELIM_DEPTH];
+#pragma unroll
+        for (int u = 0; u < ELIM_DEPTH; ++u) {
+            const uint32_t c = c0 + u;
+            // owner of chunk c: the last lane whose first chunk index is <= c
+            const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
+            const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 32 + lane;
+            const uint32_t su = __shfl_sync(0xffffffffu, s, own);
+            const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
+            mm[u] = __shfl_sync(0xffffffffu, m, own);
+            ok[u] = c < total && off < lu;
             v[u] = make_uint2(0, 0);
-            if (ss[u] + lane < ee[u]) v[u] = __ldg(ent + ss[u] + lane);
+            if (ok[u]) v[u] = __ldg(ent + su + off);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (idx[u] < 0) continue;  // warp-uniform
-            if (ss[u] + lane < ee[u]) elim_rmw<SMALLP>(acc, v[u], mm[u], p2);
+        for (int u = 0; u < ELIM_DEPTH; ++u) {
+            if (c0 + u >= total) break;  // warp-uniform
+            if (ok[u]) elim_rmw<SMALLP>(acc, v[u], mm[u], p2);
             __syncwarp();
-            for (uint32_t q = ss[u] + 32 + lane; q < ee[u]; q += 32) elim_rmw<SMALLP>(acc, __ldg(ent + q), mm[u], p2);
-            if (ee[u] - ss[u] > 32) __syncwarp();
-            if (lane == 0) fma += ee[u] - ss[u];
         }
     }
 }
 
 template <bool SMALLP>
-__global__ void __launch_bounds__(ELIM_THREADS, 1) elim_kernel(ElimArgs a) {
+__global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
     extern __shared__ __align__(16) unsigned char elim_smem[];
-    uint64_t* acc = reinterpret_cast<uint64_t*>(elim_smem);
-    __shared__ uint32_t s_x[WINDOW];
-    __shared__ uint32_t s_nz;
-    __shared__ uint32_t s_q;
-
     const Layout& L = a.L;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* acc = reinterpret_cast<uint64_t*>(elim_smem) + (size_t)warp * L.tile_cols;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t p = a.f.p;
+    const uint32_t p = a.f.p, nr = L.n_rows;
     const uint64_t p2 = a.f.p2;
-    uint32_t* lk = a.list_k + (uint64_t)blockIdx.x * L.n_top;
-    uint32_t* lm = a.list_m + (uint64_t)blockIdx.x * L.n_top;
+    const uint64_t slot = (uint64_t)blockIdx.x * ELIM_CTA_WARPS + warp;
+    uint32_t* lk = a.list_k + slot * L.n_top;
+    uint32_t* lm = a.list_m + slot * L.n_top;
     unsigned long long fma = 0, npiv = 0, fma_top = 0;
 
     for (;;) {
-        if (tid == 0) s_q = atomicAdd(a.queue, 1u);
-        __syncthreads();
-        const uint32_t q = s_q;
-        __syncthreads();
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(a.queue, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
         if (q >= a.n_local) break;
         const uint32_t li = a.n_local - 1 - q;                 // later rows have smaller leads: more work
         const uint32_t r = a.row_begin + li * a.row_step;      // index among the rows to reduce
-        const uint64_t grow = (uint64_t)(L.n_top + r) * L.n_bins;
+        const uint32_t grow = L.n_top + r;
         const uint32_t first = a.first_piv[r];
         const uint32_t t_first = first < L.n_top ? first / L.tile_cols : L.n_tiles_piv;
         uint32_t nlist = 0;
@@ -114,10 +127,12 @@ __global__ void __launch_bounds__(ELIM_THREADS, 1) elim_kernel(ElimArgs a) {
 
         for (uint32_t t = t_first; t < L.n_tiles; ++t) {
             const uint32_t t0 = lay_tile_start(L, t), tw = lay_tile_width(L, t);
-            for (uint32_t i = tid; i < tw; i += ELIM_THREADS) acc[i] = 0;
-            __syncthreads();
+            const uint32_t* seg_s = a.seg + (uint64_t)t * nr;
+            const uint32_t* seg_e = seg_s + nr;
+            for (uint32_t i = lane; i < tw; i += 32) acc[i] = 0;
+            __syncwarp();
             {   // the row itself
-                const uint32_t s = a.seg[grow + t * ELIM_WARPS + warp], e = a.seg[grow + t * ELIM_WARPS + warp + 1];
+                const uint32_t s = seg_s[grow], e = seg_e[grow];
                 for (uint32_t k = s + lane; k < e; k += 32) { const uint2 en = __ldg(a.ent + k); acc[en.x] = en.y; }
                 __syncwarp();
             }
@@ -125,75 +140,70 @@ __global__ void __launch_bounds__(ELIM_THREADS, 1) elim_kernel(ElimArgs a) {
             for (uint32_t base = 0; base < nlist; base += 32) {
                 const uint32_t i = base + lane;
                 uint32_t s = 0, e = 0, m = 0;
-                if (i < nlist) {
-                    const uint64_t o = (uint64_t)lk[i] * L.n_bins + t * ELIM_WARPS + warp;
-                    m = lm[i]; s = a.seg[o]; e = a.seg[o + 1];
-                }
+                if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; e = seg_e[k]; }
                 elim_apply_batch<SMALLP>(acc, a.ent, s, e, m, lane, p2, fma);
             }
-            __syncthreads();
 
             if (t < L.n_tiles_piv) {
                 const uint32_t nwin = (tw + WINDOW - 1) / WINDOW;
-                for (uint32_t g = (t == t_first ? (first - t0) / WINDOW : 0); g < nwin; ++g) {
+                uint32_t g = (t == t_first ? (first - t0) / WINDOW : 0);
+                // segment pointers of the window's 32 pivot rows, fetched one window ahead
+                uint32_t ps = 0, pe = 0;
+                if (g < nwin && t0 + g * WINDOW + lane < L.n_top) { ps = seg_s[t0 + g * WINDOW + lane]; pe = seg_e[t0 + g * WINDOW + lane]; }
+                for (; g < nwin; ++g) {
                     const uint32_t k0 = t0 + g * WINDOW;
-                    if (warp == 0) {
-                        const uint32_t c = g * WINDOW + lane;
-                        uint32_t x = c < tw ? fp_reduce64(acc[c], a.f) : 0u;
-                        if (__ballot_sync(0xffffffffu, x != 0)) {
-                            const uint32_t* dg = a.diag + (uint64_t)(k0 / WINDOW) * WINDOW * WINDOW + lane;
-                            uint32_t d[WINDOW];
-#pragma unroll
-                            for (int i = 0; i < WINDOW; ++i) d[i] = __ldg(dg + i * WINDOW);
-#pragma unroll
-                            for (int i = 0; i < WINDOW - 1; ++i) {
-                                const uint32_t xi = __shfl_sync(0xffffffffu, x, i);
-                                if (xi == 0) continue;  // warp-uniform
-                                const uint32_t y = fp_reduce64((uint64_t)x + (uint64_t)(p - xi) * d[i], a.f);
-                                if ((int)lane > i) x = y;
-                            }
+                    const uint32_t c = g * WINDOW + lane;
+                    const uint32_t s = ps, e = pe;
+                    if (g + 1 < nwin && k0 + WINDOW + lane < L.n_top) { ps = seg_s[k0 + WINDOW + lane]; pe = seg_e[k0 + WINDOW + lane]; }
+                    const uint32_t av = c < tw ? fp_reduce64(acc[c], a.f) : 0u;
+                    const uint32_t nza = __ballot_sync(0xffffffffu, av != 0);
+                    if (nza == 0) continue;
+                    uint32_t x = av;
+                    uint32_t need = nza & a.dnz[k0 / WINDOW];
+                    if (need) {   // x = a * (I + M): add a_i * M[i][lane] for the flagged rows i
+                        const uint32_t* dg = a.diag + (uint64_t)(k0 / WINDOW) * WINDOW * WINDOW + lane;
+                        uint64_t xa = av;
+                        while (need) {
+                            int i0 = __ffs(need) - 1; need &= need - 1;
+                            int i1 = need ? __ffs(need) - 1 : -1; if (need) need &= need - 1;
+                            const uint32_t m0 = __ldg(dg + i0 * WINDOW);
+                            const uint32_t m1 = i1 >= 0 ? __ldg(dg + i1 * WINDOW) : 0u;
+                            xa = fp_mac<false>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);
+                            if (i1 >= 0) xa = fp_mac<false>(xa, __shfl_sync(0xffffffffu, av, i1), m1, p2);
                         }
-                        const uint32_t nzm = __ballot_sync(0xffffffffu, x != 0);
-                        s_x[lane] = x;
-                        if (lane == 0) s_nz = nzm;
-                        if (x) {
-                            const uint32_t i = nlist + __popc(nzm & lt);
-                            lk[i] = k0 + lane; lm[i] = p - x;
-                            fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
-                        }
+                        x = fp_reduce64(xa, a.f);
                     }
-                    __syncthreads();
-                    const uint32_t nzm = s_nz;
-                    if (nzm) {
-                        uint32_t s = 0, e = 0, m = 0;
-                        if ((nzm >> lane) & 1u) {
-                            const uint64_t o = (uint64_t)(k0 + lane) * L.n_bins + t * ELIM_WARPS + warp;
-                            m = p - s_x[lane]; s = a.seg[o]; e = a.seg[o + 1];
-                        }
-                        elim_apply_batch<SMALLP>(acc, a.ent, s, e, m, lane, p2, fma);
-                        nlist += __popc(nzm);
+                    const uint32_t nzm = __ballot_sync(0xffffffffu, x != 0);
+                    if (nzm == 0) continue;
+                    uint32_t m = 0;
+                    if (x) {
+                        const uint32_t i = nlist + __popc(nzm & lt);
+                        m = p - x;
+                        lk[i] = k0 + lane; lm[i] = m;
+                        fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
                     }
-                    __syncthreads();
+                    nlist += __popc(nzm);
+                    elim_apply_batch<SMALLP>(acc, a.ent, x ? s : 0u, x ? e : 0u, m, lane, p2, fma);
                 }
+                __syncwarp();
             } else {
                 uint32_t* out = a.dprime + (uint64_t)li * L.n_nonpiv + (t0 - L.n_top);
-                for (uint32_t i = tid; i < tw; i += ELIM_THREADS) {
+                for (uint32_t i = lane; i < tw; i += 32) {
                     const uint32_t v = fp_reduce64(acc[i], a.f);
                     out[i] = v;
                     nz |= v != 0;
                 }
-                __syncthreads();
+                __syncwarp();
             }
         }
-        const int any = __syncthreads_or(nz ? 1 : 0);
-        if (tid == 0) a.row_nz[li] = any ? 1u : 0u;
-        npiv += (warp == 0 && lane == 0) ? nlist : 0;
+        const int any = __any_sync(0xffffffffu, nz);
+        if (lane == 0) a.row_nz[li] = any ? 1u : 0u;
+        npiv += lane == 0 ? nlist : 0;
     }
-    if (lane == 0) {
-        if (fma) atomicAdd(a.stats + 1, fma);
-        if (npiv) atomicAdd(a.stats + 0, npiv);
-    }
-    if (warp == 0 && fma_top) atomicAdd(a.stats + 2, fma_top);
+    for (int o = 16; o; o >>= 1) fma += __shfl_xor_sync(0xffffffffu, fma, o);
+    if (lane == 0 && fma) atomicAdd(a.stats + 1, fma);
+    if (npiv) atomicAdd(a.stats + 0, npiv);
+    if (fma_top) atomicAdd(a.stats + 2, fma_top);
 }
 
 }  // namespace gcu

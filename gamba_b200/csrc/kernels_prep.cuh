@@ -1,5 +1,5 @@
 // Staging kernels: turn the block-form CSR handed over at the ABI (column lists +
-// shared coefficient arrays) into the bucketed device layout of
+// shared coefficient arrays) into the tiled device layout of
 // layout.cuh. One warp per row; coefficients are gathered from the shared arrays
 // exactly once per step (rows share arrays ~25:1, source/matrix.hpp:189-193).
 #pragma once
@@ -15,9 +15,11 @@ struct PrepArgs {
     const uint32_t* coeff_id;
     const uint64_t* coeff_off;
     const uint32_t* pool;
-    uint32_t* seg;        // in: zero / out of count: per-bin counts / after scan: starts
+    uint32_t* cnt;        // [n_rows * n_tiles + 1] row-major: counts, then (after the scan) starts
+    uint32_t* seg;        // [(n_tiles + 1) * n_rows] tile-major starts (layout.cuh)
     uint2* ent;
-    uint32_t* diag;
+    uint32_t* diag;       // [n_windows][32][32]
+    uint32_t* dnz;        // [n_windows]
     uint32_t* first_piv;  // per bottom row: smallest pivot column present (n_top if none)
 };
 
@@ -29,24 +31,22 @@ __device__ __forceinline__ bool prep_in_window(const Layout& L, uint32_t row, ui
 __global__ void __launch_bounds__(256) prep_count_kernel(PrepArgs a) {
     extern __shared__ uint32_t sh_hist[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_rows = a.L.n_top + a.L.n_bot;
     const uint32_t row = blockIdx.x * 8 + warp;
-    uint32_t* hist = sh_hist + warp * a.L.n_bins;
-    for (uint32_t b = lane; b < a.L.n_bins; b += 32) hist[b] = 0;
+    const uint32_t nt = a.L.n_tiles;
+    uint32_t* hist = sh_hist + warp * nt;
+    for (uint32_t b = lane; b < nt; b += 32) hist[b] = 0;
     __syncwarp();
-    if (row < n_rows) {
+    if (row < a.L.n_rows) {
         const uint64_t s = a.row_ptr[row], e = a.row_ptr[row + 1];
         uint32_t fp = a.L.n_top;
         for (uint64_t k = s + lane; k < e; k += 32) {
             const uint32_t c = a.col[k];
             if (c < a.L.n_top && c < fp) fp = c;
             if (prep_in_window(a.L, row, c)) continue;
-            const uint32_t t = lay_tile(a.L, c);
-            const uint32_t off = c - lay_tile_start(a.L, t);
-            atomicAdd(&hist[t * ELIM_WARPS + lay_bucket(off)], 1u);
+            atomicAdd(&hist[lay_tile(a.L, c)], 1u);
         }
         __syncwarp();
-        for (uint32_t b = lane; b < a.L.n_bins; b += 32) a.seg[(uint64_t)row * a.L.n_bins + b] = hist[b];
+        for (uint32_t b = lane; b < nt; b += 32) a.cnt[(uint64_t)row * nt + b] = hist[b];
         if (row >= a.L.n_top) {
             for (int o = 16; o; o >>= 1) fp = min(fp, __shfl_xor_sync(0xffffffffu, fp, o));
             if (lane == 0) a.first_piv[row - a.L.n_top] = fp;
@@ -57,11 +57,16 @@ __global__ void __launch_bounds__(256) prep_count_kernel(PrepArgs a) {
 __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
     extern __shared__ uint32_t sh_cur[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_rows = a.L.n_top + a.L.n_bot;
     const uint32_t row = blockIdx.x * 8 + warp;
-    if (row >= n_rows) return;
-    uint32_t* cur = sh_cur + warp * a.L.n_bins;
-    for (uint32_t b = lane; b < a.L.n_bins; b += 32) cur[b] = a.seg[(uint64_t)row * a.L.n_bins + b];
+    const uint32_t nt = a.L.n_tiles, nr = a.L.n_rows;
+    if (row >= nr) return;
+    uint32_t* cur = sh_cur + warp * nt;
+    for (uint32_t b = lane; b < nt; b += 32) {
+        const uint32_t st = a.cnt[(uint64_t)row * nt + b];
+        cur[b] = st;
+        a.seg[(uint64_t)b * nr + row] = st;
+    }
+    if (lane == 0) a.seg[(uint64_t)nt * nr + row] = a.cnt[(uint64_t)(row + 1) * nt];  // row end
     __syncwarp();
     const uint64_t s = a.row_ptr[row], e = a.row_ptr[row + 1];
     const uint32_t* cf = a.pool + a.coeff_off[a.coeff_id[row]];
@@ -77,22 +82,49 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
                 if (c != row)  // the unit diagonal is implicit
                     a.diag[((uint64_t)(row / WINDOW) * WINDOW + (row % WINDOW)) * WINDOW + (c % WINDOW)] = val;
             } else {
-                const uint32_t t = lay_tile(a.L, c);
-                off = c - lay_tile_start(a.L, t);
-                bin = t * ELIM_WARPS + lay_bucket(off);
+                bin = lay_tile(a.L, c);
+                off = c - lay_tile_start(a.L, bin);
             }
         }
-        // stable placement: rank among the lanes of this chunk that share the bin
+        // stable placement: rank among the lanes of this chunk that share the tile
         const uint32_t peers = __match_any_sync(0xffffffffu, bin);
         if (bin != 0xffffffffu) {
-            const uint32_t rank = __popc(peers & lt);
-            const uint32_t pos = cur[bin] + rank;
+            const uint32_t pos = cur[bin] + __popc(peers & lt);
             a.ent[pos] = make_uint2(off, val);
         }
         __syncwarp();
         if (bin != 0xffffffffu && (peers >> lane) <= 1u) cur[bin] += __popc(peers);  // highest lane of the group
         __syncwarp();
     }
+}
+
+// One warp per window: replace the strictly-upper block N (A_ww = I + N, diagonal implicit) by the
+// strictly-upper part M of (I + N)^-1 = I + M, lane = column:  M[i] = -N[i] - sum_{j>i} N[i][j] * M[j].
+__global__ void __launch_bounds__(256) prep_diag_inverse_kernel(PrepArgs a) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * 8 + warp;
+    if (w >= a.L.n_windows) return;
+    uint32_t* blk = a.diag + (uint64_t)w * WINDOW * WINDOW;
+    uint32_t n[WINDOW], inv[WINDOW];
+#pragma unroll
+    for (int i = 0; i < WINDOW; ++i) { n[i] = blk[i * WINDOW + lane]; inv[i] = 0; }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = WINDOW - 2; i >= 0; --i) {
+        if (__ballot_sync(0xffffffffu, n[i] != 0) == 0) continue;  // empty row: inverse row is e_i
+        uint64_t acc = n[i] ? (uint64_t)(a.f.p - n[i]) : 0ull;
+#pragma unroll
+        for (int j = i + 1; j < WINDOW; ++j) {
+            const uint32_t nij = __shfl_sync(0xffffffffu, n[i], j);
+            if (nij == 0) continue;  // warp-uniform
+            if (inv[j]) acc = fp_reduce64(acc + (uint64_t)(a.f.p - nij) * inv[j], a.f);
+        }
+        inv[i] = (int)lane > i ? fp_reduce64(acc, a.f) : 0u;
+        if (__ballot_sync(0xffffffffu, inv[i] != 0)) mask |= 1u << i;
+    }
+#pragma unroll
+    for (int i = 0; i < WINDOW; ++i) blk[i * WINDOW + lane] = inv[i];
+    if (lane == 0) a.dnz[w] = mask;
 }
 
 }  // namespace gcu
