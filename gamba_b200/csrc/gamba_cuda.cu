@@ -132,8 +132,10 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     const uint32_t gran = WINDOW;
     const uint32_t want_warps = (uint32_t)std::max<int64_t>(ELIM_CTA_WARPS, opt_warps_per_sm > 0 ? opt_warps_per_sm : 12);
     const uint32_t ctas = std::max(1u, want_warps / ELIM_CTA_WARPS);
-    const size_t per_cta = ((size_t)smem_per_sm / ctas) - 1024 - 64;   // 1 KB per resident CTA is reserved
-    uint32_t tmax = (uint32_t)(std::min<size_t>(per_cta, (size_t)max_smem_optin - 64) / (ELIM_CTA_WARPS * sizeof(uint64_t))) / gran * gran;
+    const size_t per_cta = std::min<size_t>(((size_t)smem_per_sm / ctas) - 1024 - 64, (size_t)max_smem_optin - 64);
+    const uint32_t words_per_col = f.small ? 1u : 2u;   // kernels_elim.cuh: Acc<SMALLP>::WORDS
+    const size_t warp_words = per_cta / sizeof(uint32_t) / ELIM_CTA_WARPS;
+    uint32_t tmax = (uint32_t)((warp_words - ELIM_SCRATCH_WORDS - 4) / words_per_col - 1) / gran * gran;
     if (opt_tile_cols > 0) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
     auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
     // pivot tiles of equal width; the non-pivot range is cut with the same width
@@ -149,7 +151,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     L.n_tiles_nonpiv = (L.n_nonpiv + t - 1) / t;
     L.n_tiles = std::max(1u, L.n_tiles_piv + L.n_tiles_nonpiv);
     L.n_windows = (n_top + WINDOW - 1) / WINDOW;
-    ctr.tile_cols = t; ctr.n_tiles = L.n_tiles; ctr.acc_bits = 64;
+    ctr.tile_cols = t; ctr.n_tiles = L.n_tiles; ctr.acc_bits = 32 * words_per_col;
 }
 
 void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
@@ -158,10 +160,10 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     if (in->n_cols < in->n_top) throw std::runtime_error("n_cols < n_top");
     const uint32_t n_rows = in->n_top + in->n_bot;
     if (in->row_ptr[n_rows] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
-    if (in->nnz >= (1ull << 32)) throw std::runtime_error("step has >= 2^32 non-zeros");
     choose_layout(in->n_top, in->n_bot, in->n_cols);
     flags = in->flags; nnz = in->nnz;
     if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
+    if (nnz + 3ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
 
     // shared coefficient arrays -> one u32 pool
@@ -199,7 +201,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     const uint64_t n_diag = std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1);
     d_cnt.ensure(n_cnt * sizeof(uint32_t));
     d_seg.ensure(std::max<uint64_t>((uint64_t)(L.n_tiles + 1) * n_rows, 1) * sizeof(uint32_t));
-    d_ent.ensure(std::max<uint64_t>(nnz, 1) * sizeof(uint2));
+    d_ent.ensure((nnz + 3ull * n_rows * L.n_tiles + 4) * sizeof(uint2));   // segments padded to 4 entries
     d_diag.ensure(n_diag * sizeof(uint32_t));
     d_dnz.ensure(std::max<uint32_t>(L.n_windows, 1) * sizeof(uint32_t));
     d_first.ensure(std::max<uint32_t>(L.n_bot, 1) * sizeof(uint32_t));
@@ -252,7 +254,9 @@ void gamba_cuda_engine::eliminate() {
     n_local = L.n_bot > rank ? (L.n_bot - rank + world - 1) / world : 0;
     n_gather_rows = world > 1 ? n_local_max * world : L.n_bot;
 
-    const size_t smem = (size_t)ELIM_CTA_WARPS * L.tile_cols * sizeof(uint64_t);
+    const uint32_t words_per_col = f.small ? 1u : 2u;
+    const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
+    const size_t smem = (size_t)ELIM_CTA_WARPS * (acc_words + ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
     auto kern = f.small ? elim_kernel<true> : elim_kernel<false>;
     GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -277,6 +281,8 @@ void gamba_cuda_engine::eliminate() {
 
     ElimArgs ea{};
     ea.L = L; ea.f = f;
+    ea.mu32 = (uint32_t)((1ull << 32) / f.p);
+    ea.norm_every = f.small ? (uint32_t)std::min<uint64_t>(0xffffffffull / (f.p - 1) - 34, 1u << 30) : 65536u - 34u;
     ea.seg = d_seg.as<uint32_t>(); ea.ent = d_ent.as<uint2>(); ea.diag = d_diag.as<uint32_t>();
     ea.dnz = d_dnz.as<uint32_t>();
     ea.first_piv = d_first.as<uint32_t>();

@@ -3,23 +3,39 @@
 // kernel/saxpy, kernel/modular_u16|u32 translation units, CMakeLists.txt:81-90).
 //
 // ONE WARP PER ROW, rows pulled from an atomic queue (most expensive first), as
-// many warps resident per SM as shared memory allows: the first version of this
-// kernel (one CTA per row, profiles/r01_v1_*) sat at 12 % active warps with 93 %
-// L2 hits — the elimination of one row is a latency chain, so throughput comes
-// from independent rows in flight, not from more threads per row.
+// many warps resident per SM as shared memory allows. History:
+//   v1  one CTA per row, 64-bit lanes, warp-per-segment        90 ms  (kat12-15 step 9)
+//       -> 12 % active warps, 93 % L2 hits: latency-bound, not HBM-bound
+//   v2  one warp per row, pipelined 32-entry chunks             35 ms
+//       -> ~25 instructions per half-empty chunk: issue-bound per warp
+//   v3  lane per segment + native 32-bit shared-memory atomics   54 ms
+//   v4  (this file) v2's chunk stream staged by cp.async + v3's atomic 32-bit lanes
 //
-// The row's accumulator is a tile of T 64-bit lanes in shared memory with delayed
-// reduction (field.cuh). The warp sweeps the column tiles left to right:
+// The row's accumulator is a tile in shared memory with DELAYED REDUCTION:
+//   p < 2^16   one 32-bit lane per column; a multiply-add adds (m*v mod p) < 2^16
+//              with ATOMS.ADD, the lane is reduced mod p only when it is read
+//              (or after `norm_every` pivot rows, long before 2^32 is reached);
+//   p < 2^31   a lo/hi pair of 32-bit lanes per column; (m*v mod p) is split into
+//              its low 16 and high 15 bits, one ATOMS.ADD each (64-bit shared
+//              atomics are a CAS loop on sm_100a, 32-bit ones are native and were
+//              measured at 5.9 lanes/clk/SM vs 2.8 for LDS.64+STS.64,
+//              tools/micro/atoms_bench.cu).
+// Pivot-row entries are staged through a per-warp ring of shared-memory slots
+// with cp.async (LDGSTS): ELIM_DEPTH x 512 B in flight per warp without holding
+// registers (segments are sector-aligned and padded for it, layout.cuh). A
+// lane-per-segment variant (every lane streaming its own pivot row with 32-byte
+// loads, possible because the atomics make cross-row conflicts safe) was measured
+// slower: 2 KB in flight per warp and uncoalesced sectors.
+//
+// The warp sweeps the column tiles left to right:
 //   1. zero the tile, scatter the row's own entries of this tile;
 //   2. DEFERRED pass: apply every pivot row found in earlier tiles (multiplier
 //      list kept per warp in global memory) restricted to this tile;
-//   3. pivot tiles only: walk the tile in WINDOWS of 32 pivot columns. The 32
-//      lanes read the window, multiply by the precomputed INVERSE of the 32x32
-//      diagonal block (layout.cuh) — no dependent chain: x = a * (I+N)^-1, only
-//      rows flagged in dnz are touched — and apply the pivot rows with x != 0 to
-//      the rest of the tile, ELIM_DEPTH row segments' loads in flight at a time;
+//   3. pivot tiles only: walk the tile in WINDOWS of 32 pivot columns: read the
+//      window, multiply by the precomputed INVERSE of the 32x32 diagonal block
+//      (x = a (I+N)^-1, no dependent chain; only rows flagged in dnz are touched),
+//      then apply the pivot rows with x != 0 to the rest of the tile;
 //   4. non-pivot tiles: reduce the lanes mod p and write the row of D'.
-// No CTA barriers, no atomics on the accumulator: a warp owns its tile.
 #pragma once
 #include "layout.cuh"
 
@@ -27,10 +43,14 @@ namespace gcu {
 
 constexpr int ELIM_CTA_WARPS = 4;
 constexpr int ELIM_CTA_THREADS = ELIM_CTA_WARPS * 32;
+constexpr int ELIM_DEPTH = 8;             // cp.async ring slots per warp (512 B each)
+constexpr int ELIM_SCRATCH_WORDS = ELIM_DEPTH * 128;   // per warp: the ring
 
 struct ElimArgs {
     Layout L;
     Fp f;
+    uint32_t mu32;               // floor(2^32 / p), Barrett constant for 32-bit operands (p < 2^16)
+    uint32_t norm_every;         // pivot rows a tile may absorb between normalisations
     const uint32_t* seg;
     const uint2* ent;
     const uint32_t* diag;
@@ -46,56 +66,111 @@ struct ElimArgs {
     unsigned long long* stats;   // [0] pivot rows applied, [1] multiply-adds done, [2] fma_top
 };
 
+// ---- accumulator policies -------------------------------------------------------------------
+
+template <bool SMALLP> struct Acc;
+
+template <> struct Acc<true> {   // p < 2^16: one u32 lane per column
+    static constexpr int WORDS = 1;
+    static __device__ __forceinline__ uint32_t mulred(uint32_t m, uint32_t v, const ElimArgs& a) {
+        const uint32_t x = m * v;                       // < 2^32
+        uint32_t r = x - __umulhi(x, a.mu32) * a.f.p;   // < 2p
+        return r >= a.f.p ? r - a.f.p : r;
+    }
+    static __device__ __forceinline__ void add(uint32_t* acc, uint32_t c, uint32_t val) { atomicAdd(acc + c, val); }
+    static __device__ __forceinline__ void set(uint32_t* acc, uint32_t c, uint32_t val) { acc[c] = val; }
+    static __device__ __forceinline__ uint32_t get(const uint32_t* acc, uint32_t c, const ElimArgs& a) {
+        const uint32_t x = acc[c];
+        uint32_t r = x - __umulhi(x, a.mu32) * a.f.p;
+        return r >= a.f.p ? r - a.f.p : r;
+    }
+};
+
+template <> struct Acc<false> {  // p < 2^31: lo/hi pair of u32 lanes per column
+    static constexpr int WORDS = 2;
+    static __device__ __forceinline__ uint32_t mulred(uint32_t m, uint32_t v, const ElimArgs& a) {
+        return fp_reduce64((uint64_t)m * v, a.f);
+    }
+    static __device__ __forceinline__ void add(uint32_t* acc, uint32_t c, uint32_t val) {
+        atomicAdd(acc + 2 * c, val & 0xffffu);
+        atomicAdd(acc + 2 * c + 1, val >> 16);
+    }
+    static __device__ __forceinline__ void set(uint32_t* acc, uint32_t c, uint32_t val) {
+        acc[2 * c] = val & 0xffffu; acc[2 * c + 1] = val >> 16;
+    }
+    static __device__ __forceinline__ uint32_t get(const uint32_t* acc, uint32_t c, const ElimArgs& a) {
+        const uint2 w = *reinterpret_cast<const uint2*>(acc + 2 * c);
+        return fp_reduce64((uint64_t)w.x + ((uint64_t)w.y << 16), a.f);
+    }
+};
+
+// Bring every lane of the tile back below p (delayed reduction: done rarely).
 template <bool SMALLP>
-__device__ __forceinline__ void elim_rmw(uint64_t* acc, uint2 en, uint32_t m, uint64_t p2) {
-    acc[en.x] = fp_mac<SMALLP>(acc[en.x], m, en.y, p2);
+__device__ __forceinline__ void elim_normalise(uint32_t* acc, uint32_t tw, uint32_t lane, const ElimArgs& a) {
+    __syncwarp();
+    for (uint32_t i = lane; i < tw; i += 32) Acc<SMALLP>::set(acc, i, Acc<SMALLP>::get(acc, i, a));
+    __syncwarp();
 }
 
-// Apply up to 32 segments (lane i holds segment i: entries [s,e) with multiplier m) to the tile.
-// The segments are cut into CHUNKS of 32 consecutive entries and the chunk stream of the whole
-// batch is software-pipelined: the loads of ELIM_DEPTH chunks are in flight before the first
-// read-modify-write. One chunk = all lanes on consecutive entries of ONE pivot row: coalesced,
-// and conflict-free because a pivot row has distinct columns. (A row's elimination is a chain of
-// L2 round trips; measured variants: 4 segments in flight with unpipelined tails 46 ms,
-// lane-per-segment with __match_any_sync conflict checks 320 ms on kat12-15 step 9.)
-constexpr int ELIM_DEPTH = 8;
+// ---- asynchronous staging of pivot-row entries (LDGSTS) ---------------------------------------
 
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gmem, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(smem_addr), "l"(gmem), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Apply up to 32 pivot-row segments (lane i holds segment i: entries [s,e), multiplier m).
+// The segments are cut into CHUNKS of 64 consecutive entries (512 B, 16 B per lane) and the chunk
+// stream of the batch runs through a ring of ELIM_DEPTH shared-memory slots filled by cp.async:
+// ELIM_DEPTH x 512 B per warp are in flight at no register cost (a row's elimination is a chain of
+// ~1 us round trips, its speed is bytes in flight). A chunk is all lanes on consecutive entries of
+// ONE pivot row: coalesced, and each lane reads back exactly the 16 B it copied itself.
 template <bool SMALLP>
-__device__ __forceinline__ void elim_apply_batch(uint64_t* acc, const uint2* __restrict__ ent, uint32_t s,
-                                                 uint32_t e, uint32_t m, uint32_t lane, uint64_t p2,
-                                                 unsigned long long& fma) {
+__device__ __forceinline__ void elim_apply_batch(uint32_t* acc, uint32_t* ring, const ElimArgs& a, uint32_t s,
+                                                 uint32_t e, uint32_t m, uint32_t lane, unsigned long long& fma) {
     const uint32_t len = e - s;
     fma += len;
-    const uint32_t nch = (len + 31) >> 5;
+    const uint32_t nch = (len + 63) >> 6;
     uint32_t inc = nch;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += y; }
     const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;
     const uint32_t exc = inc - nch;
-    for (uint32_t c0 = 0; c0 < total; c0 += ELIM_DEPTH) {
-        uint2 v[ELIM_DEPTH];
-        uint32_t mm[ELIM_DEPTH];
-        bool ok[ELIM_DEPTH];
-#pragma unroll
-        for (int u = 0; u < ELIM_DEPTH; ++u) {
-            const uint32_t c = c0 + u;
-            // owner of chunk c: the last lane whose first chunk index is <= c
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+
+    auto issue = [&](uint32_t c) {
+        if (c < total) {
             const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
-            const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 32 + lane;
+            const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 64 + lane * 2;
             const uint32_t su = __shfl_sync(0xffffffffu, s, own);
             const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
-            mm[u] = __shfl_sync(0xffffffffu, m, own);
-            ok[u] = c < total && off < lu;
-            v[u] = make_uint2(0, 0);
-            if (ok[u]) v[u] = __ldg(ent + su + off);
+            cp_async16(ring_addr + (c % ELIM_DEPTH) * 512, a.ent + su + off, off < lu);
         }
-#pragma unroll
-        for (int u = 0; u < ELIM_DEPTH; ++u) {
-            if (c0 + u >= total) break;  // warp-uniform
-            if (ok[u]) elim_rmw<SMALLP>(acc, v[u], mm[u], p2);
-            __syncwarp();
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (uint32_t c = 0; c + 1 < ELIM_DEPTH; ++c) issue(c);
+#pragma unroll 1
+    for (uint32_t c = 0; c < total; ++c) {
+        issue(c + ELIM_DEPTH - 1);
+        cp_async_wait<ELIM_DEPTH - 1>();
+        const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
+        const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 64 + lane * 2;
+        const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
+        const uint32_t mu = __shfl_sync(0xffffffffu, m, own);
+        if (off < lu) {   // lu is a multiple of 4, off is even: both entries are inside (padding has value 0)
+            const uint4 q = *reinterpret_cast<const uint4*>(ring + (c % ELIM_DEPTH) * 128 + lane * 4);
+            if (q.y) Acc<SMALLP>::add(acc, q.x, Acc<SMALLP>::mulred(mu, q.y, a));
+            if (q.w) Acc<SMALLP>::add(acc, q.z, Acc<SMALLP>::mulred(mu, q.w, a));
         }
     }
+    cp_async_wait<0>();
+    __syncwarp();
 }
 
 template <bool SMALLP>
@@ -103,7 +178,10 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
     extern __shared__ __align__(16) unsigned char elim_smem[];
     const Layout& L = a.L;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t* acc = reinterpret_cast<uint64_t*>(elim_smem) + (size_t)warp * L.tile_cols;
+    constexpr int W = Acc<SMALLP>::WORDS;
+    const uint32_t acc_words = ((L.tile_cols + 1) * W + 3u) & ~3u;               // +1: the sink lane
+    uint32_t* acc = reinterpret_cast<uint32_t*>(elim_smem) + (size_t)warp * (acc_words + ELIM_SCRATCH_WORDS);
+    uint32_t* scr = acc + acc_words;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t p = a.f.p, nr = L.n_rows;
     const uint64_t p2 = a.f.p2;
@@ -129,19 +207,22 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             const uint32_t t0 = lay_tile_start(L, t), tw = lay_tile_width(L, t);
             const uint32_t* seg_s = a.seg + (uint64_t)t * nr;
             const uint32_t* seg_e = seg_s + nr;
-            for (uint32_t i = lane; i < tw; i += 32) acc[i] = 0;
+            for (uint32_t i = lane; i < acc_words; i += 32) acc[i] = 0;
             __syncwarp();
             {   // the row itself
                 const uint32_t s = seg_s[grow], e = seg_e[grow];
-                for (uint32_t k = s + lane; k < e; k += 32) { const uint2 en = __ldg(a.ent + k); acc[en.x] = en.y; }
+                for (uint32_t k = s + lane; k < e; k += 32) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x, en.y); }
                 __syncwarp();
             }
+            uint32_t absorbed = 1;   // rows added into this tile since the last normalisation
             // deferred pass over the pivots found in earlier tiles
             for (uint32_t base = 0; base < nlist; base += 32) {
                 const uint32_t i = base + lane;
                 uint32_t s = 0, e = 0, m = 0;
                 if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; e = seg_e[k]; }
-                elim_apply_batch<SMALLP>(acc, a.ent, s, e, m, lane, p2, fma);
+                if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, lane, a); absorbed = 1; }
+                absorbed += 32;
+                elim_apply_batch<SMALLP>(acc, scr, a, s, e, m, lane, fma);
             }
 
             if (t < L.n_tiles_piv) {
@@ -155,7 +236,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                     const uint32_t c = g * WINDOW + lane;
                     const uint32_t s = ps, e = pe;
                     if (g + 1 < nwin && k0 + WINDOW + lane < L.n_top) { ps = seg_s[k0 + WINDOW + lane]; pe = seg_e[k0 + WINDOW + lane]; }
-                    const uint32_t av = c < tw ? fp_reduce64(acc[c], a.f) : 0u;
+                    const uint32_t av = c < tw ? Acc<SMALLP>::get(acc, c, a) : 0u;
                     const uint32_t nza = __ballot_sync(0xffffffffu, av != 0);
                     if (nza == 0) continue;
                     uint32_t x = av;
@@ -164,8 +245,8 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                         const uint32_t* dg = a.diag + (uint64_t)(k0 / WINDOW) * WINDOW * WINDOW + lane;
                         uint64_t xa = av;
                         while (need) {
-                            int i0 = __ffs(need) - 1; need &= need - 1;
-                            int i1 = need ? __ffs(need) - 1 : -1; if (need) need &= need - 1;
+                            const int i0 = __ffs(need) - 1; need &= need - 1;
+                            const int i1 = need ? __ffs(need) - 1 : -1; if (need) need &= need - 1;
                             const uint32_t m0 = __ldg(dg + i0 * WINDOW);
                             const uint32_t m1 = i1 >= 0 ? __ldg(dg + i1 * WINDOW) : 0u;
                             xa = fp_mac<false>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);
@@ -183,13 +264,15 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                         fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
                     }
                     nlist += __popc(nzm);
-                    elim_apply_batch<SMALLP>(acc, a.ent, x ? s : 0u, x ? e : 0u, m, lane, p2, fma);
+                    if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, lane, a); absorbed = 1; }
+                    absorbed += 32;
+                    elim_apply_batch<SMALLP>(acc, scr, a, x ? s : 0u, x ? e : 0u, m, lane, fma);
                 }
                 __syncwarp();
             } else {
                 uint32_t* out = a.dprime + (uint64_t)li * L.n_nonpiv + (t0 - L.n_top);
                 for (uint32_t i = lane; i < tw; i += 32) {
-                    const uint32_t v = fp_reduce64(acc[i], a.f);
+                    const uint32_t v = Acc<SMALLP>::get(acc, i, a);
                     out[i] = v;
                     nz |= v != 0;
                 }

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) prep_count_kernel(PrepArgs a) {
             atomicAdd(&hist[lay_tile(a.L, c)], 1u);
         }
         __syncwarp();
-        for (uint32_t b = lane; b < nt; b += 32) a.cnt[(uint64_t)row * nt + b] = hist[b];
+        for (uint32_t b = lane; b < nt; b += 32) a.cnt[(uint64_t)row * nt + b] = (hist[b] + 3u) & ~3u;  // padded to 32 B
         if (row >= a.L.n_top) {
             for (int o = 16; o; o >>= 1) fp = min(fp, __shfl_xor_sync(0xffffffffu, fp, o));
             if (lane == 0) a.first_piv[row - a.L.n_top] = fp;
@@ -96,6 +96,10 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
         if (bin != 0xffffffffu && (peers >> lane) <= 1u) cur[bin] += __popc(peers);  // highest lane of the group
         __syncwarp();
     }
+    // pad every (row, tile) segment to a multiple of 4 entries with zero-valued entries aimed at the
+    // sink lane (index tile_cols) of the accumulator tile
+    for (uint32_t b = lane; b < nt; b += 32)
+        for (uint32_t pos = cur[b]; pos & 3u; ++pos) a.ent[pos] = make_uint2(a.L.tile_cols, 0u);
 }
 
 // One warp per window: replace the strictly-upper block N (A_ww = I + N, diagonal implicit) by the

@@ -1,7 +1,8 @@
 // Device layout of one staged F4 step (DESIGN.md "Data layout in HBM").
 //
 // The elimination kernel gives every row to reduce ONE WARP whose accumulator is
-// a tile of 64-bit lanes in shared memory. A full-width accumulator does not fit
+// a tile in shared memory (32-bit lanes updated with native shared-memory atomics:
+// one lane per column for p < 2^16, a lo/hi pair of lanes per column otherwise). A full-width accumulator does not fit
 // (n_cols * 8 B = 0.24 .. 1.6 MB for the named systems), and the
 // kernel is latency-bound, so many independent rows must be in flight per SM:
 // the column range is cut into TILES of T columns (T * 8 B of shared memory per
@@ -9,7 +10,10 @@
 //
 // Pivot rows (A|B) and rows to reduce (C|D) are therefore stored re-tiled:
 //   ent[]      (tile-relative column, value) pairs, grouped per row by tile,
-//              ascending column inside a tile
+//              ascending column inside a tile; every (row, tile) segment starts on
+//              a 32-byte boundary and is padded to a multiple of 4 entries with
+//              (tile_cols, 0) — a zero aimed at the tile's sink lane — so that a
+//              lane can stream its segment with 32-byte sector loads
 //   seg[]      seg[t * n_rows + row] = first entry of (row, tile t); plane n_tiles
 //              holds the row end. Tile-major so that 32 consecutive pivot rows
 //              (one window) or a run of applied pivots read coalesced.
