@@ -77,7 +77,7 @@ struct gamba_cuda_engine {
     cudaEvent_t ev[6]{};
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
-    int64_t opt_warps_per_sm = 0;
+    int64_t opt_ctas_per_sm = 0;
 
     // staged step
     bool staged = false;
@@ -130,12 +130,11 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     // Tile width from the number of rows (= warps) wanted in flight per SM: the kernel is
     // latency-bound, shared memory per SM / (warps per SM) is what one accumulator tile gets.
     const uint32_t gran = WINDOW;
-    const uint32_t want_warps = (uint32_t)std::max<int64_t>(ELIM_CTA_WARPS, opt_warps_per_sm > 0 ? opt_warps_per_sm : 12);
-    const uint32_t ctas = std::max(1u, want_warps / ELIM_CTA_WARPS);
+    const uint32_t ctas = (uint32_t)std::max<int64_t>(1, opt_ctas_per_sm > 0 ? opt_ctas_per_sm : 4);
     const size_t per_cta = std::min<size_t>(((size_t)smem_per_sm / ctas) - 1024 - 64, (size_t)max_smem_optin - 64);
     const uint32_t words_per_col = f.small ? 1u : 2u;   // kernels_elim.cuh: Acc<SMALLP>::WORDS
-    const size_t warp_words = per_cta / sizeof(uint32_t) / ELIM_CTA_WARPS;
-    uint32_t tmax = (uint32_t)((warp_words - ELIM_SCRATCH_WORDS - 4) / words_per_col - 1) / gran * gran;
+    const size_t cta_words = per_cta / sizeof(uint32_t) - (size_t)ELIM_CTA_WARPS * ELIM_SCRATCH_WORDS;
+    uint32_t tmax = (uint32_t)((cta_words - 4) / words_per_col - 1) / gran * gran;
     if (opt_tile_cols > 0) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
     auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
     // pivot tiles of equal width; the non-pivot range is cut with the same width
@@ -256,16 +255,15 @@ void gamba_cuda_engine::eliminate() {
 
     const uint32_t words_per_col = f.small ? 1u : 2u;
     const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
-    const size_t smem = (size_t)ELIM_CTA_WARPS * (acc_words + ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
+    const size_t smem = (acc_words + (size_t)ELIM_CTA_WARPS * ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
     auto kern = f.small ? elim_kernel<true> : elim_kernel<false>;
     GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ELIM_CTA_THREADS, smem));
     if (occ < 1) throw std::runtime_error("elimination kernel does not fit on an SM");
-    if (opt_warps_per_sm > 0) occ = std::min<int>(occ, std::max<int>(1, (int)opt_warps_per_sm / ELIM_CTA_WARPS));
-    const int want_ctas = (int)((std::max(1u, n_local) + ELIM_CTA_WARPS - 1) / ELIM_CTA_WARPS);
-    elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, want_ctas));
-    const uint64_t n_slots = (uint64_t)elim_grid * ELIM_CTA_WARPS;
+    if (opt_ctas_per_sm > 0) occ = std::min<int>(occ, (int)opt_ctas_per_sm);
+    elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
+    const uint64_t n_slots = (uint64_t)elim_grid;
 
     d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.n_nonpiv, 1) * sizeof(uint32_t));
     d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
@@ -484,7 +482,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
     return guarded([&] {
         const std::string k = key ? key : "";
         if (k == "tile_cols") e->opt_tile_cols = value;
-        else if (k == "warps_per_sm") e->opt_warps_per_sm = value;
+        else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
         else throw std::runtime_error("unknown option " + k);
     });
 }

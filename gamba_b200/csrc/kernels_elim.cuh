@@ -2,14 +2,19 @@
 // against the pivot rows (role of the reference's closed kernel/reduce_u16|u32,
 // kernel/saxpy, kernel/modular_u16|u32 translation units, CMakeLists.txt:81-90).
 //
-// ONE WARP PER ROW, rows pulled from an atomic queue (most expensive first), as
-// many warps resident per SM as shared memory allows. History:
+// ONE CTA PER ROW IN FLIGHT (ELIM_CTA_WARPS warps sharing one accumulator tile),
+// rows pulled from an atomic queue (most expensive first), as many CTAs resident
+// per SM as shared memory allows. History:
 //   v1  one CTA per row, 64-bit lanes, warp-per-segment        90 ms  (kat12-15 step 9)
 //       -> 12 % active warps, 93 % L2 hits: latency-bound, not HBM-bound
 //   v2  one warp per row, pipelined 32-entry chunks             35 ms
 //       -> ~25 instructions per half-empty chunk: issue-bound per warp
 //   v3  lane per segment + native 32-bit shared-memory atomics   54 ms
-//   v4  (this file) v2's chunk stream staged by cp.async + v3's atomic 32-bit lanes
+//   v4  one warp per row, chunk stream staged by cp.async, atomic lanes   51 ms
+//       -> a single warp retires one 64-entry chunk per ~450 cycles whatever the
+//          load depth: instruction latency per warp, so a row needs several warps
+//   v5  (this file) v4's stream dealt round-robin to the warps of a CTA; the native
+//       32-bit atomics make concurrent updates of the shared tile by all warps safe
 //
 // The row's accumulator is a tile in shared memory with DELAYED REDUCTION:
 //   p < 2^16   one 32-bit lane per column; a multiply-add adds (m*v mod p) < 2^16
@@ -41,9 +46,9 @@
 
 namespace gcu {
 
-constexpr int ELIM_CTA_WARPS = 4;
+constexpr int ELIM_CTA_WARPS = 8;
 constexpr int ELIM_CTA_THREADS = ELIM_CTA_WARPS * 32;
-constexpr int ELIM_DEPTH = 8;             // cp.async ring slots per warp (512 B each)
+constexpr int ELIM_DEPTH = 4;             // cp.async ring slots per warp (512 B each)
 constexpr int ELIM_SCRATCH_WORDS = ELIM_DEPTH * 128;   // per warp: the ring
 
 struct ElimArgs {
@@ -58,8 +63,8 @@ struct ElimArgs {
     const uint32_t* first_piv;
     uint32_t* dprime;            // [n_local][n_nonpiv] standard residues
     uint32_t* row_nz;            // [n_local] 1 iff the reduced row is non-zero
-    uint32_t* list_k;            // [warps in grid][n_top] pivot columns applied so far
-    uint32_t* list_m;            // [warps in grid][n_top] their multipliers (p - x)
+    uint32_t* list_k;            // [gridDim][n_top] pivot columns applied so far
+    uint32_t* list_m;            // [gridDim][n_top] their multipliers (p - x)
     uint32_t* queue;             // atomic row counter
     uint32_t row_begin, row_step, n_local;  // rows r = row_begin + i * row_step, i < n_local
     const uint64_t* row_ptr;     // block-form CSR row pointers (for the fma_top invariant)
@@ -106,10 +111,10 @@ template <> struct Acc<false> {  // p < 2^31: lo/hi pair of u32 lanes per column
 
 // Bring every lane of the tile back below p (delayed reduction: done rarely).
 template <bool SMALLP>
-__device__ __forceinline__ void elim_normalise(uint32_t* acc, uint32_t tw, uint32_t lane, const ElimArgs& a) {
-    __syncwarp();
-    for (uint32_t i = lane; i < tw; i += 32) Acc<SMALLP>::set(acc, i, Acc<SMALLP>::get(acc, i, a));
-    __syncwarp();
+__device__ __forceinline__ void elim_normalise(uint32_t* acc, uint32_t tw, const ElimArgs& a) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < tw; i += ELIM_CTA_THREADS) Acc<SMALLP>::set(acc, i, Acc<SMALLP>::get(acc, i, a));
+    __syncthreads();
 }
 
 // ---- asynchronous staging of pivot-row entries (LDGSTS) ---------------------------------------
@@ -131,69 +136,75 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ONE pivot row: coalesced, and each lane reads back exactly the 16 B it copied itself.
 template <bool SMALLP>
 __device__ __forceinline__ void elim_apply_batch(uint32_t* acc, uint32_t* ring, const ElimArgs& a, uint32_t s,
-                                                 uint32_t e, uint32_t m, uint32_t lane, unsigned long long& fma) {
+                                                 uint32_t e, uint32_t m, uint32_t lane, uint32_t warp,
+                                                 unsigned long long& fma) {
     const uint32_t len = e - s;
-    fma += len;
+    if (warp == 0) fma += len;
     const uint32_t nch = (len + 63) >> 6;
     uint32_t inc = nch;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += y; }
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    if (total == 0) return;
+    const uint32_t all = __shfl_sync(0xffffffffu, inc, 31);
+    if (all <= warp) return;
     const uint32_t exc = inc - nch;
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    // this warp's share of the chunk stream: chunks warp, warp + W, warp + 2W, ... (local index c)
+    const uint32_t total = (all - warp + ELIM_CTA_WARPS - 1) / ELIM_CTA_WARPS;
+    auto chunk_of = [&](uint32_t c) { return warp + c * ELIM_CTA_WARPS; };
 
-    auto issue = [&](uint32_t c) {
-        if (c < total) {
+    auto issue = [&](uint32_t cl) {
+        if (cl < total) {
+            const uint32_t c = chunk_of(cl);
             const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
             const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 64 + lane * 2;
             const uint32_t su = __shfl_sync(0xffffffffu, s, own);
             const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
-            cp_async16(ring_addr + (c % ELIM_DEPTH) * 512, a.ent + su + off, off < lu);
+            cp_async16(ring_addr + (cl % ELIM_DEPTH) * 512, a.ent + su + off, off < lu);
         }
         cp_async_commit();
     };
 #pragma unroll 1
     for (uint32_t c = 0; c + 1 < ELIM_DEPTH; ++c) issue(c);
 #pragma unroll 1
-    for (uint32_t c = 0; c < total; ++c) {
-        issue(c + ELIM_DEPTH - 1);
+    for (uint32_t cl = 0; cl < total; ++cl) {
+        issue(cl + ELIM_DEPTH - 1);
         cp_async_wait<ELIM_DEPTH - 1>();
+        const uint32_t c = chunk_of(cl);
         const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
         const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 64 + lane * 2;
         const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
         const uint32_t mu = __shfl_sync(0xffffffffu, m, own);
         if (off < lu) {   // lu is a multiple of 4, off is even: both entries are inside (padding has value 0)
-            const uint4 q = *reinterpret_cast<const uint4*>(ring + (c % ELIM_DEPTH) * 128 + lane * 4);
+            const uint4 q = *reinterpret_cast<const uint4*>(ring + (cl % ELIM_DEPTH) * 128 + lane * 4);
             if (q.y) Acc<SMALLP>::add(acc, q.x, Acc<SMALLP>::mulred(mu, q.y, a));
             if (q.w) Acc<SMALLP>::add(acc, q.z, Acc<SMALLP>::mulred(mu, q.w, a));
         }
     }
     cp_async_wait<0>();
-    __syncwarp();
 }
 
 template <bool SMALLP>
 __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
     extern __shared__ __align__(16) unsigned char elim_smem[];
+    __shared__ uint32_t s_q;
     const Layout& L = a.L;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int W = Acc<SMALLP>::WORDS;
     const uint32_t acc_words = ((L.tile_cols + 1) * W + 3u) & ~3u;               // +1: the sink lane
-    uint32_t* acc = reinterpret_cast<uint32_t*>(elim_smem) + (size_t)warp * (acc_words + ELIM_SCRATCH_WORDS);
-    uint32_t* scr = acc + acc_words;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(elim_smem);
+    uint32_t* ring = acc + acc_words + warp * ELIM_SCRATCH_WORDS;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t p = a.f.p, nr = L.n_rows;
     const uint64_t p2 = a.f.p2;
-    const uint64_t slot = (uint64_t)blockIdx.x * ELIM_CTA_WARPS + warp;
-    uint32_t* lk = a.list_k + slot * L.n_top;
-    uint32_t* lm = a.list_m + slot * L.n_top;
+    uint32_t* lk = a.list_k + (uint64_t)blockIdx.x * L.n_top;
+    uint32_t* lm = a.list_m + (uint64_t)blockIdx.x * L.n_top;
     unsigned long long fma = 0, npiv = 0, fma_top = 0;
 
     for (;;) {
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(a.queue, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(a.queue, 1u);
+        __syncthreads();
+        const uint32_t q = s_q;
         if (q >= a.n_local) break;
         const uint32_t li = a.n_local - 1 - q;                 // later rows have smaller leads: more work
         const uint32_t r = a.row_begin + li * a.row_step;      // index among the rows to reduce
@@ -207,23 +218,24 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             const uint32_t t0 = lay_tile_start(L, t), tw = lay_tile_width(L, t);
             const uint32_t* seg_s = a.seg + (uint64_t)t * nr;
             const uint32_t* seg_e = seg_s + nr;
-            for (uint32_t i = lane; i < acc_words; i += 32) acc[i] = 0;
-            __syncwarp();
+            for (uint32_t i = tid; i < acc_words; i += ELIM_CTA_THREADS) acc[i] = 0;
+            __syncthreads();
             {   // the row itself
                 const uint32_t s = seg_s[grow], e = seg_e[grow];
-                for (uint32_t k = s + lane; k < e; k += 32) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x, en.y); }
-                __syncwarp();
+                for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x, en.y); }
             }
+            __syncthreads();
             uint32_t absorbed = 1;   // rows added into this tile since the last normalisation
-            // deferred pass over the pivots found in earlier tiles
+            // deferred pass over the pivots found in earlier tiles (batches commute: no barrier between them)
             for (uint32_t base = 0; base < nlist; base += 32) {
                 const uint32_t i = base + lane;
                 uint32_t s = 0, e = 0, m = 0;
                 if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; e = seg_e[k]; }
-                if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, lane, a); absorbed = 1; }
+                if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
                 absorbed += 32;
-                elim_apply_batch<SMALLP>(acc, scr, a, s, e, m, lane, fma);
+                elim_apply_batch<SMALLP>(acc, ring, a, s, e, m, lane, warp, fma);
             }
+            __syncthreads();
 
             if (t < L.n_tiles_piv) {
                 const uint32_t nwin = (tw + WINDOW - 1) / WINDOW;
@@ -232,13 +244,14 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                 uint32_t ps = 0, pe = 0;
                 if (g < nwin && t0 + g * WINDOW + lane < L.n_top) { ps = seg_s[t0 + g * WINDOW + lane]; pe = seg_e[t0 + g * WINDOW + lane]; }
                 for (; g < nwin; ++g) {
+                    // every warp derives the window's multipliers itself (identical results, no broadcast)
                     const uint32_t k0 = t0 + g * WINDOW;
                     const uint32_t c = g * WINDOW + lane;
                     const uint32_t s = ps, e = pe;
                     if (g + 1 < nwin && k0 + WINDOW + lane < L.n_top) { ps = seg_s[k0 + WINDOW + lane]; pe = seg_e[k0 + WINDOW + lane]; }
                     const uint32_t av = c < tw ? Acc<SMALLP>::get(acc, c, a) : 0u;
                     const uint32_t nza = __ballot_sync(0xffffffffu, av != 0);
-                    if (nza == 0) continue;
+                    if (nza == 0) continue;           // CTA-uniform: all warps read the same lanes
                     uint32_t x = av;
                     uint32_t need = nza & a.dnz[k0 / WINDOW];
                     if (need) {   // x = a * (I + M): add a_i * M[i][lane] for the flagged rows i
@@ -255,38 +268,39 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                         x = fp_reduce64(xa, a.f);
                     }
                     const uint32_t nzm = __ballot_sync(0xffffffffu, x != 0);
-                    if (nzm == 0) continue;
+                    if (nzm == 0) continue;           // CTA-uniform
                     uint32_t m = 0;
                     if (x) {
-                        const uint32_t i = nlist + __popc(nzm & lt);
                         m = p - x;
-                        lk[i] = k0 + lane; lm[i] = m;
-                        fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
+                        if (warp == 0) {
+                            const uint32_t i = nlist + __popc(nzm & lt);
+                            lk[i] = k0 + lane; lm[i] = m;
+                            fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
+                        }
                     }
                     nlist += __popc(nzm);
-                    if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, lane, a); absorbed = 1; }
+                    if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
                     absorbed += 32;
-                    elim_apply_batch<SMALLP>(acc, scr, a, x ? s : 0u, x ? e : 0u, m, lane, fma);
+                    elim_apply_batch<SMALLP>(acc, ring, a, x ? s : 0u, x ? e : 0u, m, lane, warp, fma);
+                    __syncthreads();                  // the next window is read after all warps' updates
                 }
-                __syncwarp();
             } else {
                 uint32_t* out = a.dprime + (uint64_t)li * L.n_nonpiv + (t0 - L.n_top);
-                for (uint32_t i = lane; i < tw; i += 32) {
+                for (uint32_t i = tid; i < tw; i += ELIM_CTA_THREADS) {
                     const uint32_t v = Acc<SMALLP>::get(acc, i, a);
                     out[i] = v;
                     nz |= v != 0;
                 }
-                __syncwarp();
             }
         }
-        const int any = __any_sync(0xffffffffu, nz);
-        if (lane == 0) a.row_nz[li] = any ? 1u : 0u;
-        npiv += lane == 0 ? nlist : 0;
+        const int any = __syncthreads_or(nz ? 1 : 0);
+        if (tid == 0) a.row_nz[li] = any ? 1u : 0u;
+        npiv += tid == 0 ? nlist : 0;
     }
     for (int o = 16; o; o >>= 1) fma += __shfl_xor_sync(0xffffffffu, fma, o);
-    if (lane == 0 && fma) atomicAdd(a.stats + 1, fma);
+    if (tid == 0 && fma) atomicAdd(a.stats + 1, fma);
     if (npiv) atomicAdd(a.stats + 0, npiv);
-    if (fma_top) atomicAdd(a.stats + 2, fma_top);
+    if (warp == 0 && fma_top) atomicAdd(a.stats + 2, fma_top);
 }
 
 }  // namespace gcu
