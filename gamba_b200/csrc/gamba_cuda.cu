@@ -320,7 +320,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
     GCU_CHECK(cudaEventRecord(ev[4], stream));
     if (nr && nc) {
-        d_lead.ensure((size_t)2 * nr * sizeof(uint32_t));
+        d_lead.ensure((size_t)3 * nr * sizeof(uint32_t));
         d_nz_list.ensure((size_t)nr * sizeof(uint32_t));
         d_piv_row.ensure((size_t)nr * sizeof(uint32_t));
         d_piv_col.ensure((size_t)nr * sizeof(uint32_t));
@@ -329,7 +329,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         EchArgs ea{};
         ea.f = f; ea.n_rows = nr; ea.n_cols = nc;
         ea.d = d_dprime.as<uint32_t>(); ea.row_nz = d_row_nz.as<uint32_t>();
-        ea.lead = d_lead.as<uint32_t>(); ea.nz_list = d_nz_list.as<uint32_t>();
+        ea.lead = d_lead.as<uint32_t>(); ea.inv_lead = d_lead.as<uint32_t>() + (size_t)2 * nr; ea.nz_list = d_nz_list.as<uint32_t>();
         ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
         ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
         ea.out_ptr = d_out_ptr.as<uint64_t>();

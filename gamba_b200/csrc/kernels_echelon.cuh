@@ -3,7 +3,8 @@
 // dense -> sparse compaction of the new rows (open reference code:
 // source/matrix.hpp:820-880).
 //
-// Exact Gauss-Jordan as ONE cooperative kernel, one grid barrier per pivot:
+// Exact Gauss-Jordan as ONE cooperative kernel, one grid barrier per pivot (a variant clearing 8
+// pivots per pass against a snapshotted panel was bit-exact but 1.8x slower on cyclic9-15):
 // every CTA re-derives the next pivot (left-most lead among the remaining
 // rows) from the double-buffered lead table, so selection needs no barrier of
 // its own; the pivot column is never written during an update (it is "dead"
@@ -29,6 +30,7 @@ struct EchArgs {
     uint32_t* d;
     const uint32_t* row_nz;         // [n_rows]
     uint32_t* lead;                 // [2][n_rows]
+    uint32_t* inv_lead;             // [n_rows] inverse of the row's lead value
     uint32_t* nz_list;              // [n_rows] rows that are not identically zero
     uint32_t* piv_row;              // [n_rows]
     uint32_t* piv_col;              // [n_rows]
@@ -82,17 +84,25 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* sh) {
     return v;
 }
 
+constexpr int ECH_GROUP = 128;                       // threads that update one row together
+constexpr int ECH_GROUPS = ECH_THREADS / ECH_GROUP;
+
+__device__ __forceinline__ void group_bar(uint32_t grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(ECH_GROUP) : "memory");
+}
+
 __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ uint64_t sh64[32];
     __shared__ uint32_t sh32[32];
-    __shared__ uint32_t s_inv;
+    __shared__ uint32_t sh_grp[ECH_GROUPS][4];
     const uint32_t tid = threadIdx.x, nb = gridDim.x, bid = blockIdx.x;
+    const uint32_t grp = tid / ECH_GROUP, gt = tid % ECH_GROUP, gw = gt >> 5;
     const uint32_t nr = a.n_rows, nc = a.n_cols, p = a.f.p;
     uint32_t* lead0 = a.lead;
     uint32_t* lead1 = a.lead + nr;
 
-    // leads of the rows (block per row) and the list of non-zero rows
+    // leads of the rows (block per row), the inverse of every lead value, the list of non-zero rows
     for (uint32_t r = bid; r < nr; r += nb) {
         uint32_t l = ECH_INF;
         if (a.row_nz[r]) {
@@ -101,6 +111,7 @@ __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
                 const uint32_t j = j0 + tid;
                 l = block_min_u32(j < nc && row[j] ? j : ECH_INF, sh32);
             }
+            if (tid == 0 && l != ECH_INF) a.inv_lead[r] = fp_inv32(row[l], p);
         }
         if (tid == 0) lead0[r] = l;
     }
@@ -129,29 +140,44 @@ __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
         const uint32_t c = (uint32_t)(key >> 32);
         const uint32_t pr = a.nz_list[(uint32_t)key];
         const uint32_t* prow = a.d + (uint64_t)pr * nc;
-        if (tid == 0) s_inv = fp_inv32(prow[c], p);
+        const uint32_t inv = a.inv_lead[pr];
         if (bid == 0 && tid == 0) { a.piv_row[step] = pr; a.piv_col[step] = c; a.is_piv_col[c] = 1; }
-        __syncthreads();
-        const uint32_t inv = s_inv;
-        for (uint32_t i = bid; i < nnz_rows; i += nb) {
+        // rows are dealt to groups of 128 threads: 4 rows per CTA in flight
+        for (uint32_t i = bid * ECH_GROUPS + grp; i < nnz_rows; i += nb * ECH_GROUPS) {
             const uint32_t r = a.nz_list[i];
-            if (r == pr) { if (tid == 0) ln[r] = ECH_INF; continue; }
+            if (r == pr) { if (gt == 0) ln[r] = ECH_INF; continue; }
             uint32_t* row = a.d + (uint64_t)r * nc;
             const uint32_t fv = row[c];
             const uint32_t lr = lc[r];
-            if (fv == 0) { if (tid == 0) ln[r] = lr; continue; }
+            if (fv == 0) { if (gt == 0) ln[r] = lr; continue; }
             const uint32_t mult = p - fp_mul(fv, inv, a.f);
             uint32_t nl = ECH_INF;
-            for (uint32_t j = c + 1 + tid; j < nc; j += ECH_THREADS) {
-                const uint32_t pv = prow[j];
-                uint32_t v = row[j];
-                if (pv) { v = fp_reduce64((uint64_t)v + (uint64_t)mult * pv, a.f); row[j] = v; }
-                if (v && nl == ECH_INF) nl = j;
+            for (uint32_t j0 = c + 1; j0 < nc; j0 += 4 * ECH_GROUP) {
+                uint32_t pv[4], v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + u * ECH_GROUP + gt;
+                    pv[u] = j < nc ? prow[j] : 0u;
+                    v[u] = j < nc ? row[j] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + u * ECH_GROUP + gt;
+                    if (pv[u]) { v[u] = fp_reduce64((uint64_t)v[u] + (uint64_t)mult * pv[u], a.f); row[j] = v[u]; }
+                    if (v[u] && nl == ECH_INF) nl = j;
+                }
             }
-            if (lr != ECH_INF) {            // a remaining row: its lead was c, find the new one
-                nl = block_min_u32(nl, sh32);
-                if (tid == 0) ln[r] = nl;
-            } else if (tid == 0) ln[r] = ECH_INF;
+            if (lr != ECH_INF) {            // a remaining row: its lead was c, find the new one (and its inverse)
+                for (int o = 16; o; o >>= 1) nl = min(nl, __shfl_xor_sync(0xffffffffu, nl, o));
+                if ((gt & 31) == 0) sh_grp[grp][gw] = nl;
+                group_bar(grp);             // also orders the row[] stores before the read below
+                if (gt == 0) {
+                    nl = min(min(sh_grp[grp][0], sh_grp[grp][1]), min(sh_grp[grp][2], sh_grp[grp][3]));
+                    ln[r] = nl;
+                    if (nl != ECH_INF) a.inv_lead[r] = fp_inv32(row[nl], p);
+                }
+                group_bar(grp);
+            } else if (gt == 0) ln[r] = ECH_INF;
         }
         grid.sync();
     }
