@@ -128,57 +128,60 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Apply up to 32 pivot-row segments (lane i holds segment i: entries [s,e), multiplier m).
-// The segments are cut into CHUNKS of 64 consecutive entries (512 B, 16 B per lane) and the chunk
-// stream of the batch runs through a ring of ELIM_DEPTH shared-memory slots filled by cp.async:
-// ELIM_DEPTH x 512 B per warp are in flight at no register cost (a row's elimination is a chain of
-// ~1 us round trips, its speed is bytes in flight). A chunk is all lanes on consecutive entries of
-// ONE pivot row: coalesced, and each lane reads back exactly the 16 B it copied itself.
-template <bool SMALLP>
-__device__ __forceinline__ void elim_apply_batch(uint32_t* acc, uint32_t* ring, const ElimArgs& a, uint32_t s,
-                                                 uint32_t e, uint32_t m, uint32_t lane, uint32_t warp,
-                                                 unsigned long long& fma) {
-    const uint32_t len = e - s;
-    if (warp == 0) fma += len;
-    const uint32_t nch = (len + 63) >> 6;
-    uint32_t inc = nch;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += y; }
-    const uint32_t all = __shfl_sync(0xffffffffu, inc, 31);
-    if (all <= warp) return;
-    const uint32_t exc = inc - nch;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
-    // this warp's share of the chunk stream: chunks warp, warp + W, warp + 2W, ... (local index c)
-    const uint32_t total = (all - warp + ELIM_CTA_WARPS - 1) / ELIM_CTA_WARPS;
-    auto chunk_of = [&](uint32_t c) { return warp + c * ELIM_CTA_WARPS; };
+// Apply the pivot-row segments selected by `mask` (lane i holds segment i: entries [s, s+len),
+// multiplier m). The segments are walked in lane order and cut into CHUNKS of 64 consecutive
+// entries (512 B, 16 B per lane) that run through the warp's ring of ELIM_DEPTH shared-memory
+// slots filled by cp.async: ELIM_DEPTH x 512 B in flight per warp at no register cost. A chunk is
+// all lanes on consecutive entries of ONE pivot row: coalesced, and each lane reads back exactly
+// the 16 B it copied itself. Two warp-uniform cursors (issue side, consume side) walk the same
+// chunk sequence, so the per-chunk bookkeeping is a compare and an add (profiles/r01_v5: the
+// previous form recomputed the chunk owner with ballot/popc/shuffles and was issue-bound).
+struct ChunkCursor {
+    uint32_t mask, s, len, m, off;
+};
 
-    auto issue = [&](uint32_t cl) {
-        if (cl < total) {
-            const uint32_t c = chunk_of(cl);
-            const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
-            const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 64 + lane * 2;
-            const uint32_t su = __shfl_sync(0xffffffffu, s, own);
-            const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
-            cp_async16(ring_addr + (cl % ELIM_DEPTH) * 512, a.ent + su + off, off < lu);
+__device__ __forceinline__ bool cursor_next(ChunkCursor& c, uint32_t s, uint32_t len, uint32_t m) {
+    if (c.off >= c.len) {
+        if (c.mask == 0) return false;
+        const int o = __ffs(c.mask) - 1;
+        c.mask &= c.mask - 1;
+        c.s = __shfl_sync(0xffffffffu, s, o);
+        c.len = __shfl_sync(0xffffffffu, len, o);
+        c.m = __shfl_sync(0xffffffffu, m, o);
+        c.off = 0;
+    }
+    return true;
+}
+
+template <bool SMALLP>
+__device__ __forceinline__ void elim_apply_segments(uint32_t* acc, uint32_t* ring, const ElimArgs& a, uint32_t s,
+                                                    uint32_t len, uint32_t m, uint32_t mask, uint32_t lane) {
+    if (mask == 0) return;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    ChunkCursor ci{mask, 0, 0, 0, 0}, cc{mask, 0, 0, 0, 0};
+    uint32_t islot = 0, cslot = 0;
+    auto issue = [&]() {
+        if (cursor_next(ci, s, len, m)) {
+            const uint32_t off = ci.off + lane * 2;
+            cp_async16(ring_addr + islot * 512, a.ent + ci.s + off, off < ci.len);
+            ci.off += 64;
         }
         cp_async_commit();
+        islot = islot + 1 == ELIM_DEPTH ? 0 : islot + 1;
     };
-#pragma unroll 1
-    for (uint32_t c = 0; c + 1 < ELIM_DEPTH; ++c) issue(c);
-#pragma unroll 1
-    for (uint32_t cl = 0; cl < total; ++cl) {
-        issue(cl + ELIM_DEPTH - 1);
+#pragma unroll
+    for (int i = 0; i + 1 < ELIM_DEPTH; ++i) issue();
+    while (cursor_next(cc, s, len, m)) {
+        issue();
         cp_async_wait<ELIM_DEPTH - 1>();
-        const uint32_t c = chunk_of(cl);
-        const int own = __popc(__ballot_sync(0xffffffffu, exc <= c)) - 1;
-        const uint32_t off = (c - __shfl_sync(0xffffffffu, exc, own)) * 64 + lane * 2;
-        const uint32_t lu = __shfl_sync(0xffffffffu, len, own);
-        const uint32_t mu = __shfl_sync(0xffffffffu, m, own);
-        if (off < lu) {   // lu is a multiple of 4, off is even: both entries are inside (padding has value 0)
-            const uint4 q = *reinterpret_cast<const uint4*>(ring + (cl % ELIM_DEPTH) * 128 + lane * 4);
-            if (q.y) Acc<SMALLP>::add(acc, q.x, Acc<SMALLP>::mulred(mu, q.y, a));
-            if (q.w) Acc<SMALLP>::add(acc, q.z, Acc<SMALLP>::mulred(mu, q.w, a));
+        const uint32_t off = cc.off + lane * 2;
+        if (off < cc.len) {   // len is a multiple of 4, off is even: both entries are inside (padding has value 0)
+            const uint4 q = *reinterpret_cast<const uint4*>(ring + cslot * 128 + lane * 4);
+            if (q.y) Acc<SMALLP>::add(acc, q.x, Acc<SMALLP>::mulred(cc.m, q.y, a));
+            if (q.w) Acc<SMALLP>::add(acc, q.z, Acc<SMALLP>::mulred(cc.m, q.w, a));
         }
+        cc.off += 64;
+        cslot = cslot + 1 == ELIM_DEPTH ? 0 : cslot + 1;
     }
     cp_async_wait<0>();
 }
@@ -226,14 +229,16 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             }
             __syncthreads();
             uint32_t absorbed = 1;   // rows added into this tile since the last normalisation
-            // deferred pass over the pivots found in earlier tiles (batches commute: no barrier between them)
-            for (uint32_t base = 0; base < nlist; base += 32) {
-                const uint32_t i = base + lane;
-                uint32_t s = 0, e = 0, m = 0;
-                if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; e = seg_e[k]; }
-                if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
-                absorbed += 32;
-                elim_apply_batch<SMALLP>(acc, ring, a, s, e, m, lane, warp, fma);
+            // deferred pass over the pivots found in earlier tiles
+            // (batches of 32 pivots are dealt to the warps; they commute, no barrier between them)
+            for (uint32_t base0 = 0; base0 < nlist; base0 += 32 * ELIM_CTA_WARPS) {
+                if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
+                absorbed += 32 * ELIM_CTA_WARPS;
+                const uint32_t i = base0 + warp * 32 + lane;
+                uint32_t s = 0, len = 0, m = 0;
+                if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; len = seg_e[k] - s; }
+                fma += len;
+                elim_apply_segments<SMALLP>(acc, ring, a, s, len, m, __ballot_sync(0xffffffffu, len != 0), lane);
             }
             __syncthreads();
 
@@ -281,7 +286,11 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                     nlist += __popc(nzm);
                     if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
                     absorbed += 32;
-                    elim_apply_batch<SMALLP>(acc, ring, a, x ? s : 0u, x ? e : 0u, m, lane, warp, fma);
+                    // the window's non-zero pivot rows are dealt to the warps by rank
+                    const uint32_t len = x ? e - s : 0u;
+                    const bool mine = len != 0 && (__popc(nzm & lt) % ELIM_CTA_WARPS) == warp;
+                    if (mine) fma += len;
+                    elim_apply_segments<SMALLP>(acc, ring, a, s, len, m, __ballot_sync(0xffffffffu, mine), lane);
                     __syncthreads();                  // the next window is read after all warps' updates
                 }
             } else {
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
         npiv += tid == 0 ? nlist : 0;
     }
     for (int o = 16; o; o >>= 1) fma += __shfl_xor_sync(0xffffffffu, fma, o);
-    if (tid == 0 && fma) atomicAdd(a.stats + 1, fma);
+    if (lane == 0 && fma) atomicAdd(a.stats + 1, fma);
     if (npiv) atomicAdd(a.stats + 0, npiv);
     if (warp == 0 && fma_top) atomicAdd(a.stats + 2, fma_top);
 }
