@@ -280,7 +280,9 @@ void gamba_cuda_engine::eliminate() {
     ElimArgs ea{};
     ea.L = L; ea.f = f;
     ea.mu32 = (uint32_t)((1ull << 32) / f.p);
-    ea.norm_every = f.small ? (uint32_t)std::min<uint64_t>(0xffffffffull / (f.p - 1) - 34, 1u << 30) : 65536u - 34u;
+    ea.negp = 0u - f.p;
+    // every add is < 2p (p < 2^16, lazy Barrett) or < 2^16 (lo/hi halves): normalise before 2^32 is reached
+    ea.norm_every = f.small ? (uint32_t)std::min<uint64_t>(0xffffffffull / (2ull * f.p) - 8 * 32 - 2, 1u << 30) : 65536u - 8 * 32 - 2;
     ea.seg = d_seg.as<uint32_t>(); ea.ent = d_ent.as<uint2>(); ea.diag = d_diag.as<uint32_t>();
     ea.dnz = d_dnz.as<uint32_t>();
     ea.first_piv = d_first.as<uint32_t>();
@@ -316,9 +318,8 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     const uint32_t nr = n_gather_rows, nc = L.n_nonpiv;
     uint32_t npiv = 0;
     uint64_t nnz_new = 0;
-    d_counts.ensure(256);
-    GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 32, stream));
-    GCU_CHECK(cudaMemsetAsync(d_counts.as<char>() + 32, 0xff, 32, stream));
+    d_counts.ensure(64);
+    GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
     GCU_CHECK(cudaEventRecord(ev[4], stream));
     if (nr && nc) {
         d_lead.ensure((size_t)3 * nr * sizeof(uint32_t));
@@ -330,8 +331,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         EchArgs ea{};
         ea.f = f; ea.n_rows = nr; ea.n_cols = nc;
         ea.d = d_dprime.as<uint32_t>(); ea.row_nz = d_row_nz.as<uint32_t>();
-        ea.lead = d_lead.as<uint32_t>(); ea.inv_lead = d_lead.as<uint32_t>() + (size_t)2 * nr;
-        ea.best = reinterpret_cast<unsigned long long*>(d_counts.as<char>() + 32); ea.nz_list = d_nz_list.as<uint32_t>();
+        ea.lead = d_lead.as<uint32_t>(); ea.inv_lead = d_lead.as<uint32_t>() + (size_t)2 * nr; ea.nz_list = d_nz_list.as<uint32_t>();
         ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
         ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
         ea.out_ptr = d_out_ptr.as<uint64_t>();

@@ -21,7 +21,7 @@
 namespace gcu {
 namespace cg = cooperative_groups;
 
-constexpr int ECH_THREADS = 1024;
+constexpr int ECH_THREADS = 512;
 constexpr uint32_t ECH_INF = 0xffffffffu;
 
 struct EchArgs {
@@ -29,9 +29,8 @@ struct EchArgs {
     uint32_t n_rows, n_cols;        // D' is n_rows x n_cols (non-pivot columns), row-major u32
     uint32_t* d;
     const uint32_t* row_nz;         // [n_rows]
-    uint32_t* lead;                 // [n_rows] lead of list row i (owned by one group)
-    unsigned long long* best;       // [3] rotating pivot candidates, preset to ~0
-    uint32_t* inv_lead;             // [n_rows] inverse of the lead value of list row i
+    uint32_t* lead;                 // [2][n_rows]
+    uint32_t* inv_lead;             // [n_rows] inverse of the row's lead value
     uint32_t* nz_list;              // [n_rows] rows that are not identically zero
     uint32_t* piv_row;              // [n_rows]
     uint32_t* piv_col;              // [n_rows]
@@ -85,148 +84,101 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* sh) {
     return v;
 }
 
-constexpr int ECH_Q = 8;                             // columns per thread and super-block (8 x 1024 columns)
-constexpr int ECH_OWN = 32;                          // owned rows handled per chunk
+constexpr int ECH_GROUP = 128;                       // threads that update one row together
+constexpr int ECH_GROUPS = ECH_THREADS / ECH_GROUP;
 
-// Exact Gauss-Jordan as ONE cooperative kernel, one grid barrier per pivot.
-//  * Rows are OWNED by CTAs (row i of the non-zero list belongs to CTA i mod #CTAs); a row's lead
-//    lives with its owner, owners publish their smallest remaining lead with one atomicMin into a
-//    rotating global slot during the update, and after the grid barrier every CTA reads the next
-//    pivot with a single load (no scan, no second barrier).
-//  * Inside a CTA the THREADS OWN COLUMNS: thread t holds columns c+1+t+1024q of the pivot row in
-//    registers and sweeps them through all owned rows, so every load of a step is independent and
-//    in flight together (the row-per-128-threads form paid one ~0.8 us DRAM round trip per 512
-//    columns: 47 us per pivot on cyclic9-15, measured with clock64).
-//  * The pivot column is never written during an update (it is dead for all rows but its pivot
-//    row), which removes the barrier between reading the multipliers and updating the rows.
+__device__ __forceinline__ void group_bar(uint32_t grp) {
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(ECH_GROUP) : "memory");
+}
+
 __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ uint64_t sh64[32];
     __shared__ uint32_t sh32[32];
-    __shared__ uint32_t sh_scan[ECH_THREADS / 32];
-    __shared__ uint32_t s_f[ECH_OWN], s_lead[ECH_OWN];
+    __shared__ uint32_t sh_grp[ECH_GROUPS][4];
     const uint32_t tid = threadIdx.x, nb = gridDim.x, bid = blockIdx.x;
+    const uint32_t grp = tid / ECH_GROUP, gt = tid % ECH_GROUP, gw = gt >> 5;
     const uint32_t nr = a.n_rows, nc = a.n_cols, p = a.f.p;
-    unsigned long long* best = a.best;               // [3] rotating (lead << 32 | list index), ~0 = none
+    uint32_t* lead0 = a.lead;
+    uint32_t* lead1 = a.lead + nr;
 
-    // list of the non-zero rows (block 0, ballot compaction)
-    if (bid == 0) {
-        uint32_t base = 0;
-        for (uint32_t r0 = 0; r0 < nr; r0 += ECH_THREADS) {
-            const uint32_t r = r0 + tid;
-            const bool nzr = r < nr && a.row_nz[r] != 0;
-            const uint32_t bal = __ballot_sync(0xffffffffu, nzr);
-            if ((tid & 31) == 0) sh_scan[tid >> 5] = __popc(bal);
-            __syncthreads();
-            uint32_t pre = base;
-            for (uint32_t w = 0; w < (tid >> 5); ++w) pre += sh_scan[w];
-            if (nzr) a.nz_list[pre + __popc(bal & ((1u << (tid & 31)) - 1u))] = r;
-            uint32_t tot = 0;
-            for (uint32_t w = 0; w < ECH_THREADS / 32; ++w) tot += sh_scan[w];
-            base += tot;
-            __syncthreads();
-        }
-        if (tid == 0) a.counts[0] = base;
-    }
-    for (uint32_t j = bid * ECH_THREADS + tid; j < nc; j += nb * ECH_THREADS) a.is_piv_col[j] = 0;
-    grid.sync();
-    const uint32_t nnz_rows = a.counts[0];
-
-    // leads of the owned rows, their inverses, and the first pivot candidate
-    {
-        unsigned long long lb = ~0ull;
-        for (uint32_t i = bid; i < nnz_rows; i += nb) {
-            const uint32_t r = a.nz_list[i];
+    // leads of the rows (block per row), the inverse of every lead value, the list of non-zero rows
+    for (uint32_t r = bid; r < nr; r += nb) {
+        uint32_t l = ECH_INF;
+        if (a.row_nz[r]) {
             const uint32_t* row = a.d + (uint64_t)r * nc;
-            uint32_t l = ECH_INF;
             for (uint32_t j0 = 0; j0 < nc && l == ECH_INF; j0 += ECH_THREADS) {
                 const uint32_t j = j0 + tid;
                 l = block_min_u32(j < nc && row[j] ? j : ECH_INF, sh32);
             }
-            if (tid == 0) {
-                a.lead[i] = l;
-                if (l != ECH_INF) {
-                    a.inv_lead[i] = fp_inv_fermat(row[l], a.f);
-                    const unsigned long long k = ((unsigned long long)l << 32) | i;
-                    lb = k < lb ? k : lb;
-                }
-            }
+            if (tid == 0 && l != ECH_INF) a.inv_lead[r] = fp_inv32(row[l], p);
         }
-        if (tid == 0 && lb != ~0ull) atomicMin(best + 0, lb);
+        if (tid == 0) lead0[r] = l;
+    }
+    for (uint32_t j = bid * ECH_THREADS + tid; j < nc; j += nb * ECH_THREADS) a.is_piv_col[j] = 0;
+    grid.sync();
+    if (bid == 0 && tid == 0) {
+        uint32_t n = 0;
+        for (uint32_t r = 0; r < nr; ++r) if (lead0[r] != ECH_INF) a.nz_list[n++] = r;
+        a.counts[0] = n;
     }
     grid.sync();
+    const uint32_t nnz_rows = a.counts[0];
 
     uint32_t step = 0;
     for (;; ++step) {
-        const unsigned long long key = *(volatile unsigned long long*)(best + step % 3);
-        if (key == ~0ull) break;
-        const uint32_t c = (uint32_t)(key >> 32), ip = (uint32_t)key;
-        const uint32_t pr = a.nz_list[ip];
-        const uint32_t* __restrict__ prow = a.d + (uint64_t)pr * nc;
-        const uint32_t inv = a.inv_lead[ip];
-        if (bid == 0 && tid == 0) { a.piv_row[step] = pr; a.piv_col[step] = c; a.is_piv_col[c] = 1; best[(step + 2) % 3] = ~0ull; }
-        unsigned long long lb = ~0ull;               // thread 0 only
-        for (uint32_t i0 = bid; i0 < nnz_rows; i0 += nb * ECH_OWN) {
-            // multipliers and leads of (a chunk of) the owned rows
-            __syncthreads();
-            if (tid < ECH_OWN) {
-                const uint32_t i = i0 + tid * nb;
-                uint32_t fv = 0, lr = ECH_INF;
-                if (i < nnz_rows) {
-                    lr = a.lead[i];
-                    if (i == ip) { a.lead[i] = ECH_INF; lr = ECH_INF; }
-                    else fv = __ldcg(a.d + (uint64_t)a.nz_list[i] * nc + c);
-                }
-                s_f[tid] = fv; s_lead[tid] = lr;
-            }
-            __syncthreads();
-            for (uint32_t jb = c + 1; jb < nc; jb += ECH_Q * ECH_THREADS) {
-                uint32_t pv[ECH_Q];
-#pragma unroll
-                for (int q = 0; q < ECH_Q; ++q) {
-                    const uint32_t j = jb + q * ECH_THREADS + tid;
-                    pv[q] = j < nc ? __ldcg(prow + j) : 0u;
-                }
-                for (uint32_t k = 0; k < ECH_OWN; ++k) {
-                    const uint32_t fv = s_f[k];
-                    if (fv == 0) continue;              // CTA-uniform
-                    uint32_t* __restrict__ row = a.d + (uint64_t)a.nz_list[i0 + k * nb] * nc;
-                    const uint32_t mult = p - fp_mul(fv, inv, a.f);
-                    uint32_t v[ECH_Q];
-#pragma unroll
-                    for (int q = 0; q < ECH_Q; ++q) {
-                        const uint32_t j = jb + q * ECH_THREADS + tid;
-                        v[q] = (j < nc && pv[q]) ? __ldcg(row + j) : 0u;
-                    }
-#pragma unroll
-                    for (int q = 0; q < ECH_Q; ++q) {
-                        const uint32_t j = jb + q * ECH_THREADS + tid;
-                        if (pv[q]) row[j] = fp_reduce64((uint64_t)v[q] + (uint64_t)mult * pv[q], a.f);
-                    }
-                }
-            }
-            // remaining rows whose lead was c: find the new lead (rare: usually one or two rows per pivot)
-            for (uint32_t k = 0; k < ECH_OWN; ++k) {
-                const uint32_t lr = s_lead[k];
-                if (lr == ECH_INF) continue;            // CTA-uniform
-                const uint32_t i = i0 + k * nb;
-                uint32_t nl = lr;
-                if (s_f[k] != 0) {
-                    __syncthreads();                    // the row[] stores above
-                    const uint32_t* row = a.d + (uint64_t)a.nz_list[i] * nc;
-                    nl = ECH_INF;
-                    for (uint32_t j0 = c + 1; j0 < nc && nl == ECH_INF; j0 += ECH_THREADS) {
-                        const uint32_t j = j0 + tid;
-                        nl = block_min_u32(j < nc && __ldcg(row + j) ? j : ECH_INF, sh32);
-                    }
-                    if (tid == 0) {
-                        a.lead[i] = nl;
-                        if (nl != ECH_INF) a.inv_lead[i] = fp_inv_fermat(__ldcg(row + nl), a.f);
-                    }
-                }
-                if (tid == 0 && nl != ECH_INF) { const unsigned long long kk = ((unsigned long long)nl << 32) | i; lb = kk < lb ? kk : lb; }
-            }
+        const uint32_t* lc = (step & 1) ? lead1 : lead0;
+        uint32_t* ln = (step & 1) ? lead0 : lead1;
+        // every CTA derives the same pivot: smallest lead, ties to the first row
+        uint64_t key = ~0ull;
+        for (uint32_t i = tid; i < nnz_rows; i += ECH_THREADS) {
+            const uint32_t l = lc[a.nz_list[i]];
+            if (l != ECH_INF) { const uint64_t k = ((uint64_t)l << 32) | i; key = k < key ? k : key; }
         }
-        if (tid == 0 && lb != ~0ull) atomicMin(best + (step + 1) % 3, lb);
+        key = block_min_u64(key, sh64);
+        if (key == ~0ull) break;
+        const uint32_t c = (uint32_t)(key >> 32);
+        const uint32_t pr = a.nz_list[(uint32_t)key];
+        const uint32_t* prow = a.d + (uint64_t)pr * nc;
+        const uint32_t inv = a.inv_lead[pr];
+        if (bid == 0 && tid == 0) { a.piv_row[step] = pr; a.piv_col[step] = c; a.is_piv_col[c] = 1; }
+        // rows are dealt to groups of 128 threads: 4 rows per CTA in flight
+        for (uint32_t i = bid * ECH_GROUPS + grp; i < nnz_rows; i += nb * ECH_GROUPS) {
+            const uint32_t r = a.nz_list[i];
+            if (r == pr) { if (gt == 0) ln[r] = ECH_INF; continue; }
+            uint32_t* row = a.d + (uint64_t)r * nc;
+            const uint32_t fv = row[c];
+            const uint32_t lr = lc[r];
+            if (fv == 0) { if (gt == 0) ln[r] = lr; continue; }
+            const uint32_t mult = p - fp_mul(fv, inv, a.f);
+            uint32_t nl = ECH_INF;
+            for (uint32_t j0 = c + 1; j0 < nc; j0 += 4 * ECH_GROUP) {
+                uint32_t pv[4], v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + u * ECH_GROUP + gt;
+                    pv[u] = j < nc ? prow[j] : 0u;
+                    v[u] = j < nc ? row[j] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + u * ECH_GROUP + gt;
+                    if (pv[u]) { v[u] = fp_reduce64((uint64_t)v[u] + (uint64_t)mult * pv[u], a.f); row[j] = v[u]; }
+                    if (v[u] && nl == ECH_INF) nl = j;
+                }
+            }
+            if (lr != ECH_INF) {            // a remaining row: its lead was c, find the new one (and its inverse)
+                for (int o = 16; o; o >>= 1) nl = min(nl, __shfl_xor_sync(0xffffffffu, nl, o));
+                if ((gt & 31) == 0) sh_grp[grp][gw] = nl;
+                group_bar(grp);             // also orders the row[] stores before the read below
+                if (gt == 0) {
+                    nl = min(min(sh_grp[grp][0], sh_grp[grp][1]), min(sh_grp[grp][2], sh_grp[grp][3]));
+                    ln[r] = nl;
+                    if (nl != ECH_INF) a.inv_lead[r] = fp_inv32(row[nl], p);
+                }
+                group_bar(grp);
+            } else if (gt == 0) ln[r] = ECH_INF;
+        }
         grid.sync();
     }
     const uint32_t npiv = step;

@@ -55,6 +55,7 @@ struct ElimArgs {
     Layout L;
     Fp f;
     uint32_t mu32;               // floor(2^32 / p), Barrett constant for 32-bit operands (p < 2^16)
+    uint32_t negp;               // 2^32 - p
     uint32_t norm_every;         // pivot rows a tile may absorb between normalisations
     const uint32_t* seg;
     const uint2* ent;
@@ -75,14 +76,18 @@ struct ElimArgs {
 
 template <bool SMALLP> struct Acc;
 
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t val) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(val) : "memory");
+}
+
 template <> struct Acc<true> {   // p < 2^16: one u32 lane per column
     static constexpr int WORDS = 1;
+    // m*v mod p up to one multiple of p: the result is < 2p (the lane is reduced when it is read)
     static __device__ __forceinline__ uint32_t mulred(uint32_t m, uint32_t v, const ElimArgs& a) {
         const uint32_t x = m * v;                       // < 2^32
-        uint32_t r = x - __umulhi(x, a.mu32) * a.f.p;   // < 2p
-        return r >= a.f.p ? r - a.f.p : r;
+        return x + __umulhi(x, a.mu32) * a.negp;        // x - q*p, one IMAD
     }
-    static __device__ __forceinline__ void add(uint32_t* acc, uint32_t c, uint32_t val) { atomicAdd(acc + c, val); }
+    static __device__ __forceinline__ void add(uint32_t acc_sa, uint32_t c, uint32_t val) { red_shared_add(acc_sa + c * 4, val); }
     static __device__ __forceinline__ void set(uint32_t* acc, uint32_t c, uint32_t val) { acc[c] = val; }
     static __device__ __forceinline__ uint32_t get(const uint32_t* acc, uint32_t c, const ElimArgs& a) {
         const uint32_t x = acc[c];
@@ -96,9 +101,9 @@ template <> struct Acc<false> {  // p < 2^31: lo/hi pair of u32 lanes per column
     static __device__ __forceinline__ uint32_t mulred(uint32_t m, uint32_t v, const ElimArgs& a) {
         return fp_reduce64((uint64_t)m * v, a.f);
     }
-    static __device__ __forceinline__ void add(uint32_t* acc, uint32_t c, uint32_t val) {
-        atomicAdd(acc + 2 * c, val & 0xffffu);
-        atomicAdd(acc + 2 * c + 1, val >> 16);
+    static __device__ __forceinline__ void add(uint32_t acc_sa, uint32_t c, uint32_t val) {
+        red_shared_add(acc_sa + c * 8, val & 0xffffu);
+        red_shared_add(acc_sa + c * 8 + 4, val >> 16);
     }
     static __device__ __forceinline__ void set(uint32_t* acc, uint32_t c, uint32_t val) {
         acc[2 * c] = val & 0xffffu; acc[2 * c + 1] = val >> 16;
@@ -154,20 +159,21 @@ __device__ __forceinline__ bool cursor_next(ChunkCursor& c, uint32_t s, uint32_t
 }
 
 template <bool SMALLP>
-__device__ __forceinline__ void elim_apply_segments(uint32_t* acc, uint32_t* ring, const ElimArgs& a, uint32_t s,
+__device__ __forceinline__ void elim_apply_segments(uint32_t acc_sa, uint32_t ring_sa, const ElimArgs& a, uint32_t s,
                                                     uint32_t len, uint32_t m, uint32_t mask, uint32_t lane) {
     if (mask == 0) return;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    static_assert((ELIM_DEPTH & (ELIM_DEPTH - 1)) == 0, "ring depth must be a power of two");
+    const uint32_t ring_lane = ring_sa + lane * 16;
     ChunkCursor ci{mask, 0, 0, 0, 0}, cc{mask, 0, 0, 0, 0};
-    uint32_t islot = 0, cslot = 0;
+    uint32_t in = 0, cn = 0;
     auto issue = [&]() {
         if (cursor_next(ci, s, len, m)) {
             const uint32_t off = ci.off + lane * 2;
-            cp_async16(ring_addr + islot * 512, a.ent + ci.s + off, off < ci.len);
+            cp_async16(ring_lane + (in & (ELIM_DEPTH - 1)) * 512, a.ent + ci.s + off, off < ci.len);
             ci.off += 64;
         }
         cp_async_commit();
-        islot = islot + 1 == ELIM_DEPTH ? 0 : islot + 1;
+        ++in;
     };
 #pragma unroll
     for (int i = 0; i + 1 < ELIM_DEPTH; ++i) issue();
@@ -175,13 +181,15 @@ __device__ __forceinline__ void elim_apply_segments(uint32_t* acc, uint32_t* rin
         issue();
         cp_async_wait<ELIM_DEPTH - 1>();
         const uint32_t off = cc.off + lane * 2;
-        if (off < cc.len) {   // len is a multiple of 4, off is even: both entries are inside (padding has value 0)
-            const uint4 q = *reinterpret_cast<const uint4*>(ring + cslot * 128 + lane * 4);
-            if (q.y) Acc<SMALLP>::add(acc, q.x, Acc<SMALLP>::mulred(cc.m, q.y, a));
-            if (q.w) Acc<SMALLP>::add(acc, q.z, Acc<SMALLP>::mulred(cc.m, q.w, a));
+        if (off < cc.len) {   // len is a multiple of 4, off is even: both entries are inside
+            uint4 q;          // padding entries carry value 0 and the sink column: adding 0 there is harmless
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "r"(ring_lane + (cn & (ELIM_DEPTH - 1)) * 512) : "memory");
+            Acc<SMALLP>::add(acc_sa, q.x, Acc<SMALLP>::mulred(cc.m, q.y, a));
+            Acc<SMALLP>::add(acc_sa, q.z, Acc<SMALLP>::mulred(cc.m, q.w, a));
         }
         cc.off += 64;
-        cslot = cslot + 1 == ELIM_DEPTH ? 0 : cslot + 1;
+        ++cn;
     }
     cp_async_wait<0>();
 }
@@ -196,6 +204,8 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
     const uint32_t acc_words = ((L.tile_cols + 1) * W + 3u) & ~3u;               // +1: the sink lane
     uint32_t* acc = reinterpret_cast<uint32_t*>(elim_smem);
     uint32_t* ring = acc + acc_words + warp * ELIM_SCRATCH_WORDS;
+    const uint32_t acc_sa = (uint32_t)__cvta_generic_to_shared(acc);
+    const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t p = a.f.p, nr = L.n_rows;
     const uint64_t p2 = a.f.p2;
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                 uint32_t s = 0, len = 0, m = 0;
                 if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; len = seg_e[k] - s; }
                 fma += len;
-                elim_apply_segments<SMALLP>(acc, ring, a, s, len, m, __ballot_sync(0xffffffffu, len != 0), lane);
+                elim_apply_segments<SMALLP>(acc_sa, ring_sa, a, s, len, m, __ballot_sync(0xffffffffu, len != 0), lane);
             }
             __syncthreads();
 
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                     const uint32_t len = x ? e - s : 0u;
                     const bool mine = len != 0 && (__popc(nzm & lt) % ELIM_CTA_WARPS) == warp;
                     if (mine) fma += len;
-                    elim_apply_segments<SMALLP>(acc, ring, a, s, len, m, __ballot_sync(0xffffffffu, mine), lane);
+                    elim_apply_segments<SMALLP>(acc_sa, ring_sa, a, s, len, m, __ballot_sync(0xffffffffu, mine), lane);
                     __syncthreads();                  // the next window is read after all warps' updates
                 }
             } else {
