@@ -76,6 +76,17 @@ __host__ __device__ inline uint32_t fp_inv32(uint32_t a, uint32_t p) {
     return t < 0 ? (uint32_t)(t + (int32_t)p) : (uint32_t)t;
 }
 
+// a^(p-2) mod p: branch-light chain of Barrett multiplications (the extended Euclid above needs
+// ~45 dependent integer divisions, several microseconds on one GPU thread)
+__host__ __device__ inline uint32_t fp_inv_fermat(uint32_t a, const Fp& f) {
+    uint32_t r = 1, b = a;
+    for (uint32_t e = f.p - 2; e; e >>= 1) {
+        if (e & 1) r = fp_mul(r, b, f);
+        b = fp_mul(b, b, f);
+    }
+    return r;
+}
+
 inline Fp fp_make(uint32_t p, uint32_t mont_bits) {
     Fp f{};
     f.p = p; f.small = p < 65536u; f.p2 = (uint64_t)p * p;

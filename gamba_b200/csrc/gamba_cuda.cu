@@ -18,6 +18,7 @@
 #include "../../include/gamba_cuda.h"
 #include "field.cuh"
 #include "kernels_echelon.cuh"
+#include "kernels_echelon_blocked.cuh"
 #include "kernels_elim.cuh"
 #include "kernels_prep.cuh"
 #include "layout.cuh"
@@ -78,6 +79,7 @@ struct gamba_cuda_engine {
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
+    int64_t opt_echelon_blocked = 1;
 
     // staged step
     bool staged = false;
@@ -92,6 +94,7 @@ struct gamba_cuda_engine {
 
     // elimination / echelon state
     gcu::DevBuf d_dprime, d_row_nz, d_list_k, d_list_m, d_queue_stats;
+    gcu::DevBuf d_eb_mult, d_eb_mask, d_eb_q, d_eb_hdr;
     gcu::DevBuf d_lead, d_nz_list, d_piv_row, d_piv_col, d_is_piv, d_counts, d_out_ptr, d_out_col, d_out_val;
     uint32_t n_local = 0, n_local_max = 0, n_gather_rows = 0;
     bool eliminated = false;
@@ -318,8 +321,9 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     const uint32_t nr = n_gather_rows, nc = L.n_nonpiv;
     uint32_t npiv = 0;
     uint64_t nnz_new = 0;
-    d_counts.ensure(64);
-    GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 64, stream));
+    d_counts.ensure(256);
+    GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 32, stream));
+    GCU_CHECK(cudaMemsetAsync(d_counts.as<char>() + 32, 0xff, 32, stream));
     GCU_CHECK(cudaEventRecord(ev[4], stream));
     if (nr && nc) {
         d_lead.ensure((size_t)3 * nr * sizeof(uint32_t));
@@ -335,17 +339,39 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
         ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
         ea.out_ptr = d_out_ptr.as<uint64_t>();
+        if (opt_echelon_blocked && nr <= EB_MAXC) {
+            d_eb_mult.ensure((size_t)nr * EB_W * sizeof(uint32_t));
+            d_eb_mask.ensure((size_t)nr * sizeof(uint32_t));
+            d_eb_q.ensure((size_t)EB_W * nc * sizeof(uint32_t));
+            d_eb_hdr.ensure(2048 * sizeof(uint32_t));
+            GCU_CHECK(cudaMemsetAsync(d_eb_mask.p, 0, (size_t)nr * sizeof(uint32_t), stream));
+            EbArgs eb{};
+            eb.f = f; eb.n_rows = nr; eb.n_cols = nc; eb.d = ea.d; eb.row_nz = ea.row_nz; eb.nz_list = ea.nz_list;
+            eb.lead = ea.lead; eb.mult = d_eb_mult.as<uint32_t>(); eb.mask = d_eb_mask.as<uint32_t>();
+            eb.q = d_eb_q.as<uint32_t>(); eb.hdr = d_eb_hdr.as<uint32_t>();
+            eb.best = reinterpret_cast<unsigned long long*>(d_counts.as<char>() + 32);
+            eb.piv_row = ea.piv_row; eb.piv_col = ea.piv_col; eb.is_piv_col = ea.is_piv_col; eb.counts = ea.counts;
+            eb.out_ptr = ea.out_ptr;
+            GCU_CHECK(cudaFuncSetAttribute(echelon_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EB_SMEM));
+            int occ = 0;
+            GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, echelon_blocked_kernel, EB_THREADS, EB_SMEM));
+            if (occ < 1) throw std::runtime_error("blocked echelon kernel does not fit on an SM");
+            void* args[] = {&eb};
+            GCU_CHECK(cudaLaunchCooperativeKernel((void*)echelon_blocked_kernel, dim3(prop.multiProcessorCount), dim3(EB_THREADS), args, EB_SMEM, stream));
+        } else {
         int occ = 0;
         GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, echelon_kernel, ECH_THREADS, 0));
         if (occ < 1) throw std::runtime_error("echelon kernel does not fit on an SM");
         const int grid = prop.multiProcessorCount * std::min(occ, 1);
         void* args[] = {&ea};
         GCU_CHECK(cudaLaunchCooperativeKernel((void*)echelon_kernel, dim3(grid), dim3(ECH_THREADS), args, 0, stream));
+        }
         ctr.kernel_launches += 1;
         h_misc.ensure(64);
         GCU_CHECK(cudaMemcpyAsync(h_misc.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
         GCU_CHECK(cudaStreamSynchronize(stream));
         npiv = h_misc.as<uint32_t>()[1];
+        if (getenv("GAMBA_CUDA_DEBUG")) { unsigned long long g[16]; GCU_CHECK(cudaMemcpy(g, d_counts.as<char>() + 64, 128, cudaMemcpyDeviceToHost)); for (int b = 0; b < 2; ++b) fprintf(stderr, "[eb] npiv=%u nr=%u nc=%u blk%d passes %llu | P1 %llu S1 %llu PC %llu P2 %llu S2 %llu P3 %llu S3 %llu (kcycles)\n", npiv, nr, nc, b ? 77 : 0, g[8*b+7], g[8*b]/1000, g[8*b+1]/1000, g[8*b+2]/1000, g[8*b+3]/1000, g[8*b+4]/1000, g[8*b+5]/1000, g[8*b+6]/1000); }
         if (npiv) {
             h_out_ptr.ensure((size_t)(npiv + 1) * sizeof(uint64_t));
             GCU_CHECK(cudaMemcpyAsync(h_out_ptr.p, d_out_ptr.p, (size_t)(npiv + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
@@ -485,6 +511,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         const std::string k = key ? key : "";
         if (k == "tile_cols") e->opt_tile_cols = value;
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
+        else if (k == "echelon_blocked") e->opt_echelon_blocked = value;
         else throw std::runtime_error("unknown option " + k);
     });
 }
