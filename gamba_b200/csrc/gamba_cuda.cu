@@ -371,7 +371,6 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         GCU_CHECK(cudaMemcpyAsync(h_misc.p, d_counts.p, 8, cudaMemcpyDeviceToHost, stream));
         GCU_CHECK(cudaStreamSynchronize(stream));
         npiv = h_misc.as<uint32_t>()[1];
-        if (getenv("GAMBA_CUDA_DEBUG")) { unsigned long long g[16]; GCU_CHECK(cudaMemcpy(g, d_counts.as<char>() + 64, 128, cudaMemcpyDeviceToHost)); for (int b = 0; b < 2; ++b) fprintf(stderr, "[eb] npiv=%u nr=%u nc=%u blk%d passes %llu | P1 %llu S1 %llu PC %llu P2 %llu S2 %llu P3 %llu S3 %llu (kcycles)\n", npiv, nr, nc, b ? 77 : 0, g[8*b+7], g[8*b]/1000, g[8*b+1]/1000, g[8*b+2]/1000, g[8*b+3]/1000, g[8*b+4]/1000, g[8*b+5]/1000, g[8*b+6]/1000); }
         if (npiv) {
             h_out_ptr.ensure((size_t)(npiv + 1) * sizeof(uint64_t));
             GCU_CHECK(cudaMemcpyAsync(h_out_ptr.p, d_out_ptr.p, (size_t)(npiv + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));

@@ -126,9 +126,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) echelon_blocked_kernel(EbArgs a
     grid.sync();
 
     uint32_t npiv = 0;
-    long long tP1 = 0, tS1 = 0, tPC = 0, tP2 = 0, tS2 = 0, tP3 = 0, tS3 = 0; uint32_t npass = 0;
     for (uint32_t pass = 0;; ++pass) {
-        const long long t0 = clock64();
         const unsigned long long key = *(volatile unsigned long long*)(a.best + pass % 3);
         if (key == ~0ull) break;
         const uint32_t c0 = (uint32_t)(key >> 32);
@@ -212,9 +210,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) echelon_blocked_kernel(EbArgs a
             }
             for (uint32_t x = tid; x < npk * EB_W; x += EB_THREADS) a.hdr[128 + x] = s_qp[x / EB_W][x % EB_W];
         }
-        const long long t1 = clock64();
         grid.sync();
-        const long long t2 = clock64();
 
         // ======================= header, PC: other rows' multipliers ==============================
         const uint32_t npk = a.hdr[0], W = a.hdr[2];
@@ -256,7 +252,6 @@ __global__ void __launch_bounds__(EB_THREADS, 1) echelon_blocked_kernel(EbArgs a
         }
         __syncthreads();
 
-        const long long t3 = clock64();
         // ======================= P2: pivot rows as used, trailing columns =========================
         const uint32_t ct = c0 + W;                                  // first trailing column
         for (uint32_t j = ct + bid * EB_THREADS + tid; j < nc; j += nb * EB_THREADS) {
@@ -274,9 +269,7 @@ __global__ void __launch_bounds__(EB_THREADS, 1) echelon_blocked_kernel(EbArgs a
                 a.q[(uint64_t)k * nc + j] = qv[k];
             }
         }
-        const long long t4 = clock64();
         grid.sync();
-        const long long t5 = clock64();
 
         // ======================= P3: one update of every row for the whole pass ===================
         {
@@ -334,12 +327,8 @@ __global__ void __launch_bounds__(EB_THREADS, 1) echelon_blocked_kernel(EbArgs a
             if (tid == 0 && lb != ~0ull) atomicMin(a.best + (pass + 1) % 3, lb);
         }
         npiv += npk;
-        const long long t6 = clock64();
         grid.sync();
-        const long long t7 = clock64();
-        tP1 += t1 - t0; tS1 += t2 - t1; tPC += t3 - t2; tP2 += t4 - t3; tS2 += t5 - t4; tP3 += t6 - t5; tS3 += t7 - t6; ++npass;
     }
-    if (tid == 0 && (bid == 0 || bid == 77)) { unsigned long long* dbg = a.best + 4 + (bid ? 8 : 0); dbg[0] = tP1; dbg[1] = tS1; dbg[2] = tPC; dbg[3] = tP2; dbg[4] = tS2; dbg[5] = tP3; dbg[6] = tS3; dbg[7] = npass; }
     if (bid == 0 && tid == 0) a.counts[1] = npiv;
 
     // non-zeros per new row
