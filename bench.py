@@ -227,6 +227,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e = LinalgEngine(s.p, device=local_rank, rank=rank, world_size=world)
         if gather:
             e.set_allgather(gather)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            e.set_option(k, int(v))
         engines.append(e)
 
     def sync():
@@ -355,6 +358,7 @@ def main():
     ap.add_argument("--max-matrices", type=int, default=0)
     ap.add_argument("--ref-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", nargs="*", default=[], help="engine options key=value (gamba_cuda_set_option)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -80,6 +80,11 @@ struct gamba_cuda_engine {
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
     int64_t opt_echelon_blocked = 1;
+    int64_t opt_mc = 0;              // Monte-Carlo combinations instead of the rows themselves
+    int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
+    int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
+    uint32_t mc_k = 0;               // combinations used by the current reduction (0 = exact)
+    uint64_t mc_draw = 0;            // counter making every draw of multipliers different
 
     // staged step
     bool staged = false;
@@ -123,6 +128,7 @@ struct gamba_cuda_engine {
     void eliminate();
     void exchange();
     void echelon(gamba_cuda_step_out* out);
+    void run_reduce(gamba_cuda_step_out* out);
 };
 
 using namespace gcu;
@@ -206,7 +212,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     d_ent.ensure((nnz + 3ull * n_rows * L.n_tiles + 4) * sizeof(uint2));   // segments padded to 4 entries
     d_diag.ensure(n_diag * sizeof(uint32_t));
     d_dnz.ensure(std::max<uint32_t>(L.n_windows, 1) * sizeof(uint32_t));
-    d_first.ensure(std::max<uint32_t>(L.n_bot, 1) * sizeof(uint32_t));
+    d_first.ensure((std::max<uint32_t>(L.n_bot, 1) + 1) * sizeof(uint32_t));
     GCU_CHECK(cudaEventRecord(ev[0], stream));
     GCU_CHECK(cudaMemsetAsync(d_cnt.p, 0, n_cnt * sizeof(uint32_t), stream));
     GCU_CHECK(cudaMemsetAsync(d_diag.p, 0, n_diag * sizeof(uint32_t), stream));
@@ -217,7 +223,8 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
     pa.cnt = d_cnt.as<uint32_t>(); pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
     pa.diag = d_diag.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
-    pa.first_piv = d_first.as<uint32_t>();
+    pa.first_piv = d_first.as<uint32_t>(); pa.first_min = d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1);
+    GCU_CHECK(cudaMemsetAsync(pa.first_min, 0xff, sizeof(uint32_t), stream));
     if (n_rows) {
         const size_t sh = (size_t)8 * L.n_tiles * sizeof(uint32_t);
         if (sh > 48 * 1024) {
@@ -252,9 +259,10 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
 void gamba_cuda_engine::eliminate() {
     if (!staged) throw std::runtime_error("no staged step");
     const uint32_t world = std::max(1u, cfg.world_size), rank = cfg.rank;
-    n_local_max = (L.n_bot + world - 1) / world;
-    n_local = L.n_bot > rank ? (L.n_bot - rank + world - 1) / world : 0;
-    n_gather_rows = world > 1 ? n_local_max * world : L.n_bot;
+    const uint32_t n_work = mc_k ? mc_k : L.n_bot;       // rows of C|D, or random combinations of them
+    n_local_max = (n_work + world - 1) / world;
+    n_local = n_work > rank ? (n_work - rank + world - 1) / world : 0;
+    n_gather_rows = world > 1 ? n_local_max * world : n_work;
 
     const uint32_t words_per_col = f.small ? 1u : 2u;
     const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
@@ -294,6 +302,9 @@ void gamba_cuda_engine::eliminate() {
     ea.queue = d_queue_stats.as<uint32_t>();
     ea.stats = reinterpret_cast<unsigned long long*>(d_queue_stats.as<char>() + 16);
     ea.row_ptr = d_row_ptr.as<uint64_t>();
+    ea.mc_rows = mc_k ? L.n_bot : 0;
+    ea.mc_seed = cfg.seed * 0x9e3779b97f4a7c15ull + mc_draw;
+    if (mc_k) { GCU_CHECK(cudaMemcpyAsync(&ea.mc_first, d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); GCU_CHECK(cudaStreamSynchronize(stream)); }
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (n_local && L.n_nonpiv) {
@@ -426,6 +437,39 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     out->d2h_bytes = (npiv + 1) * 8ull + nnz_new * 8ull + npiv * 4ull + 24;
 }
 
+// Exact mode: every row of C|D is eliminated. Monte-Carlo mode (option "mc"): K random combinations of
+// all the rows are eliminated instead and the result is accepted only if the rank of D' leaves a margin
+// of 32 combinations (K - rank >= 32): K random vectors of a space of dimension rank span it except
+// with probability ~p^-(K-rank) <= 3^-32, so the row space - hence the canonical RREF - is that of the
+// exact computation. Otherwise K is doubled, and beyond n_bot/3 combinations the step runs exactly.
+void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
+    uint32_t k = 0;
+    if (opt_mc && !(flags & GAMBA_CUDA_STEP_FINAL) && L.n_bot >= 256) {
+        k = opt_mc_k > 0 ? (uint32_t)opt_mc_k : (last_rank < 0 ? 64u : (uint32_t)(last_rank + 32 + last_rank / 8));
+        k = (k + 7) / 8 * 8;
+        if ((uint64_t)k * 3 >= L.n_bot) k = 0;
+    }
+    double acc_elim = 0, acc_ech = 0;
+    ctr.mc_attempts = 0;
+    for (;;) {
+        mc_k = k; ++mc_draw; ++ctr.mc_attempts;
+        eliminate();
+        exchange();
+        echelon(out);
+        acc_elim += t_elim_dev; acc_ech += t_ech_dev;
+        if (mc_k && out->n_new + 32 > mc_k) {          // margin not met: more combinations, or exact
+            k = mc_k * 2;
+            if ((uint64_t)k * 3 >= L.n_bot) k = 0;
+            continue;
+        }
+        break;
+    }
+    ctr.mc_combinations = mc_k;
+    last_rank = out->n_new;
+    out->seconds_eliminate = acc_elim; out->seconds_echelon = acc_ech;
+    out->seconds_device = t_prep_dev + acc_elim + acc_ech;
+}
+
 // ------------------------------------------------------------------ C ABI -----
 
 template <class F>
@@ -478,9 +522,7 @@ int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out) {
     return guarded([&] {
         GCU_CHECK(cudaSetDevice((int)e->cfg.device));
         const double t0 = gcu::wall_s();
-        e->eliminate();
-        e->exchange();
-        e->echelon(out);
+        e->run_reduce(out);
         out->seconds_total = gcu::wall_s() - t0;
     });
 }
@@ -490,9 +532,7 @@ int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_
         GCU_CHECK(cudaSetDevice((int)e->cfg.device));
         const double t0 = gcu::wall_s();
         e->stage(in);
-        e->eliminate();
-        e->exchange();
-        e->echelon(out);
+        e->run_reduce(out);
         out->seconds_total = gcu::wall_s() - t0;
     });
 }
@@ -511,6 +551,9 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         if (k == "tile_cols") e->opt_tile_cols = value;
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
         else if (k == "echelon_blocked") e->opt_echelon_blocked = value;
+        else if (k == "mc") e->opt_mc = value;
+        else if (k == "mc_k") e->opt_mc_k = value;
+        else if (k == "rank_hint") e->last_rank = value;
         else throw std::runtime_error("unknown option " + k);
     });
 }

@@ -21,6 +21,7 @@ struct PrepArgs {
     uint32_t* diag;       // [n_windows][32][32]
     uint32_t* dnz;        // [n_windows]
     uint32_t* first_piv;  // per bottom row: smallest pivot column present (n_top if none)
+    uint32_t* first_min;  // min of first_piv over all rows to reduce (preset to 0xffffffff)
 };
 
 // in-window entries of a pivot row go to the dense diagonal block, not to ent[]
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) prep_count_kernel(PrepArgs a) {
         for (uint32_t b = lane; b < nt; b += 32) a.cnt[(uint64_t)row * nt + b] = (hist[b] + 3u) & ~3u;  // padded to 32 B
         if (row >= a.L.n_top) {
             for (int o = 16; o; o >>= 1) fp = min(fp, __shfl_xor_sync(0xffffffffu, fp, o));
-            if (lane == 0) a.first_piv[row - a.L.n_top] = fp;
+            if (lane == 0) { a.first_piv[row - a.L.n_top] = fp; atomicMin(a.first_min, fp); }
         }
     }
 }

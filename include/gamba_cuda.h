@@ -135,10 +135,15 @@ typedef struct gamba_cuda_counters {
     uint64_t fma_applied;              /* multiply-adds the elimination kernel did, last step   */
     uint64_t fma_top;                  /* matrix invariant of SURVEY.md §8(d): sum over pivot hits of
                                           nnz(pivot row), this rank's rows, last step              */
+    uint32_t mc_combinations;          /* Monte-Carlo mode: combinations eliminated by the last step (0 = the
+                                          step ran exactly)                                         */
+    uint32_t mc_attempts;              /* ... and how many draws it took to meet the rank margin      */
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
-/* Tuning knobs (0 = automatic). */
+/* Options: "tile_cols", "ctas_per_sm" (0 = automatic), "echelon_blocked" (default 1),
+   "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
+   margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);
 
 #ifdef __cplusplus

@@ -205,3 +205,26 @@ def test_full_size_properties(built, p):
     s2 = Step(p, 0, r.n_new, s.n_nonpiv, r.row_ptr, r.col, np.arange(r.n_new, dtype=np.uint32), lens, r.val)
     assert eng.reduce(s2).same_as(r)
     eng.close()
+
+
+def test_monte_carlo_mode_is_bit_exact(step_dirs):
+    """Option "mc": random combinations of the rows to reduce are eliminated instead of the rows themselves
+    (README.md:5 of the reference: "Monte-Carlo F4"); accepted only with a rank margin, so the canonical
+    RREF is the one of the exact computation."""
+    from gamba_b200 import LinalgEngine
+    eng = LinalgEngine(32003)
+    eng.set_option("mc", 1)
+    d = step_dirs("cyclic8-15", ("--dump-min-nnz", "100000"))
+    assert check_dir(d, eng) >= 5
+    used = 0
+    for f in sorted(glob.glob(os.path.join(d, "step_*.bin"))):
+        s = load_step(f)
+        if f.endswith("step_final.bin") or s.n_bot < 256:
+            continue
+        eng.set_option("rank_hint", 8)       # far too small: the margin test must force more combinations
+        assert eng.reduce(s).same_as(load_rows(f.replace("step_", "rows_"))), f
+        c = eng.counters()
+        used += c["mc_combinations"] > 0
+        assert c["mc_attempts"] >= 1
+    assert used > 0
+    eng.close()
