@@ -18,7 +18,7 @@
 #include "../../include/gamba_cuda.h"
 #include "field.cuh"
 #include "kernels_echelon.cuh"
-#include "kernels_echelon_blocked.cuh"
+#include "kernels_echelon_mma.cuh"
 #include "kernels_elim.cuh"
 #include "kernels_prep.cuh"
 #include "layout.cuh"
@@ -79,7 +79,7 @@ struct gamba_cuda_engine {
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
-    int64_t opt_echelon_blocked = 1;
+    int64_t opt_echelon_mma = 1;     // 1: blocked echelon on the tensor cores, 0: per-pivot kernel
     int64_t opt_mc = 0;              // Monte-Carlo combinations instead of the rows themselves
     int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
     int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
@@ -99,7 +99,7 @@ struct gamba_cuda_engine {
 
     // elimination / echelon state
     gcu::DevBuf d_dprime, d_row_nz, d_list_k, d_list_m, d_queue_stats;
-    gcu::DevBuf d_eb_mult, d_eb_mask, d_eb_q, d_eb_hdr;
+    gcu::DevBuf d_em_live, d_em_xa, d_em_pbt;
     gcu::DevBuf d_lead, d_nz_list, d_piv_row, d_piv_col, d_is_piv, d_counts, d_out_ptr, d_out_col, d_out_val;
     uint32_t n_local = 0, n_local_max = 0, n_gather_rows = 0;
     bool eliminated = false;
@@ -136,6 +136,7 @@ using namespace gcu;
 void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols) {
     L = Layout{};
     L.n_top = n_top; L.n_bot = n_bot; L.n_cols = n_cols; L.n_nonpiv = n_cols - n_top; L.n_rows = n_top + n_bot;
+    L.ld_dprime = (L.n_nonpiv + 3u) & ~3u;
     // Tile width from the number of rows (= warps) wanted in flight per SM: the kernel is
     // latency-bound, shared memory per SM / (warps per SM) is what one accumulator tile gets.
     const uint32_t gran = WINDOW;
@@ -276,7 +277,7 @@ void gamba_cuda_engine::eliminate() {
     elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
     const uint64_t n_slots = (uint64_t)elim_grid;
 
-    d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.n_nonpiv, 1) * sizeof(uint32_t));
+    d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.ld_dprime, 1) * sizeof(uint32_t));
     d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
     d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
     d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
@@ -285,7 +286,7 @@ void gamba_cuda_engine::eliminate() {
     GCU_CHECK(cudaMemsetAsync(d_row_nz.p, 0, std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t), stream));
 
     // local block of D' sits at its final place inside the gather buffer
-    uint32_t* dloc = d_dprime.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max * L.n_nonpiv : 0);
+    uint32_t* dloc = d_dprime.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max * L.ld_dprime : 0);
     uint32_t* nzloc = d_row_nz.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max : 0);
 
     ElimArgs ea{};
@@ -319,7 +320,7 @@ void gamba_cuda_engine::eliminate() {
 void gamba_cuda_engine::exchange() {
     if (cfg.world_size <= 1) return;
     if (!gather_fn) throw std::runtime_error("world_size > 1 but no all-gather callback set");
-    const size_t bytes_d = (size_t)n_local_max * L.n_nonpiv * sizeof(uint32_t);
+    const size_t bytes_d = (size_t)n_local_max * L.ld_dprime * sizeof(uint32_t);
     const size_t bytes_z = (size_t)n_local_max * sizeof(uint32_t);
     const char* send_d = d_dprime.as<char>() + (size_t)cfg.rank * bytes_d;
     const char* send_z = d_row_nz.as<char>() + (size_t)cfg.rank * bytes_z;
@@ -344,31 +345,35 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         d_is_piv.ensure(nc);
         d_out_ptr.ensure((size_t)(nr + 1) * sizeof(uint64_t));
         EchArgs ea{};
-        ea.f = f; ea.n_rows = nr; ea.n_cols = nc;
+        ea.f = f; ea.n_rows = nr; ea.n_cols = nc; ea.ld = L.ld_dprime;
         ea.d = d_dprime.as<uint32_t>(); ea.row_nz = d_row_nz.as<uint32_t>();
         ea.lead = d_lead.as<uint32_t>(); ea.inv_lead = d_lead.as<uint32_t>() + (size_t)2 * nr; ea.nz_list = d_nz_list.as<uint32_t>();
         ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
         ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
         ea.out_ptr = d_out_ptr.as<uint64_t>();
-        if (opt_echelon_blocked && nr <= EB_MAXC) {
-            d_eb_mult.ensure((size_t)nr * EB_W * sizeof(uint32_t));
-            d_eb_mask.ensure((size_t)nr * sizeof(uint32_t));
-            d_eb_q.ensure((size_t)EB_W * nc * sizeof(uint32_t));
-            d_eb_hdr.ensure(2048 * sizeof(uint32_t));
-            GCU_CHECK(cudaMemsetAsync(d_eb_mask.p, 0, (size_t)nr * sizeof(uint32_t), stream));
-            EbArgs eb{};
-            eb.f = f; eb.n_rows = nr; eb.n_cols = nc; eb.d = ea.d; eb.row_nz = ea.row_nz; eb.nz_list = ea.nz_list;
-            eb.lead = ea.lead; eb.mult = d_eb_mult.as<uint32_t>(); eb.mask = d_eb_mask.as<uint32_t>();
-            eb.q = d_eb_q.as<uint32_t>(); eb.hdr = d_eb_hdr.as<uint32_t>();
-            eb.best = reinterpret_cast<unsigned long long*>(d_counts.as<char>() + 32);
-            eb.piv_row = ea.piv_row; eb.piv_col = ea.piv_col; eb.is_piv_col = ea.is_piv_col; eb.counts = ea.counts;
-            eb.out_ptr = ea.out_ptr;
-            GCU_CHECK(cudaFuncSetAttribute(echelon_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EB_SMEM));
+        if (opt_echelon_mma) {
+            // blocked Gauss-Jordan, trailing updates on the tensor cores (kernels_echelon_mma.cuh)
+            const uint32_t nl = f.small ? 2u : 4u;
+            const uint32_t ncp = (nc + EM_CW - 1) / EM_CW * EM_CW;
+            d_lead.ensure((size_t)2 * nr * sizeof(uint32_t));
+            d_piv_row.ensure((size_t)2 * nr * sizeof(uint32_t));
+            d_piv_col.ensure((size_t)2 * nr * sizeof(uint32_t));
+            d_em_live.ensure((size_t)nr * sizeof(uint32_t));
+            d_em_xa.ensure((size_t)nr * nl * 32);
+            d_em_pbt.ensure((size_t)nl * ncp * 32);
+            EmArgs em{};
+            em.f = f; em.n_rows = nr; em.n_cols = nc; em.ld = L.ld_dprime; em.ncp = ncp;
+            em.d = ea.d; em.row_nz = ea.row_nz; em.lead = d_lead.as<uint32_t>(); em.live = d_em_live.as<uint32_t>();
+            em.xa = d_em_xa.as<uint8_t>(); em.pbt = d_em_pbt.as<uint8_t>();
+            em.piv_row = d_piv_row.as<uint32_t>(); em.piv_col = d_piv_col.as<uint32_t>();
+            em.is_piv_col = ea.is_piv_col; em.counts = ea.counts; em.out_ptr = ea.out_ptr;
+            auto kern = f.small ? (void*)echelon_mma_kernel<2> : (void*)echelon_mma_kernel<4>;
+            GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_SMEM));
             int occ = 0;
-            GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, echelon_blocked_kernel, EB_THREADS, EB_SMEM));
-            if (occ < 1) throw std::runtime_error("blocked echelon kernel does not fit on an SM");
-            void* args[] = {&eb};
-            GCU_CHECK(cudaLaunchCooperativeKernel((void*)echelon_blocked_kernel, dim3(prop.multiProcessorCount), dim3(EB_THREADS), args, EB_SMEM, stream));
+            GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EM_THREADS, EM_SMEM));
+            if (occ < 1) throw std::runtime_error("tensor-core echelon kernel does not fit on an SM");
+            void* args[] = {&em};
+            GCU_CHECK(cudaLaunchCooperativeKernel(kern, dim3(prop.multiProcessorCount), dim3(EM_THREADS), args, EM_SMEM, stream));
         } else {
         int occ = 0;
         GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, echelon_kernel, ECH_THREADS, 0));
@@ -390,7 +395,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
             d_out_col.ensure(nnz_new * sizeof(uint32_t));
             d_out_val.ensure(nnz_new * sizeof(uint32_t));
             EmitArgs em{};
-            em.f = f; em.n_cols = nc; em.n_piv = npiv; em.d = d_dprime.as<uint32_t>();
+            em.f = f; em.n_cols = nc; em.n_piv = npiv; em.ld = L.ld_dprime; em.d = d_dprime.as<uint32_t>();
             em.piv_row = d_piv_row.as<uint32_t>(); em.piv_col = d_piv_col.as<uint32_t>();
             em.is_piv_col = d_is_piv.as<uint8_t>(); em.out_ptr = d_out_ptr.as<uint64_t>();
             em.out_col = d_out_col.as<uint32_t>(); em.out_val = d_out_val.as<uint32_t>();
@@ -550,7 +555,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         const std::string k = key ? key : "";
         if (k == "tile_cols") e->opt_tile_cols = value;
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
-        else if (k == "echelon_blocked") e->opt_echelon_blocked = value;
+        else if (k == "echelon_mma") e->opt_echelon_mma = value;
         else if (k == "mc") e->opt_mc = value;
         else if (k == "mc_k") e->opt_mc_k = value;
         else if (k == "rank_hint") e->last_rank = value;

@@ -26,7 +26,7 @@ constexpr uint32_t ECH_INF = 0xffffffffu;
 
 struct EchArgs {
     Fp f;
-    uint32_t n_rows, n_cols;        // D' is n_rows x n_cols (non-pivot columns), row-major u32
+    uint32_t n_rows, n_cols, ld;    // D' is n_rows x n_cols (non-pivot columns), row-major u32, row pitch ld
     uint32_t* d;
     const uint32_t* row_nz;         // [n_rows]
     uint32_t* lead;                 // [2][n_rows]
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
     for (uint32_t r = bid; r < nr; r += nb) {
         uint32_t l = ECH_INF;
         if (a.row_nz[r]) {
-            const uint32_t* row = a.d + (uint64_t)r * nc;
+            const uint32_t* row = a.d + (uint64_t)r * a.ld;
             for (uint32_t j0 = 0; j0 < nc && l == ECH_INF; j0 += ECH_THREADS) {
                 const uint32_t j = j0 + tid;
                 l = block_min_u32(j < nc && row[j] ? j : ECH_INF, sh32);
@@ -139,14 +139,14 @@ __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
         if (key == ~0ull) break;
         const uint32_t c = (uint32_t)(key >> 32);
         const uint32_t pr = a.nz_list[(uint32_t)key];
-        const uint32_t* prow = a.d + (uint64_t)pr * nc;
+        const uint32_t* prow = a.d + (uint64_t)pr * a.ld;
         const uint32_t inv = a.inv_lead[pr];
         if (bid == 0 && tid == 0) { a.piv_row[step] = pr; a.piv_col[step] = c; a.is_piv_col[c] = 1; }
         // rows are dealt to groups of 128 threads: 4 rows per CTA in flight
         for (uint32_t i = bid * ECH_GROUPS + grp; i < nnz_rows; i += nb * ECH_GROUPS) {
             const uint32_t r = a.nz_list[i];
             if (r == pr) { if (gt == 0) ln[r] = ECH_INF; continue; }
-            uint32_t* row = a.d + (uint64_t)r * nc;
+            uint32_t* row = a.d + (uint64_t)r * a.ld;
             const uint32_t fv = row[c];
             const uint32_t lr = lc[r];
             if (fv == 0) { if (gt == 0) ln[r] = lr; continue; }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
 
     // non-zeros per pivot row over the live columns (its own pivot + non-pivot columns)
     for (uint32_t s = bid; s < npiv; s += nb) {
-        const uint32_t* row = a.d + (uint64_t)a.piv_row[s] * nc;
+        const uint32_t* row = a.d + (uint64_t)a.piv_row[s] * a.ld;
         const uint32_t c = a.piv_col[s];
         uint32_t n = 0;
         for (uint32_t j = c + tid; j < nc; j += ECH_THREADS) n += (j == c || (!a.is_piv_col[j] && row[j])) ? 1u : 0u;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
 
 struct EmitArgs {
     Fp f;
-    uint32_t n_cols, n_piv;
+    uint32_t n_cols, n_piv, ld;
     const uint32_t* d;
     const uint32_t* piv_row;
     const uint32_t* piv_col;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) emit_kernel(EmitArgs a) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_base;
     const uint32_t s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t* row = a.d + (uint64_t)a.piv_row[s] * a.n_cols;
+    const uint32_t* row = a.d + (uint64_t)a.piv_row[s] * a.ld;
     const uint32_t c = a.piv_col[s];
     __shared__ uint32_t s_scale;
     if (tid == 0) {

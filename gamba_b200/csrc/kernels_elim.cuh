@@ -62,7 +62,7 @@ struct ElimArgs {
     const uint32_t* diag;
     const uint32_t* dnz;
     const uint32_t* first_piv;
-    uint32_t* dprime;            // [n_local][n_nonpiv] standard residues
+    uint32_t* dprime;            // [n_local][ld_dprime] standard residues
     uint32_t* row_nz;            // [n_local] 1 iff the reduced row is non-zero
     uint32_t* list_k;            // [gridDim][n_top] pivot columns applied so far
     uint32_t* list_m;            // [gridDim][n_top] their multipliers (p - x)
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                     __syncthreads();                  // the next window is read after all warps' updates
                 }
             } else {
-                uint32_t* out = a.dprime + (uint64_t)li * L.n_nonpiv + (t0 - L.n_top);
+                uint32_t* out = a.dprime + (uint64_t)li * L.ld_dprime + (t0 - L.n_top);
                 for (uint32_t i = tid; i < tw; i += ELIM_CTA_THREADS) {
                     const uint32_t v = Acc<SMALLP>::get(acc, i, a);
                     out[i] = v;

@@ -32,6 +32,7 @@ constexpr int WINDOW = 32;                // pivot columns solved together
 
 struct Layout {
     uint32_t n_top, n_bot, n_cols, n_nonpiv, n_rows;
+    uint32_t ld_dprime;                   // row pitch of the dense D' block: n_nonpiv rounded up to 4 (16-byte rows)
     uint32_t tile_cols;                   // T, multiple of WINDOW
     uint32_t n_tiles_piv, n_tiles_nonpiv, n_tiles;
     uint32_t n_windows;                   // ceil(n_top / 32)

@@ -141,7 +141,8 @@ typedef struct gamba_cuda_counters {
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
-/* Options: "tile_cols", "ctas_per_sm" (0 = automatic), "echelon_blocked" (default 1),
+/* Options: "tile_cols", "ctas_per_sm" (0 = automatic), "echelon_mma" (default 1: blocked echelon with int8
+   tensor-core trailing updates; 0: one rank-1 update per pivot),
    "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
    margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);
