@@ -131,6 +131,21 @@ def generate_workload(system: str, min_nnz: int, rank: int, world: int) -> list[
     return files
 
 
+def load_workload(args, rank: int, world: int):
+    """List of step matrices: the named system's F4 steps, or `synthetic:ROWSxCOLS[:density[:bits]]`
+    (BASELINE.json configs[4]: F4-shaped random matrix, every rank generates the same one from the seed)."""
+    from gamba_b200 import load_step
+    from gamba_b200.stepfile import synthetic_step_large
+    if args.system.startswith("synthetic:"):
+        parts = args.system.split(":")
+        nr, nc = (int(x) for x in parts[1].lower().split("x"))
+        dens = float(parts[2]) if len(parts) > 2 else 0.005
+        p = {"15": 32003, "31": 2147483647}[parts[3] if len(parts) > 3 else "31"]
+        return [synthetic_step_large(nr, nc, dens, p)], f"synthetic F4-shaped matrix {nr} x {nc}, density {dens}, p={p}, seed 967557673"
+    files = generate_workload(args.system, args.min_nnz, rank, world)
+    return [load_step(f) for f in files], f"{args.system} F4 step matrices with >= {args.min_nnz} nnz"
+
+
 def bytes_alg(step, fma_top: int) -> float:
     w = 2 if step.p < 65536 else 4
     return fma_top * (4 + w) + step.nnz * (4 + w) + step.n_bot * step.n_nonpiv * 8
@@ -161,8 +176,7 @@ def run_reference(args, rank: int, world: int):
     from gamba_b200 import load_step
     from oracle import oracle
     oracle.build()
-    files = generate_workload(args.system, args.min_nnz, 0, 1)
-    steps = [load_step(f) for f in files]
+    steps, wl_desc = load_workload(args, 0, 1)
     # smallest matrix of the batch, thinned so that one bench step is a few seconds of CPU work
     s = min(steps, key=lambda x: x.nnz * x.n_bot)
     est_fma = 0.5 * s.n_bot * (s.nnz / s.n_rows) * s.n_top * 0.25   # rough: quarter of the pivots hit per row
@@ -184,7 +198,7 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64 accumulators over F_p (p=32003)", "data": "synthetic (generated system, no dataset)",
-        "config": {"workload": f"{args.system} F4 step matrices with >= {args.min_nnz} nnz", "sample": desc},
+        "config": {"workload": wl_desc, "sample": desc},
         "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": desc, "cpu": cpu_model(),
                          "note": "oracle port; the reference's own engine (linalg_v3.hpp, kernel/*) is closed source"},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -202,8 +216,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    files = generate_workload(args.system, args.min_nnz, rank, world)
-    steps = [load_step(f) for f in files]
+    steps, wl_desc = load_workload(args, rank, world)
     if args.max_matrices:
         steps = sorted(steps, key=lambda s: -s.nnz)[: args.max_matrices]
     total_nnz = sum(s.nnz for s in steps)
@@ -223,10 +236,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     engines = []
     gather = parallel.make_allgather() if world > 1 else None
+    bcast = parallel.make_broadcast() if world > 1 and not args.no_bcast else None
     for s in steps:
         e = LinalgEngine(s.p, device=local_rank, rank=rank, world_size=world)
         if gather:
             e.set_allgather(gather)
+        if bcast:
+            e.set_broadcast(bcast)
         for kv in args.opt:
             k, v = kv.split("=")
             e.set_option(k, int(v))
@@ -242,8 +258,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return sum(e.counters()["kernel_launches"] for e in engines)
 
     # ---- value: steps resident in HBM --------------------------------------------------------
+    def mine(s):   # with the NCCL broadcast only rank 0 hands the step over
+        return s if (rank == 0 or not bcast) else None
     for e, s in zip(engines, steps):
-        e.stage(s)
+        e.stage(mine(s))
     for _ in range(args.warmup):
         for e in engines:
             e.reduce_staged()
@@ -268,13 +286,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- e2e: pinned host buffers in, host buffers out -----------------------------------------
     for _ in range(max(1, args.warmup // 2)):
         for e, s in zip(engines, steps):
-            e.reduce(s)
+            e.reduce(mine(s))
     sync()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(args.steps):
         for e, s in zip(engines, steps):
-            e.reduce(s)
+            e.reduce(mine(s))
             h2d += e.last["h2d_bytes"]; d2h += e.last["d2h_bytes"]
     sync()
     t_e2e = time.perf_counter() - t0
@@ -303,9 +321,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64 accumulators over F_p (p=%d)" % steps[0].p, "data": "synthetic (generated system, no dataset)",
-            "config": {"workload": f"{args.system} F4 step matrices with >= {args.min_nnz} nnz ({len(steps)} matrices, "
+            "config": {"workload": f"{wl_desc} ({len(steps)} matrices, "
                                    f"{total_nnz} nnz per pass, largest {max(s.n_rows for s in steps)} x {max(s.n_cols for s in steps)})",
-                       "parallelism": f"C|D rows sharded r % {world}, A|B replicated, all-gather of D'" if world > 1 else "1 GPU",
+                       "parallelism": (f"C|D rows sharded r % {world}, step uploaded by rank 0 and replicated by NCCL broadcast, "
+                                       f"NCCL all-gather of D' rows, echelon replicated") if world > 1 else "1 GPU",
                        "l2": "inputs larger than L2 (every pass cycles through all matrices; smallest staged step > 126 MB)",
                        "max_spairs": 2000, "tile_cols": c["tile_cols"], "acc_bits": c["acc_bits"]},
             "e2e": {"value": total_nnz * args.steps / t_e2e, "unit": "nnz/s", "h2d_bytes_per_step": h2d // args.steps,
@@ -358,6 +377,7 @@ def main():
     ap.add_argument("--max-matrices", type=int, default=0)
     ap.add_argument("--ref-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bcast", action="store_true", help="N>1: every rank uploads the step itself (no NCCL broadcast)")
     ap.add_argument("--opt", nargs="*", default=[], help="engine options key=value (gamba_cuda_set_option)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -37,10 +37,11 @@ class Counters(C.Structure):
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+BROADCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 
 # every symbol include/gamba_cuda.h declares
 SYMBOLS = ["gamba_cuda_abi_version", "gamba_cuda_last_error", "gamba_cuda_create", "gamba_cuda_destroy",
-           "gamba_cuda_reduce", "gamba_cuda_stage", "gamba_cuda_reduce_staged", "gamba_cuda_set_allgather",
+           "gamba_cuda_reduce", "gamba_cuda_stage", "gamba_cuda_reduce_staged", "gamba_cuda_set_allgather", "gamba_cuda_set_broadcast",
            "gamba_cuda_get_counters", "gamba_cuda_set_option"]
 
 _lib = None
@@ -63,6 +64,7 @@ def load() -> C.CDLL:
     lib.gamba_cuda_stage.argtypes = [C.c_void_p, C.POINTER(StepIn)]
     lib.gamba_cuda_reduce_staged.argtypes = [C.c_void_p, C.POINTER(StepOut)]
     lib.gamba_cuda_set_allgather.argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p]
+    lib.gamba_cuda_set_broadcast.argtypes = [C.c_void_p, BROADCAST_FN, C.c_void_p]
     lib.gamba_cuda_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.gamba_cuda_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     _lib = lib

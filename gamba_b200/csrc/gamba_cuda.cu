@@ -114,6 +114,10 @@ struct gamba_cuda_engine {
 
     gamba_cuda_allgather_fn gather_fn = nullptr;
     void* gather_user = nullptr;
+    gamba_cuda_broadcast_fn bcast_fn = nullptr;
+    void* bcast_user = nullptr;
+    gcu::DevBuf d_hdr;
+    gcu::HostBuf h_hdr;
 
     gamba_cuda_counters ctr{};
     double t_elim_dev = 0, t_ech_dev = 0;
@@ -163,28 +167,51 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     ctr.tile_cols = t; ctr.n_tiles = L.n_tiles; ctr.acc_bits = 32 * words_per_col;
 }
 
+// Sizes of a step; with world_size > 1 and a broadcast callback only rank 0 holds the step on the host
+// and this header travels first ("ncclBroadcast of the flattened A|B").
+struct StepHdr { uint32_t n_top, n_bot, n_cols, n_arr; uint64_t nnz, pool_len; uint32_t flags, pad; };
+
 void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     const double t0 = wall_s();
     staged = false; eliminated = false;
-    if (in->n_cols < in->n_top) throw std::runtime_error("n_cols < n_top");
-    const uint32_t n_rows = in->n_top + in->n_bot;
-    if (in->row_ptr[n_rows] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
-    choose_layout(in->n_top, in->n_bot, in->n_cols);
-    flags = in->flags; nnz = in->nnz;
+    const bool use_bcast = cfg.world_size > 1 && bcast_fn != nullptr;
+    const bool have = !use_bcast || cfg.rank == 0;       // this rank uploads the step from its host buffers
+    if (have && !in) throw std::runtime_error("no step passed (only ranks > 0 of a broadcasting group may pass NULL)");
+    StepHdr hd{};
+    if (have) {
+        if (in->n_cols < in->n_top) throw std::runtime_error("n_cols < n_top");
+        if (in->row_ptr[in->n_top + in->n_bot] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
+        hd.n_top = in->n_top; hd.n_bot = in->n_bot; hd.n_cols = in->n_cols; hd.n_arr = in->n_coeff_arrays;
+        hd.nnz = in->nnz; hd.flags = in->flags;
+        for (uint32_t i = 0; i < in->n_coeff_arrays; ++i) hd.pool_len += in->coeff_len[i];
+    }
+    if (use_bcast) {
+        d_hdr.ensure(sizeof(StepHdr)); h_hdr.ensure(sizeof(StepHdr));
+        if (have) {
+            std::memcpy(h_hdr.p, &hd, sizeof hd);
+            GCU_CHECK(cudaMemcpyAsync(d_hdr.p, h_hdr.p, sizeof hd, cudaMemcpyHostToDevice, stream));
+        }
+        if (bcast_fn(bcast_user, d_hdr.p, sizeof hd, 0, stream)) throw std::runtime_error("broadcast of the step header failed");
+        GCU_CHECK(cudaMemcpyAsync(h_hdr.p, d_hdr.p, sizeof hd, cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaStreamSynchronize(stream));
+        std::memcpy(&hd, h_hdr.p, sizeof hd);
+    }
+    const uint32_t n_rows = hd.n_top + hd.n_bot;
+    choose_layout(hd.n_top, hd.n_bot, hd.n_cols);
+    flags = hd.flags; nnz = hd.nnz;
     if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
     if (nnz + 3ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
 
     // shared coefficient arrays -> one u32 pool
-    const uint32_t na = in->n_coeff_arrays;
+    const uint32_t na = hd.n_arr;
+    const uint64_t tot = hd.pool_len;
     h_off.ensure((na + 1) * sizeof(uint64_t));
     uint64_t* off = h_off.as<uint64_t>();
-    uint64_t tot = 0;
-    for (uint32_t i = 0; i < na; ++i) { off[i] = tot; tot += in->coeff_len[i]; }
-    off[na] = tot;
     h_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
     uint32_t* pool = h_pool.as<uint32_t>();
-    for (uint32_t i = 0; i < na; ++i) {
+    if (have) { uint64_t t = 0; for (uint32_t i = 0; i < na; ++i) { off[i] = t; t += in->coeff_len[i]; } off[na] = t; }
+    for (uint32_t i = 0; have && i < na; ++i) {
         const uint32_t n = in->coeff_len[i];
         uint32_t* dst = pool + off[i];
         switch (cfg.coeff_bytes) {
@@ -199,12 +226,22 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
     d_coeff_off.ensure((na + 1) * sizeof(uint64_t));
     d_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
-    GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-    GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-    GCU_CHECK(cudaMemcpyAsync(d_pool.p, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-    h2d_bytes = (n_rows + 1) * 8ull + nnz * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull;
+    h2d_bytes = 0;
+    if (have) {
+        GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+        GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+        GCU_CHECK(cudaMemcpyAsync(d_pool.p, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        h2d_bytes = (n_rows + 1) * 8ull + nnz * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull;
+    }
+    if (use_bcast) {   // A|B and C|D replicated over NVLink instead of one H2D copy per rank
+        const std::pair<void*, size_t> bufs[] = {{d_row_ptr.p, (n_rows + 1) * sizeof(uint64_t)}, {d_col.p, nnz * sizeof(uint32_t)},
+                                                 {d_coeff_id.p, n_rows * sizeof(uint32_t)}, {d_coeff_off.p, (na + 1) * sizeof(uint64_t)},
+                                                 {d_pool.p, tot * sizeof(uint32_t)}};
+        for (auto const& b : bufs)
+            if (b.second && bcast_fn(bcast_user, b.first, b.second, 0, stream)) throw std::runtime_error("broadcast of the step failed");
+    }
 
     const uint64_t n_cnt = (uint64_t)n_rows * L.n_tiles + 1;
     const uint64_t n_diag = std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1);
@@ -544,6 +581,10 @@ int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_
 
 int gamba_cuda_set_allgather(gamba_cuda_engine* e, gamba_cuda_allgather_fn fn, void* user) {
     return guarded([&] { e->gather_fn = fn; e->gather_user = user; });
+}
+
+int gamba_cuda_set_broadcast(gamba_cuda_engine* e, gamba_cuda_broadcast_fn fn, void* user) {
+    return guarded([&] { e->bcast_fn = fn; e->bcast_user = user; });
 }
 
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c) {

@@ -245,6 +245,9 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             const uint32_t t0 = lay_tile_start(L, t), tw = lay_tile_width(L, t);
             const uint32_t* seg_s = a.seg + (uint64_t)t * nr;
             const uint32_t* seg_e = seg_s + nr;
+            // the previous tile is read (last window / write-out of D') by other threads than those that
+            // zero the same words here (two words per column for p >= 2^16): cyclic9-31 lost updates without this
+            __syncthreads();
             for (uint32_t i = tid; i < acc_words; i += ELIM_CTA_THREADS) acc[i] = 0;
             __syncthreads();
             uint32_t absorbed = 1;   // rows added into this tile since the last normalisation

@@ -69,18 +69,20 @@ class LinalgEngine:
             raise RuntimeError(f"{what}: " + self.lib.gamba_cuda_last_error().decode())
 
     # -- the reference-facing calls ------------------------------------------------
-    def reduce(self, s: Step, final: bool = False) -> Rows:
-        """Host buffers in, host buffers out (H2D + kernels + D2H)."""
-        sin, out = self._step_in(s, _lib.STEP_FINAL if final else 0), _lib.StepOut()
-        self._check(self.lib.gamba_cuda_reduce(self.h, C.byref(sin), C.byref(out)), "gamba_cuda_reduce")
+    def reduce(self, s: Step | None, final: bool = False) -> Rows:
+        """Host buffers in, host buffers out (H2D + kernels + D2H). `s` may be None on ranks > 0 of a
+        broadcasting group (set_broadcast): the step then arrives from rank 0 over NCCL."""
+        out = _lib.StepOut()
+        sin = C.byref(self._step_in(s, _lib.STEP_FINAL if final else 0)) if s is not None else None
+        self._check(self.lib.gamba_cuda_reduce(self.h, sin, C.byref(out)), "gamba_cuda_reduce")
         return self._rows(out)
 
     def reduce_final(self, s: Step) -> Rows:
         return self.reduce(s, final=True)
 
-    def stage(self, s: Step, final: bool = False) -> None:
-        sin = self._step_in(s, _lib.STEP_FINAL if final else 0)
-        self._check(self.lib.gamba_cuda_stage(self.h, C.byref(sin)), "gamba_cuda_stage")
+    def stage(self, s: Step | None, final: bool = False) -> None:
+        sin = C.byref(self._step_in(s, _lib.STEP_FINAL if final else 0)) if s is not None else None
+        self._check(self.lib.gamba_cuda_stage(self.h, sin), "gamba_cuda_stage")
 
     def reduce_staged(self) -> Rows:
         out = _lib.StepOut()
@@ -94,6 +96,19 @@ class LinalgEngine:
 
     def set_option(self, key: str, value: int) -> None:
         self._check(self.lib.gamba_cuda_set_option(self.h, key.encode(), int(value)), "gamba_cuda_set_option")
+
+    def set_broadcast(self, fn) -> None:
+        """fn(buf_ptr, nbytes, root, stream_ptr) -> None; see parallel.make_broadcast."""
+        def tramp(_user, buf, nbytes, root, stream):
+            try:
+                fn(buf, nbytes, root, stream)
+                return 0
+            except Exception:  # noqa: BLE001 - reported through the C status code
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._bcb = _lib.BROADCAST_FN(tramp)
+        self._check(self.lib.gamba_cuda_set_broadcast(self.h, self._bcb, None), "gamba_cuda_set_broadcast")
 
     def set_allgather(self, fn) -> None:
         """fn(send_ptr, recv_ptr, bytes_per_rank, stream_ptr) -> None; see parallel.py."""

@@ -428,7 +428,9 @@ void F4::run() {
     if (rounds)
         std::printf("%4s %4s %14s %22s %8s %9s %10s %10s\n", "step", "deg", "pairs/queue",
                     "matrix (rows x cols)", "dens %", "new rows", "linalg s", "step s");
+    bool stopped = false;
     while (!P_.empty() && !trivial_) {
+        if (prm_.stop_after > 0 && (long)stats.steps >= prm_.stop_after) { stopped = true; break; }
         double ts = now_s();
         size_t prev = G_.size();
         int32_t deg; size_t queue = P_.size();
@@ -468,7 +470,7 @@ void F4::run() {
                     G_[i].redundant = true; break;
                 }
             }
-        if (!prm_.no_reduce) final_reduce();
+        if (!prm_.no_reduce && !stopped) final_reduce();
         else {
             std::vector<Poly> out;
             for (uint32_t i : nonredundant()) out.push_back(std::move(G_[i]));

@@ -28,6 +28,7 @@ struct Params {
     int threads = 1;
     std::string dump_dir;       // write every step matrix (+ result) here
     long dump_min_nnz = 0;
+    long stop_after = 0;        // debugging: leave the F4 loop after this many steps (0 = run to the end)
 };
 
 struct Stats {

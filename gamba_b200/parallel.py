@@ -43,6 +43,17 @@ def make_allgather(group=None):
     return gather
 
 
+def make_broadcast(group=None):
+    """Callback for LinalgEngine.set_broadcast: in-place broadcast of a device buffer from `root`
+    (NCCL over NVLink), ordered on the engine's stream."""
+    def bcast(buf_ptr, nbytes, root, stream_ptr):
+        buf = torch.as_tensor(_DevMem(buf_ptr, nbytes), device="cuda")
+        ext = torch.cuda.ExternalStream(stream_ptr)
+        with torch.cuda.stream(ext):
+            dist.broadcast(buf, src=root, group=group)
+    return bcast
+
+
 def allgather_rows(local_block: torch.Tensor, group=None) -> torch.Tensor:
     """Host/any-backend variant: local_block is [rows_per_rank, n_nonpiv]; returns the gathered
     [world * rows_per_rank, n_nonpiv] block in the layout the engine's echelon reads."""

@@ -126,3 +126,39 @@ def synthetic_step(n_rows: int, n_cols: int, density: float, p: int, seed: int =
     coeff_id = rng.integers(0, n_arr, size=n_rows).astype(np.uint32)
     return Step(p, n_top, n_bot, n_cols, row_ptr, col, coeff_id,
                 np.full(n_arr, row_len, dtype=np.uint32), pool_rows.reshape(-1).copy())
+
+
+def synthetic_step_large(n_rows: int, n_cols: int, density: float, p: int, seed: int = 967557673,
+                         top_frac: float = 0.92, share: int = 25, chunk_rows: int = 8192) -> Step:
+    """Vectorised generator of the same F4-shaped family for the BASELINE.json configs[4] sweep
+    (50k x 80k ... 500k x 800k at ~0.5 % density): per row `density * n_cols` columns drawn
+    uniformly right of the lead (duplicates dropped, so rows near the right edge get shorter)."""
+    rng = np.random.default_rng(seed)
+    n_top = min(max(1, int(top_frac * n_rows)), n_cols - 1)
+    n_bot = max(1, n_rows - n_top)
+    n_rows = n_top + n_bot
+    row_len = max(2, int(round(density * n_cols)))
+    piv_orig = np.sort(rng.choice(n_cols - 1, size=n_top, replace=False))
+    is_piv = np.zeros(n_cols, dtype=bool); is_piv[piv_orig] = True
+    newcol = np.empty(n_cols, dtype=np.uint32)
+    newcol[is_piv] = np.arange(n_top, dtype=np.uint32)
+    newcol[~is_piv] = n_top + np.arange(n_cols - n_top, dtype=np.uint32)
+    leads = np.concatenate([piv_orig, np.sort(rng.choice(piv_orig, size=n_bot))[::-1]]).astype(np.int64)
+    parts, lens = [], np.empty(n_rows, dtype=np.int64)
+    for r0 in range(0, n_rows, chunk_rows):
+        ld = leads[r0:r0 + chunk_rows]
+        avail = (n_cols - 1 - ld)[:, None]
+        c = ld[:, None] + 1 + (rng.random((len(ld), row_len - 1)) * avail).astype(np.int64)
+        c.sort(axis=1)
+        c = np.concatenate([ld[:, None], c], axis=1)
+        keep = np.ones(c.shape, dtype=bool)
+        keep[:, 1:] = (c[:, 1:] != c[:, :-1]) & (avail > 0)
+        lens[r0:r0 + chunk_rows] = keep.sum(axis=1)
+        parts.append(newcol[c[keep]])
+    row_ptr = np.zeros(n_rows + 1, dtype=np.uint64); np.cumsum(lens, out=row_ptr[1:])
+    n_arr = max(1, n_rows // share)
+    pool_rows = rng.integers(1, p, size=(n_arr, row_len), dtype=np.int64).astype(np.uint32)
+    pool_rows[:, 0] = 1
+    coeff_id = rng.integers(0, n_arr, size=n_rows).astype(np.uint32)
+    return Step(p, n_top, n_bot, n_cols, row_ptr, np.concatenate(parts), coeff_id,
+                np.full(n_arr, row_len, dtype=np.uint32), pool_rows.reshape(-1).copy())

@@ -123,6 +123,14 @@ typedef int (*gamba_cuda_allgather_fn)(void* user, const void* send_dev, void* r
                                        size_t bytes_per_rank, void* stream);
 int gamba_cuda_set_allgather(gamba_cuda_engine* e, gamba_cuda_allgather_fn fn, void* user);
 
+/* Replication of the step ("ncclBroadcast of the flattened A|B"). With world_size > 1 and
+   this callback set, only rank 0 copies the step from its host buffers; gamba_cuda_stage / gamba_cuda_reduce
+   on the other ranks take in == NULL and receive the flattened arrays (and their sizes) device to device.
+   bcast(user, buf_dev, bytes, root, stream) must behave like ncclBroadcast in place on `stream`. Without the
+   callback every rank passes the same step and uploads it itself. */
+typedef int (*gamba_cuda_broadcast_fn)(void* user, void* buf_dev, size_t bytes, int root, void* stream);
+int gamba_cuda_set_broadcast(gamba_cuda_engine* e, gamba_cuda_broadcast_fn fn, void* user);
+
 /* Introspection used by the benchmark and the tests. */
 typedef struct gamba_cuda_counters {
     uint64_t kernel_launches;          /* kernels of this library launched since create         */

@@ -228,3 +228,12 @@ def test_monte_carlo_mode_is_bit_exact(step_dirs):
         assert c["mc_attempts"] >= 1
     assert used > 0
     eng.close()
+
+
+def test_31bit_prime_with_several_non_pivot_tiles(step_dirs, engines):
+    """Regression (cyclic9-31 steps 9-10): two words per accumulator column for p >= 2^16 and more than
+    one non-pivot tile — the tile was zeroed for the next pass while other threads still wrote it out."""
+    d = step_dirs("cyclic9-31", ("--stop-after", "10", "--dump-min-nnz", "1000000"))
+    eng = engines(2147483647)
+    assert check_dir(d, eng) >= 2
+    assert eng.counters()["n_tiles"] >= 3

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--max-steps", type=int, default=10 ** 9)
     ap.add_argument("--opt", nargs="*", default=[])
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--stop-after", type=int, default=0)
     a = ap.parse_args()
     dirs = [a.dir] if a.dir else []
     oracle.build()
@@ -32,7 +33,7 @@ def main():
         inp = systems.write_system(name, os.path.join(d, name + ".txt"))
         t = time.time()
         subprocess.run([oracle.DRIVER, "-i", inp, "-o", os.path.join(d, "out.txt"), "-v", "0", "--dump-steps", d,
-                        "--dump-min-nnz", str(a.min_nnz)], check=True)
+                        "--dump-min-nnz", str(a.min_nnz)] + (["--stop-after", str(a.stop_after)] if a.stop_after else []), check=True)
         print(f"# {name}: oracle driver {time.time() - t:.1f}s -> {d}", flush=True)
         dirs.append(d)
     bad = 0
