@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <stdexcept>
 
 namespace gb {
@@ -15,6 +16,8 @@ F4::F4(const PolySystem& in, const Params& prm, Engine& eng)
     : in_(in), prm_(prm), eng_(eng), p_(in.p) {
     if (prm_.num_elim < 0 || (prm_.num_elim != 0 && (size_t)prm_.num_elim >= in.vars.size()))
         throw std::runtime_error("Elimination block size must be smaller than the number of variables.");
+    nthreads_ = prm_.threads > 0 ? prm_.threads : std::max(1, std::min((int)std::thread::hardware_concurrency(), 16));
+    pool_ = std::make_unique<ThreadPool>(nthreads_);
     cx_.init((int)in.vars.size(), prm_.num_elim, prm_.seed);
     bt_ = MonoTable(&cx_, 1 << 16);
     st_ = MonoTable(&cx_, 1 << 16);
@@ -84,6 +87,7 @@ void F4::update(uint32_t h) {
     eh = ehv.data();
     const uint64_t mh = G_[h].lm_mask;
 
+    double tu = now_s();
     // B criterion on the old pairs
     {
         size_t w = 0;
@@ -106,13 +110,21 @@ void F4::update(uint32_t h) {
         P_.resize(w);
     }
 
-    struct NP { uint32_t i, lcm; int32_t deg; uint64_t mask; bool coprime, dead; };
+    upd_t_[0] += now_s() - tu; tu = now_s();
+    // Candidate pairs (i, h). Their lcms stay in a local, contiguous arena until the criteria have run:
+    // ~99 % of the candidates are discarded, and only the survivors' lcms enter the basis table.
+    struct NP { uint32_t i, at; int32_t deg; uint64_t mask, key; bool coprime, dead; };
     std::vector<NP> np;
     np.reserve(h);
-    std::vector<uint16_t> el(st);
+    std::vector<uint16_t>& L = upd_lcm_;
+    L.clear();
+    bool keys_ok = cx_.nelim == 0;
     for (uint32_t i = 0; i < h; ++i) {
         if (G_[i].redundant) continue;
         const uint16_t* ei = bt_.e(G_[i].mon[0]);
+        const size_t at = L.size();
+        L.resize(at + st);
+        uint16_t* el = &L[at];
         uint32_t d = 0, d1 = 0; bool cop = true;
         for (int v = 0; v < nv; ++v) {
             uint16_t a = ei[2 + v], b = eh[2 + v];
@@ -122,36 +134,51 @@ void F4::update(uint32_t h) {
         }
         if (d >= (1u << 16)) throw std::overflow_error("degree overflow");
         el[0] = (uint16_t)d; el[1] = (uint16_t)d1;
-        uint32_t l = bt_.insert(el.data(), cx_.hash(el.data()));
-        np.push_back({i, l, (int32_t)d, G_[i].lm_mask | mh, cop, false});
+        // order-preserving 64-bit prefix of the grevlex comparison (degree, then the last 7 variables reversed)
+        uint64_t key = 0;
+        if (cx_.nelim == 0) {
+            keys_ok &= d < 256;
+            key = (uint64_t)(d & 0xff) << 56;
+            for (int v = nv - 1, sh = 48; v >= 0 && sh >= 0; --v, sh -= 8) key |= (uint64_t)(0xffu - (el[2 + v] & 0xffu)) << sh;
+        }
+        np.push_back({i, (uint32_t)(at / st), (int32_t)d, G_[i].lm_mask | mh, key, cop, false});
     }
+    auto ex_of = [&](const NP& q) { return &L[(size_t)q.at * st]; };
+    auto same = [&](const NP& a, const NP& b) { return std::memcmp(ex_of(a), ex_of(b), st * sizeof(uint16_t)) == 0; };
+    upd_t_[1] += now_s() - tu; tu = now_s();
     // increasing lcm; equal lcm: coprime first, then older generator first
     std::sort(np.begin(), np.end(), [&](NP const& a, NP const& b) {
-        if (a.lcm != b.lcm) return cx_.cmp(bt_.e(a.lcm), bt_.e(b.lcm)) < 0;
+        if (keys_ok && a.key != b.key) return a.key < b.key;
+        const int c = cx_.cmp(ex_of(a), ex_of(b));
+        if (c != 0) return c < 0;
         if (a.coprime != b.coprime) return a.coprime;
         return a.i < b.i;
     });
+    upd_t_[2] += now_s() - tu; tu = now_s();
     // M criterion: a strictly smaller lcm divides
     for (size_t a = 0; a < np.size(); ++a) {
         if (np[a].coprime) continue;
-        const uint16_t* ea = bt_.e(np[a].lcm);
+        const uint16_t* ea = ex_of(np[a]);
         const uint64_t nm = ~np[a].mask;
         for (size_t b = 0; b < a; ++b) {
             if (np[b].mask & nm) continue;
-            if (np[b].lcm == np[a].lcm) continue;
-            if (cx_.divides(bt_.e(np[b].lcm), ea)) { np[a].dead = true; break; }
+            if (same(np[b], np[a])) continue;
+            if (cx_.divides(ex_of(np[b]), ea)) { np[a].dead = true; break; }
         }
     }
+    upd_t_[3] += now_s() - tu; tu = now_s();
     // F criterion: keep the first pair of every run of equal lcm
     for (size_t a = 1; a < np.size(); ++a) {
         if (np[a].coprime || np[a].dead) continue;
-        for (size_t b = a; b > 0 && np[b - 1].lcm == np[a].lcm; --b)
+        for (size_t b = a; b > 0 && same(np[b - 1], np[a]); --b)
             if (!np[b - 1].dead) { np[a].dead = true; break; }
     }
     for (auto const& q : np) {
         if (q.dead || q.coprime) { ++stats.gm_removed; continue; }
-        P_.push_back({q.i, h, q.lcm, q.deg});
+        const uint16_t* el = ex_of(q);
+        P_.push_back({q.i, h, bt_.insert(el, cx_.hash(el)), q.deg});
     }
+    upd_t_[4] += now_s() - tu; tu = now_s();
     // older generators whose lead is divisible by the new lead become redundant
     for (uint32_t i = 0; i < h; ++i) {
         if (G_[i].redundant) continue;
@@ -200,22 +227,51 @@ void F4::clear_step() {
     has_red_.clear();
 }
 
-void F4::add_row(uint32_t gen, const uint16_t* q, uint32_t hq, bool top) {
-    const Poly& f = G_[gen];
+// Append the rows gen[i] * x^q[i] (q: flat exponent vectors of full stride) to the step: every term
+// is multiplied and looked up / inserted in the step table. The rows are independent, so they are
+// generated by all threads against the concurrent table (mono.hpp: insert_mt); row numbering is the
+// order of the batch, hence deterministic, and nothing downstream depends on the handle numbering.
+void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>& qs, const std::vector<uint32_t>& hqs,
+                  const std::vector<uint8_t>& tops) {
     const int st = cx_.stride;
-    uint16_t tmp[258];
-    size_t base = row_mon_.size();
-    row_mon_.resize(base + f.mon.size());
-    for (size_t k = 0; k < f.mon.size(); ++k) {
-        const uint16_t* a = bt_.e(f.mon[k]);
-        for (int i = 0; i < st; ++i) tmp[i] = (uint16_t)(a[i] + q[i]);
-        row_mon_[base + k] = st_.insert(tmp, bt_.hv[f.mon[k]] + hq);
+    const size_t nb = gens.size();
+    if (nb == 0) return;
+    const size_t r0 = row_gen_.size();
+    uint64_t terms = 0;
+    row_off_.reserve(row_off_.size() + nb);
+    for (size_t i = 0; i < nb; ++i) { terms += G_[gens[i]].mon.size(); row_off_.push_back(row_off_[r0] + terms); }
+    row_mon_.resize(row_off_.back());
+    row_gen_.insert(row_gen_.end(), gens.begin(), gens.end());
+    row_top_.insert(row_top_.end(), tops.begin(), tops.end());
+    // Sub-batches: the table must have room for every term of a batch being NEW (no growth inside the
+    // parallel region), while almost all terms are hits - so a batch is capped near the table's size.
+    for (size_t b0 = 0; b0 < nb;) {
+        double tA = now_s();
+        const uint64_t cap = std::max<uint64_t>(1u << 20, st_.size());
+        size_t b1 = b0; uint64_t bt = 0;
+        while (b1 < nb && (b1 == b0 || bt + G_[gens[b1]].mon.size() <= cap)) bt += G_[gens[b1++]].mon.size();
+        st_.reserve_more(bt);
+        dbg_t_[0] += now_s() - tA; tA = now_s();
+        pool_->parallel_for(b1 - b0, 8, [&](size_t i0, size_t i1) {
+            for (size_t i = b0 + i0; i < b0 + i1; ++i) {
+                const Poly& f = G_[gens[i]];
+                const uint16_t* q = &qs[i * st];
+                const uint32_t hq = hqs[i];
+                uint32_t* out = &row_mon_[row_off_[r0 + i]];
+                uint16_t tmp[258];
+                for (size_t k = 0; k < f.mon.size(); ++k) {
+                    const uint16_t* a = bt_.e(f.mon[k]);
+                    for (int j = 0; j < st; ++j) tmp[j] = (uint16_t)(a[j] + q[j]);
+                    out[k] = st_.insert_mt(tmp, bt_.hv[f.mon[k]] + hq);
+                }
+            }
+        });
+        dbg_t_[1] += now_s() - tA;
+        b0 = b1;
     }
-    row_off_.push_back(row_mon_.size());
-    row_gen_.push_back(gen);
-    row_top_.push_back(top ? 1 : 0);
     if (has_red_.size() < st_.size()) has_red_.resize(st_.size(), 0);
-    if (top) has_red_[row_mon_[base]] = 1;
+    for (size_t i = 0; i < nb; ++i)
+        if (tops[i]) has_red_[row_mon_[row_off_[r0 + i]]] = 1;
 }
 
 // Rows of the selected pairs (source/matrix.hpp:215-347): per distinct lcm the
@@ -223,7 +279,9 @@ void F4::add_row(uint32_t gen, const uint16_t* q, uint32_t hq, bool top) {
 void F4::build_pair_rows(long n_sel) {
     double t0 = now_s();
     const int st = cx_.stride;
-    std::vector<uint32_t> gens;
+    std::vector<uint32_t> gens, bg, bh;
+    std::vector<uint16_t> bq;
+    std::vector<uint8_t> bt;
     std::vector<uint16_t> q(st);
     for (long a = 0; a < n_sel;) {
         long b = a; gens.clear();
@@ -240,10 +298,11 @@ void F4::build_pair_rows(long n_sel) {
         for (size_t k = 0; k < gens.size(); ++k) {
             const uint16_t* lm = bt_.e(G_[gens[k]].mon[0]);
             for (int i = 0; i < st; ++i) q[i] = (uint16_t)(el[i] - lm[i]);
-            add_row(gens[k], q.data(), cx_.hash(q.data()), k == 0);
+            bg.push_back(gens[k]); bq.insert(bq.end(), q.begin(), q.end()); bh.push_back(cx_.hash(q.data())); bt.push_back(k == 0);
         }
         a = b;
     }
+    add_rows(bg, bq, bh, bt);
     P_.erase(P_.begin(), P_.begin() + n_sel);
     stats.t_rows += now_s() - t0;
 }
@@ -272,23 +331,45 @@ void F4::symbolic() {
         cmask[c] = G_[cand[c]].lm_mask;
         std::memcpy(&cexp[c * nv], bt_.e(G_[cand[c]].mon[0]) + 2, nv * sizeof(uint16_t));
     }
-    std::vector<uint16_t> q(st), em(st);
-    for (uint32_t m = 0; m < st_.size(); ++m) {
-        if (m < has_red_.size() && has_red_[m]) continue;
-        std::memcpy(em.data(), st_.e(m), st * sizeof(uint16_t));
-        const uint64_t nm = ~cx_.divmask(em.data());
-        size_t hit = nc;
-        for (size_t c = 0; c < nc; ++c) {
-            if (cmask[c] & nm) continue;
-            const uint16_t* le = &cexp[c * nv];
-            bool ok = true;
-            for (int v = 0; v < nv; ++v) if (le[v] > em[2 + v]) { ok = false; break; }
-            if (ok) { hit = c; break; }
+    // Waves: all monomials that appeared in the previous wave are searched for a reducer in parallel
+    // (read-only), then the multiplied reducer rows are generated in parallel. The closure - hence the
+    // matrix - is the same as with the reference's one-monomial-at-a-time worklist.
+    std::vector<uint32_t> hit, bg, bh;
+    std::vector<uint16_t> bq;
+    std::vector<uint8_t> bt;
+    for (size_t m0 = 0; m0 < st_.size();) {
+        const size_t m1 = st_.size();
+        if (has_red_.size() < m1) has_red_.resize(m1, 0);
+        hit.assign(m1 - m0, (uint32_t)nc);
+        double tB = now_s();
+        pool_->parallel_for(m1 - m0, 64, [&](size_t a0, size_t a1) {
+        for (size_t m = m0 + a0; m < m0 + a1; ++m) {
+            if (has_red_[m]) continue;
+            const uint16_t* em = st_.e((uint32_t)m);
+            const uint64_t nm = ~cx_.divmask(em);
+            for (size_t c = 0; c < nc; ++c) {
+                if (cmask[c] & nm) continue;
+                const uint16_t* le = &cexp[c * nv];
+                bool ok = true;
+                for (int v = 0; v < nv; ++v) if (le[v] > em[2 + v]) { ok = false; break; }
+                if (ok) { hit[m - m0] = (uint32_t)c; break; }
+            }
         }
-        if (hit == nc) continue;
-        const uint16_t* lm = bt_.e(G_[cand[hit]].mon[0]);
-        for (int i = 0; i < st; ++i) q[i] = (uint16_t)(em[i] - lm[i]);
-        add_row(cand[hit], q.data(), cx_.hash(q.data()), true);
+        });
+        dbg_t_[2] += now_s() - tB; dbg_waves_++;
+        bg.clear(); bq.clear(); bh.clear(); bt.clear();
+        for (size_t m = m0; m < m1; ++m) {
+            const uint32_t c = hit[m - m0];
+            if (c == nc) continue;
+            const uint16_t* em = st_.e((uint32_t)m);
+            const uint16_t* lm = bt_.e(G_[cand[c]].mon[0]);
+            const size_t o = bq.size();
+            bq.resize(o + st);
+            for (int i = 0; i < st; ++i) bq[o + i] = (uint16_t)(em[i] - lm[i]);
+            bg.push_back(cand[c]); bh.push_back(cx_.hash(&bq[o])); bt.push_back(1);
+        }
+        add_rows(bg, bq, bh, bt);
+        m0 = m1;
     }
     if (has_red_.size() < st_.size()) has_red_.resize(st_.size(), 0);
     stats.t_symbolic += now_s() - t0;
@@ -302,9 +383,7 @@ void F4::convert() {
     const uint32_t nc = (uint32_t)st_.size();
     order_.resize(nc);
     std::iota(order_.begin(), order_.end(), 0u);
-    std::sort(order_.begin(), order_.end(), [&](uint32_t a, uint32_t b) {
-        return cx_.cmp(st_.e(a), st_.e(b)) > 0;
-    });
+    parallel_sort(*pool_, order_, [&](uint32_t a, uint32_t b) { return cx_.cmp(st_.e(a), st_.e(b)) > 0; });
     std::vector<uint32_t> colof(nc);
     for (uint32_t c = 0; c < nc; ++c) colof[order_[c]] = c;
 
@@ -333,25 +412,35 @@ void F4::convert() {
     for (uint32_t h = 0; h < nc; ++h) h2c[h] = newcol[colof[h]];
 
     M_.p = p_; M_.n_top = ntop; M_.n_bot = (uint32_t)bot.size(); M_.n_cols = nc;
-    M_.row_ptr.assign(1, 0); M_.row_ptr.reserve(nrows + 1);
+    M_.row_ptr.assign(nrows + 1, 0);
     M_.col.resize(row_mon_.size());
-    M_.coeff_id.clear(); M_.cf_ptr.clear(); M_.cf_len.clear();
+    M_.coeff_id.assign(nrows, 0); M_.cf_ptr.clear(); M_.cf_len.clear();
     static std::vector<int32_t> gmap;
     gmap.assign(G_.size(), -1);
+    std::vector<uint32_t> rows(top);
+    rows.insert(rows.end(), bot.begin(), bot.end());
     uint64_t w = 0;
-    auto emit = [&](uint32_t r) {
-        for (uint64_t k = row_off_[r]; k < row_off_[r + 1]; ++k) M_.col[w++] = h2c[row_mon_[k]];
-        M_.row_ptr.push_back(w);
-        uint32_t g = row_gen_[r];
+    for (size_t i = 0; i < nrows; ++i) {
+        const uint32_t r = rows[i];
+        w += row_off_[r + 1] - row_off_[r];
+        M_.row_ptr[i + 1] = w;
+        const uint32_t g = row_gen_[r];
         if (gmap[g] < 0) {
             gmap[g] = (int32_t)M_.cf_ptr.size();
             M_.cf_ptr.push_back(G_[g].cf.data());
             M_.cf_len.push_back((uint32_t)G_[g].cf.size());
         }
-        M_.coeff_id.push_back((uint32_t)gmap[g]);
-    };
-    for (uint32_t r : top) emit(r);
-    for (uint32_t r : bot) emit(r);
+        M_.coeff_id[i] = (uint32_t)gmap[g];
+    }
+    pool_->parallel_for(nrows, 64, [&](size_t i0, size_t i1) {
+    for (size_t i = i0; i < i1; ++i) {
+        const uint32_t r = rows[i];
+        uint32_t* dst = &M_.col[M_.row_ptr[i]];
+        const uint32_t* src = &row_mon_[row_off_[r]];
+        const uint64_t len = row_off_[r + 1] - row_off_[r];
+        for (uint64_t k = 0; k < len; ++k) dst[k] = h2c[src[k]];
+    }
+    });
     stats.t_convert += now_s() - t0;
     stats.max_rows = std::max<uint64_t>(stats.max_rows, nrows);
     stats.max_cols = std::max<uint64_t>(stats.max_cols, nc);
@@ -393,9 +482,12 @@ void F4::final_reduce() {
     clear_step();
     std::vector<uint32_t> nr = nonredundant();
     std::vector<uint16_t> one(cx_.stride, 0);
-    for (uint32_t g : nr) {
-        add_row(g, one.data(), 0, false);
-        has_red_[row_mon_[row_off_[row_gen_.size() - 1]]] = 1;  // leads need no reducer
+    {
+        std::vector<uint16_t> qs(nr.size() * cx_.stride, 0);
+        std::vector<uint32_t> hs(nr.size(), 0);
+        std::vector<uint8_t> tp(nr.size(), 0);
+        add_rows(nr, qs, hs, tp);
+        for (size_t i = 0; i < nr.size(); ++i) has_red_[row_mon_[row_off_[i]]] = 1;  // leads need no reducer
     }
     symbolic();
     convert();
@@ -478,6 +570,8 @@ void F4::run() {
         }
     }
     stats.t_total = now_s() - t_start;
+    if (getenv("GAMBA_DEBUG_TIMERS")) std::fprintf(stderr, "dbg: reserve %.3f rowgen %.3f search %.3f waves %ld\n", dbg_t_[0], dbg_t_[1], dbg_t_[2], dbg_waves_),
+        std::fprintf(stderr, "dbg update: B %.3f build %.3f sort %.3f M %.3f F+push %.3f\n", upd_t_[0], upd_t_[1], upd_t_[2], upd_t_[3], upd_t_[4]);
 }
 
 // Generators in increasing order of leading monomial (source/basis.hpp:923-972).

@@ -9,12 +9,14 @@
 #pragma once
 #include <chrono>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "engine.hpp"
 #include "io.hpp"
 #include "mono.hpp"
+#include "par.hpp"
 
 namespace gb {
 
@@ -25,7 +27,7 @@ struct Params {
     bool no_reduce = false;
     uint64_t seed = 967557673ull;
     int verbose = 2;
-    int threads = 1;
+    int threads = 0;            // -t: host threads (0 = all hardware threads, at most 16)
     std::string dump_dir;       // write every step matrix (+ result) here
     long dump_min_nnz = 0;
     long stop_after = 0;        // debugging: leave the F4 loop after this many steps (0 = run to the end)
@@ -64,6 +66,12 @@ private:
     std::vector<Poly> G_;
     std::vector<Pair> P_;
     bool trivial_ = false;
+    int nthreads_ = 1;          // host threads for row generation, reducer search, column mapping
+    std::unique_ptr<ThreadPool> pool_;
+    double dbg_t_[4] = {0, 0, 0, 0};
+    long dbg_waves_ = 0;
+    double upd_t_[5] = {0, 0, 0, 0, 0};
+    std::vector<uint16_t> upd_lcm_;      // update(): lcms of the candidate pairs of one generator
 
     // per-step state
     std::vector<uint32_t> row_mon_;      // flat step-table handles
@@ -81,7 +89,8 @@ private:
     void update_all(size_t from);
     long select_pairs(int32_t& deg);
     void clear_step();
-    void add_row(uint32_t gen, const uint16_t* q, uint32_t hq, bool top);
+    void add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>& qs, const std::vector<uint32_t>& hqs,
+                  const std::vector<uint8_t>& tops);
     void build_pair_rows(long n_sel);
     void symbolic();
     void convert();

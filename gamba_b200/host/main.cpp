@@ -25,7 +25,7 @@ static void usage() {
         "  --max-spairs UINT               Max pairs of minimal degree per round (0 = all)\n"
         "  --all-pairs                     Select all pairs in the queue in each round\n"
         "  --no-reduce                     Do not compute a reduced Groebner basis\n"
-        "  -t,--threads UINT               Number of threads (unused, as in the reference)\n"
+        "  -t,--threads UINT               Host threads for the symbolic phases (0 = all, at most 16)\n"
         "  -v,--verbose UINT               Verbosity level (default 2)\n"
         "  --dump-steps DIR                Write every step matrix and its result to DIR\n"
         "  --dump-min-nnz N                ... only steps with at least N non-zeros\n"

@@ -7,6 +7,7 @@
 // one flat exponent arena per table, 32-bit handles, additive hashing.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -68,31 +69,45 @@ struct MonoCtx {
     }
 };
 
-// Open-addressing set of monomials. Handles are dense indices 0..size()-1 in
-// insertion order, which the symbolic preprocessing relies on.
+// Open-addressing set of monomials. Handles are dense indices 0..size()-1. Storage is
+// capacity-managed so that a parallel phase (insert_mt, after reserve_more) never reallocates.
 struct MonoTable {
+    static constexpr uint32_t PENDING = 0xffffffffu;
     const MonoCtx* cx = nullptr;
-    std::vector<uint16_t> ex;
-    std::vector<uint32_t> hv;
-    std::vector<uint32_t> slots;  // handle + 1, 0 = empty
+    std::vector<uint16_t> ex;     // capacity * stride
+    std::vector<uint32_t> hv;     // capacity
+    std::vector<uint32_t> slots;  // handle + 1, 0 = empty, PENDING = being written
     uint32_t mask = 0;
+    uint32_t n = 0;               // monomials stored
 
     explicit MonoTable(const MonoCtx* c = nullptr, size_t cap = 1 << 16) : cx(c) {
         slots.assign(cap, 0); mask = (uint32_t)cap - 1;
     }
-    size_t size() const { return hv.size(); }
+    size_t size() const { return n; }
     const uint16_t* e(uint32_t h) const { return &ex[(size_t)h * cx->stride]; }
     void clear() {
-        ex.clear(); hv.clear();
+        n = 0;
         std::fill(slots.begin(), slots.end(), 0u);
     }
-    void grow() {
-        size_t cap = slots.size() * 2;
+    void rehash(size_t cap) {
         slots.assign(cap, 0); mask = (uint32_t)cap - 1;
-        for (uint32_t h = 0; h < hv.size(); ++h) {
+        for (uint32_t h = 0; h < n; ++h) {
             uint32_t s = hv[h] & mask;
             while (slots[s]) s = (s + 1) & mask;
             slots[s] = h + 1;
+        }
+    }
+    // Room for `extra` more monomials without any reallocation or rehash.
+    void reserve_more(size_t extra) {
+        const size_t want = (size_t)n + extra;
+        if (hv.size() < want) {
+            size_t cap = std::max<size_t>(want, hv.size() + hv.size() / 2 + 1024);
+            hv.resize(cap); ex.resize(cap * cx->stride);
+        }
+        if (want * 2 > slots.size()) {
+            size_t cap = slots.size();
+            while (want * 2 > cap) cap *= 2;
+            rehash(cap);
         }
     }
     // Insert the monomial with exponent vector e (full stride, degrees filled
@@ -106,12 +121,45 @@ struct MonoTable {
                 return cand;
             s = (s + 1) & mask;
         }
-        uint32_t id = (uint32_t)hv.size();
+        if (hv.size() <= n || ((size_t)n + 1) * 2 > slots.size()) {
+            // e_ may point into ex: copy before growing
+            uint16_t tmp[256 + 2];
+            std::memcpy(tmp, e_, st * sizeof(uint16_t));
+            reserve_more(1);
+            return insert(tmp, h);
+        }
+        const uint32_t id = n++;
         slots[s] = id + 1;
-        hv.push_back(h);
-        ex.insert(ex.end(), e_, e_ + st);
-        if (hv.size() * 2 > slots.size()) grow();
+        hv[id] = h;
+        std::memcpy(&ex[(size_t)id * st], e_, st * sizeof(uint16_t));
         return id;
+    }
+    // Concurrent insert (several threads, after reserve_more covered every insert of the phase).
+    // A slot is claimed with a PENDING mark, filled, then published; readers of a pending slot wait.
+    uint32_t insert_mt(const uint16_t* e_, uint32_t h) {
+        const int st = cx->stride;
+        uint32_t s = h & mask;
+        for (;;) {
+            uint32_t v = __atomic_load_n(&slots[s], __ATOMIC_ACQUIRE);
+            if (v == 0) {
+                uint32_t expect = 0;
+                if (__atomic_compare_exchange_n(&slots[s], &expect, PENDING, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+                    const uint32_t id = __atomic_fetch_add(&n, 1u, __ATOMIC_RELAXED);
+                    hv[id] = h;
+                    std::memcpy(&ex[(size_t)id * st], e_, st * sizeof(uint16_t));
+                    __atomic_store_n(&slots[s], id + 1, __ATOMIC_RELEASE);
+                    return id;
+                }
+                v = expect;
+            }
+            while (v == PENDING) {
+                __builtin_ia32_pause();
+                v = __atomic_load_n(&slots[s], __ATOMIC_ACQUIRE);
+            }
+            const uint32_t cand = v - 1;
+            if (hv[cand] == h && std::memcmp(&ex[(size_t)cand * st], e_, st * sizeof(uint16_t)) == 0) return cand;
+            s = (s + 1) & mask;
+        }
     }
     // Insert the product a*b of two exponent vectors (a, b may live anywhere).
     uint32_t insert_product(const uint16_t* a, uint32_t ha, const uint16_t* b, uint32_t hb) {
