@@ -33,7 +33,8 @@ class StepOut(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("steps", C.c_uint64), ("sm_count", C.c_uint32),
                 ("tile_cols", C.c_uint32), ("n_tiles", C.c_uint32), ("acc_bits", C.c_uint32),
-                ("pivots_applied", C.c_uint64), ("fma_applied", C.c_uint64), ("fma_top", C.c_uint64), ("mc_combinations", C.c_uint32), ("mc_attempts", C.c_uint32)]
+                ("pivots_applied", C.c_uint64), ("fma_applied", C.c_uint64), ("fma_top", C.c_uint64), ("mc_combinations", C.c_uint32), ("mc_attempts", C.c_uint32),
+                ("seconds_stage_last", C.c_double)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -41,7 +42,7 @@ BROADCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
 
 # every symbol include/gamba_cuda.h declares
 SYMBOLS = ["gamba_cuda_abi_version", "gamba_cuda_last_error", "gamba_cuda_create", "gamba_cuda_destroy",
-           "gamba_cuda_reduce", "gamba_cuda_stage", "gamba_cuda_reduce_staged", "gamba_cuda_set_allgather", "gamba_cuda_set_broadcast",
+           "gamba_cuda_reduce", "gamba_cuda_stage", "gamba_cuda_reduce_staged", "gamba_cuda_set_allgather", "gamba_cuda_set_broadcast", "gamba_cuda_host_alloc", "gamba_cuda_host_free",
            "gamba_cuda_get_counters", "gamba_cuda_set_option"]
 
 _lib = None

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cub/device/device_scan.cuh>
 #include <stdexcept>
@@ -41,7 +42,7 @@ struct DevBuf {
         if (bytes <= cap) return;
         if (p) GCU_CHECK(cudaFree(p));
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 2 + 256;   // matrices grow from step to step: few, generous reallocations
         GCU_CHECK(cudaMalloc(&p, want));
         cap = want;
     }
@@ -56,7 +57,7 @@ struct HostBuf {  // pinned
         if (bytes <= cap) return;
         if (p) GCU_CHECK(cudaFreeHost(p));
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 2 + 256;   // matrices grow from step to step: few, generous reallocations
         GCU_CHECK(cudaMallocHost(&p, want));
         cap = want;
     }
@@ -122,7 +123,11 @@ struct gamba_cuda_engine {
     gamba_cuda_counters ctr{};
     double t_elim_dev = 0, t_ech_dev = 0;
 
+    double dbg_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     ~gamba_cuda_engine() {
+        if (std::getenv("GAMBA_DEBUG_TIMERS"))
+            std::fprintf(stderr, "dbg stage: hdr+layout %.3f alloc %.3f copies+pack %.3f alloc2 %.3f kernels+sync %.3f | reduce: elim-launch %.3f echelon+d2h %.3f\n",
+                         dbg_[0], dbg_[1], dbg_[2], dbg_[3], dbg_[4], dbg_[5], dbg_[6]);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -203,6 +208,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     if (nnz + 3ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
 
+    double tq = wall_s(); dbg_[0] += tq - t0;
     // shared coefficient arrays -> one u32 pool
     const uint32_t na = hd.n_arr;
     const uint64_t tot = hd.pool_len;
@@ -210,27 +216,31 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     uint64_t* off = h_off.as<uint64_t>();
     h_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
     uint32_t* pool = h_pool.as<uint32_t>();
+    auto pack_pool = [&]() {
     if (have) { uint64_t t = 0; for (uint32_t i = 0; i < na; ++i) { off[i] = t; t += in->coeff_len[i]; } off[na] = t; }
-    for (uint32_t i = 0; have && i < na; ++i) {
-        const uint32_t n = in->coeff_len[i];
-        uint32_t* dst = pool + off[i];
-        switch (cfg.coeff_bytes) {
-            case 4: std::memcpy(dst, in->coeff_ptr[i], (size_t)n * 4); break;
-            case 2: { const uint16_t* s = (const uint16_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
-            default: { const uint8_t* s = (const uint8_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
+        for (uint32_t i = 0; have && i < na; ++i) {
+            const uint32_t n = in->coeff_len[i];
+            uint32_t* dst = pool + off[i];
+            switch (cfg.coeff_bytes) {
+                case 4: std::memcpy(dst, in->coeff_ptr[i], (size_t)n * 4); break;
+                case 2: { const uint16_t* s = (const uint16_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
+                default: { const uint8_t* s = (const uint8_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
+            }
         }
-    }
-
+    };
     d_row_ptr.ensure((n_rows + 1) * sizeof(uint64_t));
     d_col.ensure(std::max<uint64_t>(nnz, 1) * sizeof(uint32_t));
     d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
     d_coeff_off.ensure((na + 1) * sizeof(uint64_t));
     d_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
     h2d_bytes = 0;
+    dbg_[1] += wall_s() - tq; tq = wall_s();
     if (have) {
         GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
         GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        // the coefficient pool is packed while the column indices (page-locked at the caller: a plain DMA) are in flight
+        pack_pool();
         GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
         GCU_CHECK(cudaMemcpyAsync(d_pool.p, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         h2d_bytes = (n_rows + 1) * 8ull + nnz * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull;
@@ -243,6 +253,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
             if (b.second && bcast_fn(bcast_user, b.first, b.second, 0, stream)) throw std::runtime_error("broadcast of the step failed");
     }
 
+    dbg_[2] += wall_s() - tq; tq = wall_s();
     const uint64_t n_cnt = (uint64_t)n_rows * L.n_tiles + 1;
     const uint64_t n_diag = std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1);
     d_cnt.ensure(n_cnt * sizeof(uint32_t));
@@ -251,6 +262,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     d_diag.ensure(n_diag * sizeof(uint32_t));
     d_dnz.ensure(std::max<uint32_t>(L.n_windows, 1) * sizeof(uint32_t));
     d_first.ensure((std::max<uint32_t>(L.n_bot, 1) + 1) * sizeof(uint32_t));
+    dbg_[3] += wall_s() - tq; tq = wall_s();
     GCU_CHECK(cudaEventRecord(ev[0], stream));
     GCU_CHECK(cudaMemsetAsync(d_cnt.p, 0, n_cnt * sizeof(uint32_t), stream));
     GCU_CHECK(cudaMemsetAsync(d_diag.p, 0, n_diag * sizeof(uint32_t), stream));
@@ -290,7 +302,9 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     float ms = 0;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
     t_prep_dev = ms * 1e-3;
+    dbg_[4] += wall_s() - tq;
     t_stage_wall = wall_s() - t0;
+    ctr.seconds_stage_last = t_stage_wall;
     staged = true;
 }
 
@@ -555,6 +569,13 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
 }
 
 void gamba_cuda_destroy(gamba_cuda_engine* e) { delete e; }
+
+void* gamba_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void gamba_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int gamba_cuda_stage(gamba_cuda_engine* e, const gamba_cuda_step_in* in) {
     return guarded([&] { GCU_CHECK(cudaSetDevice((int)e->cfg.device)); e->stage(in); });

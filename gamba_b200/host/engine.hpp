@@ -13,19 +13,60 @@
 //     with coefficient k of the row's *shared* coefficient array coeff_id[row].
 // Coefficients are standard residues in [0,p); every row is monic.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace gb {
 
+// Allocation of the one O(nnz) array that crosses the boundary every step. The CUDA engine installs
+// page-locked allocation (gamba_cuda_host_alloc) so that the H2D copy is a plain DMA; default: malloc.
+struct HostAllocHook { void* (*alloc)(size_t) = nullptr; void (*release)(void*) = nullptr; };
+inline HostAllocHook& host_alloc_hook() { static HostAllocHook h; return h; }
+
+class ColArray {
+public:
+    ColArray() = default;
+    ColArray(const ColArray&) = delete;
+    ColArray& operator=(const ColArray&) = delete;
+    ~ColArray() { drop(); }
+    uint32_t* data() { return p_; }
+    const uint32_t* data() const { return p_; }
+    size_t size() const { return n_; }
+    uint32_t& operator[](size_t i) { return p_[i]; }
+    const uint32_t& operator[](size_t i) const { return p_[i]; }
+    void resize(size_t n) {          // contents are NOT preserved
+        if (n > cap_) {
+            drop();
+            const size_t cap = n + n / 2 + 1024;
+            auto& h = host_alloc_hook();
+            p_ = static_cast<uint32_t*>(h.alloc ? h.alloc(cap * sizeof(uint32_t)) : std::malloc(cap * sizeof(uint32_t)));
+            if (!p_) throw std::runtime_error("out of host memory for the step matrix");
+            pinned_ = h.alloc != nullptr; cap_ = cap;
+        }
+        n_ = n;
+    }
+    void assign(const uint32_t* a, const uint32_t* b) { resize((size_t)(b - a)); std::copy(a, b, p_); }
+
+private:
+    void drop() {
+        if (p_) { if (pinned_) host_alloc_hook().release(p_); else std::free(p_); }
+        p_ = nullptr; cap_ = n_ = 0;
+    }
+    uint32_t* p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+    bool pinned_ = false;
+};
+
 struct StepMatrix {
     uint32_t p = 0;
     uint32_t n_top = 0, n_bot = 0, n_cols = 0;
     std::vector<uint64_t> row_ptr;      // n_top + n_bot + 1
-    std::vector<uint32_t> col;          // nnz, block-form column numbers
+    ColArray col;                       // nnz, block-form column numbers
     std::vector<uint32_t> coeff_id;     // per row, index into cf_ptr / cf_len
     std::vector<const uint32_t*> cf_ptr;
     std::vector<uint32_t> cf_len;

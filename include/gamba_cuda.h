@@ -105,6 +105,11 @@ const char* gamba_cuda_last_error(void);
 int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out);
 void gamba_cuda_destroy(gamba_cuda_engine* e);
 
+/* Page-locked host memory for the caller's step arrays (col_idx above all): H2D copies from it are plain
+   DMA transfers. Optional - any host memory is accepted by the calls below. NULL on failure. */
+void* gamba_cuda_host_alloc(size_t bytes);
+void gamba_cuda_host_free(void* p);
+
 /* One F4 step (or the final inter-reduction): host buffers in, host buffers out. */
 int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_cuda_step_out* out);
 
@@ -146,6 +151,7 @@ typedef struct gamba_cuda_counters {
     uint32_t mc_combinations;          /* Monte-Carlo mode: combinations eliminated by the last step (0 = the
                                           step ran exactly)                                         */
     uint32_t mc_attempts;              /* ... and how many draws it took to meet the rank margin      */
+    double seconds_stage_last;         /* wall time of the last staging: H2D (or broadcast) + staging kernels */
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
