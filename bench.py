@@ -48,6 +48,15 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic():
+    """DRAM bytes per elimination-kernel launch from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01b_elim_traffic.json")) as f:
+            return float(json.load(f)["mean_dram_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def cpu_model() -> str:
     try:
         for line in open("/proc/cpuinfo"):
@@ -197,7 +206,7 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u64 accumulators over F_p (p=32003)", "data": "synthetic (generated system, no dataset)",
+        "vs_baseline": None, "dtype": "u64 (CPU oracle accumulators) over F_p", "data": "synthetic (generated system, no dataset)",
         "config": {"workload": wl_desc, "sample": desc},
         "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": desc, "cpu": cpu_model(),
                          "note": "oracle port; the reference's own engine (linalg_v3.hpp, kernel/*) is closed source"},
@@ -320,7 +329,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": total_nnz * args.steps / t_res, "unit": "nnz/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64 accumulators over F_p (p=%d)" % steps[0].p, "data": "synthetic (generated system, no dataset)",
+            "dtype": "u32 residues mod p=%d (32-bit delayed-reduction lanes; u8 limbs on the tensor cores in the echelon)" % steps[0].p, "data": "synthetic (generated system, no dataset)",
             "config": {"workload": f"{wl_desc} ({len(steps)} matrices, "
                                    f"{total_nnz} nnz per pass, largest {max(s.n_rows for s in steps)} x {max(s.n_cols for s in steps)})",
                        "parallelism": (f"C|D rows sharded r % {world}, step uploaded by rank 0 and replicated by NCCL broadcast, "
@@ -332,7 +341,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "gpu_launches": n_launch,
             "clocks": clocks,
             "roofline": {"kernel": "elim_kernel (C|D by A|B)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic() if args.system == "cyclic9-15" else None,
+                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01b_elim_traffic.json (A|B is served from L2)",
+                         "peak_source": peak_src,
                          "bytes_alg_per_launch": alg, "avg_launch_ms": dur * 1e3,
                          "share_of_device_time": sum(elim_s) / max(dev_s, 1e-12),
                          "fma_top_per_pass": int(sum(fma_top))},
