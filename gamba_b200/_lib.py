@@ -19,7 +19,8 @@ class Config(C.Structure):
 class StepIn(C.Structure):
     _fields_ = [("n_top", C.c_uint32), ("n_bot", C.c_uint32), ("n_cols", C.c_uint32), ("n_coeff_arrays", C.c_uint32),
                 ("nnz", C.c_uint64), ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p), ("coeff_id", C.c_void_p),
-                ("coeff_ptr", C.c_void_p), ("coeff_len", C.c_void_p), ("flags", C.c_uint32)]
+                ("coeff_ptr", C.c_void_p), ("coeff_len", C.c_void_p), ("flags", C.c_uint32),
+                ("col_map_len", C.c_uint32), ("row_src", C.c_void_p), ("col_map", C.c_void_p), ("col_idx_len", C.c_uint64)]
 
 
 class StepOut(C.Structure):

@@ -14,6 +14,7 @@
 #include <cub/device/device_scan.cuh>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gamba_cuda.h"
@@ -81,6 +82,9 @@ struct gamba_cuda_engine {
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
     int64_t opt_echelon_mma = 1;     // 1: blocked echelon on the tensor cores, 0: per-pivot kernel
+    int64_t opt_coeff_cache = 0;     // keep coefficient arrays on the device across steps (caller: immutable arrays)
+    std::unordered_map<const void*, std::pair<uint64_t, uint32_t>> cache;   // host pointer -> (offset in d_pool, length)
+    uint64_t cache_used = 0;
     int64_t opt_mc = 0;              // Monte-Carlo combinations instead of the rows themselves
     int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
     int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
@@ -92,7 +96,7 @@ struct gamba_cuda_engine {
     gcu::Layout L{};
     uint32_t flags = 0;
     uint64_t nnz = 0;
-    gcu::DevBuf d_row_ptr, d_col, d_coeff_id, d_coeff_off, d_pool;
+    gcu::DevBuf d_row_ptr, d_col, d_coeff_id, d_coeff_off, d_pool, d_row_src, d_col_map;
     gcu::DevBuf d_cnt, d_seg, d_ent, d_diag, d_dnz, d_first, d_scan_tmp;
     gcu::HostBuf h_pool, h_off;
     uint64_t h2d_bytes = 0;
@@ -174,7 +178,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
 
 // Sizes of a step; with world_size > 1 and a broadcast callback only rank 0 holds the step on the host
 // and this header travels first ("ncclBroadcast of the flattened A|B").
-struct StepHdr { uint32_t n_top, n_bot, n_cols, n_arr; uint64_t nnz, pool_len; uint32_t flags, pad; };
+struct StepHdr { uint32_t n_top, n_bot, n_cols, n_arr; uint64_t nnz, pool_len, n_src; uint32_t flags, col_map_len, has_row_src, pad; };
 
 void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     const double t0 = wall_s();
@@ -188,6 +192,9 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         if (in->row_ptr[in->n_top + in->n_bot] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
         hd.n_top = in->n_top; hd.n_bot = in->n_bot; hd.n_cols = in->n_cols; hd.n_arr = in->n_coeff_arrays;
         hd.nnz = in->nnz; hd.flags = in->flags;
+        hd.n_src = in->col_idx_len ? in->col_idx_len : in->nnz;
+        hd.col_map_len = in->col_map ? in->col_map_len : 0; hd.has_row_src = in->row_src != nullptr;
+        if (hd.n_src < hd.nnz && !hd.has_row_src) throw std::runtime_error("col_idx_len < nnz");
         for (uint32_t i = 0; i < in->n_coeff_arrays; ++i) hd.pool_len += in->coeff_len[i];
     }
     if (use_bcast) {
@@ -209,44 +216,80 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
 
     double tq = wall_s(); dbg_[0] += tq - t0;
-    // shared coefficient arrays -> one u32 pool
+    // shared coefficient arrays -> one u32 pool. With the option "coeff_cache" the pool is an append-only
+    // device arena keyed by (host pointer, length): the caller promises that coefficient arrays are immutable
+    // while the engine lives (source/matrix.hpp:189-193: they alias basis storage), so an array crosses
+    // PCIe once per run instead of once per step.
     const uint32_t na = hd.n_arr;
-    const uint64_t tot = hd.pool_len;
+    const bool cached = opt_coeff_cache && !use_bcast;
     h_off.ensure((na + 1) * sizeof(uint64_t));
     uint64_t* off = h_off.as<uint64_t>();
+    uint64_t tot = hd.pool_len;          // entries to upload this step
+    uint64_t pool_base = 0;              // where they go in d_pool
+    std::vector<uint32_t> fresh;         // arrays not yet on the device
+    if (cached) {
+        tot = 0; pool_base = cache_used;
+        fresh.reserve(na);
+        for (uint32_t i = 0; i < na; ++i) {
+            auto it = cache.find(in->coeff_ptr[i]);
+            if (it != cache.end() && it->second.second >= in->coeff_len[i]) { off[i] = it->second.first; continue; }
+            off[i] = cache_used + tot; tot += in->coeff_len[i];
+            cache[in->coeff_ptr[i]] = {off[i], in->coeff_len[i]};
+            fresh.push_back(i);
+        }
+        off[na] = cache_used + tot;
+        if ((cache_used + tot) * sizeof(uint32_t) > d_pool.cap) {      // grow the arena, keeping what is there
+            gcu::DevBuf bigger;
+            bigger.ensure((cache_used + tot) * 2 * sizeof(uint32_t));
+            if (cache_used) GCU_CHECK(cudaMemcpyAsync(bigger.p, d_pool.p, cache_used * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+            GCU_CHECK(cudaStreamSynchronize(stream));
+            std::swap(bigger.p, d_pool.p); std::swap(bigger.cap, d_pool.cap);
+        }
+        cache_used += tot;
+    } else if (have) {
+        uint64_t t = 0;
+        for (uint32_t i = 0; i < na; ++i) { off[i] = t; t += in->coeff_len[i]; }
+        off[na] = t;
+    }
     h_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
     uint32_t* pool = h_pool.as<uint32_t>();
-    auto pack_pool = [&]() {
-    if (have) { uint64_t t = 0; for (uint32_t i = 0; i < na; ++i) { off[i] = t; t += in->coeff_len[i]; } off[na] = t; }
-        for (uint32_t i = 0; have && i < na; ++i) {
-            const uint32_t n = in->coeff_len[i];
-            uint32_t* dst = pool + off[i];
-            switch (cfg.coeff_bytes) {
-                case 4: std::memcpy(dst, in->coeff_ptr[i], (size_t)n * 4); break;
-                case 2: { const uint16_t* s = (const uint16_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
-                default: { const uint8_t* s = (const uint8_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
-            }
+    auto pack_one = [&](uint32_t i, uint32_t* dst) {
+        const uint32_t n = in->coeff_len[i];
+        switch (cfg.coeff_bytes) {
+            case 4: std::memcpy(dst, in->coeff_ptr[i], (size_t)n * 4); break;
+            case 2: { const uint16_t* s = (const uint16_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
+            default: { const uint8_t* s = (const uint8_t*)in->coeff_ptr[i]; for (uint32_t k = 0; k < n; ++k) dst[k] = s[k]; } break;
         }
     };
+    auto pack_pool = [&]() {
+        if (cached) { uint64_t t = 0; for (uint32_t i : fresh) { pack_one(i, pool + t); t += in->coeff_len[i]; } }
+        else if (have) for (uint32_t i = 0; i < na; ++i) pack_one(i, pool + off[i]);
+    };
     d_row_ptr.ensure((n_rows + 1) * sizeof(uint64_t));
-    d_col.ensure(std::max<uint64_t>(nnz, 1) * sizeof(uint32_t));
+    d_col.ensure(std::max<uint64_t>(hd.n_src, 1) * sizeof(uint32_t));
+    if (hd.has_row_src) d_row_src.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint64_t));
+    if (hd.col_map_len) d_col_map.ensure((size_t)hd.col_map_len * sizeof(uint32_t));
     d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
     d_coeff_off.ensure((na + 1) * sizeof(uint64_t));
-    d_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
+    if (!cached) d_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
     h2d_bytes = 0;
     dbg_[1] += wall_s() - tq; tq = wall_s();
     if (have) {
         GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-        GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, hd.n_src * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        if (hd.has_row_src) GCU_CHECK(cudaMemcpyAsync(d_row_src.p, in->row_src, n_rows * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+        if (hd.col_map_len) GCU_CHECK(cudaMemcpyAsync(d_col_map.p, in->col_map, (size_t)hd.col_map_len * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         // the coefficient pool is packed while the column indices (page-locked at the caller: a plain DMA) are in flight
         pack_pool();
         GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-        GCU_CHECK(cudaMemcpyAsync(d_pool.p, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        h2d_bytes = (n_rows + 1) * 8ull + nnz * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull;
+        if (tot) GCU_CHECK(cudaMemcpyAsync(d_pool.as<uint32_t>() + pool_base, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        h2d_bytes = (n_rows + 1) * 8ull + hd.n_src * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull +
+                    (hd.has_row_src ? n_rows * 8ull : 0) + hd.col_map_len * 4ull;
     }
     if (use_bcast) {   // A|B and C|D replicated over NVLink instead of one H2D copy per rank
-        const std::pair<void*, size_t> bufs[] = {{d_row_ptr.p, (n_rows + 1) * sizeof(uint64_t)}, {d_col.p, nnz * sizeof(uint32_t)},
+        const std::pair<void*, size_t> bufs[] = {{d_row_ptr.p, (n_rows + 1) * sizeof(uint64_t)}, {d_col.p, hd.n_src * sizeof(uint32_t)},
+                                                 {d_row_src.p, hd.has_row_src ? n_rows * sizeof(uint64_t) : 0}, {d_col_map.p, (size_t)hd.col_map_len * sizeof(uint32_t)},
                                                  {d_coeff_id.p, n_rows * sizeof(uint32_t)}, {d_coeff_off.p, (na + 1) * sizeof(uint64_t)},
                                                  {d_pool.p, tot * sizeof(uint32_t)}};
         for (auto const& b : bufs)
@@ -273,6 +316,8 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
     pa.cnt = d_cnt.as<uint32_t>(); pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
     pa.diag = d_diag.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
+    pa.row_src = hd.has_row_src ? d_row_src.as<uint64_t>() : nullptr;
+    pa.col_map = hd.col_map_len ? d_col_map.as<uint32_t>() : nullptr;
     pa.first_piv = d_first.as<uint32_t>(); pa.first_min = d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1);
     GCU_CHECK(cudaMemsetAsync(pa.first_min, 0xff, sizeof(uint32_t), stream));
     if (n_rows) {
@@ -618,6 +663,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         if (k == "tile_cols") e->opt_tile_cols = value;
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
         else if (k == "echelon_mma") e->opt_echelon_mma = value;
+        else if (k == "coeff_cache") { e->opt_coeff_cache = value; e->cache.clear(); e->cache_used = 0; }
         else if (k == "mc") e->opt_mc = value;
         else if (k == "mc_k") e->opt_mc_k = value;
         else if (k == "rank_hint") e->last_rank = value;

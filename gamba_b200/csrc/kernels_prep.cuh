@@ -22,6 +22,8 @@ struct PrepArgs {
     uint32_t* dnz;        // [n_windows]
     uint32_t* first_piv;  // per bottom row: smallest pivot column present (n_top if none)
     uint32_t* first_min;  // min of first_piv over all rows to reduce (preset to 0xffffffff)
+    const uint64_t* row_src;  // optional: where row r's entries start in col[] (default row_ptr[r])
+    const uint32_t* col_map;  // optional: col[] holds handles, block-form column = col_map[handle]
 };
 
 // in-window entries of a pivot row go to the dense diagonal block, not to ent[]
@@ -38,10 +40,10 @@ __global__ void __launch_bounds__(256) prep_count_kernel(PrepArgs a) {
     for (uint32_t b = lane; b < nt; b += 32) hist[b] = 0;
     __syncwarp();
     if (row < a.L.n_rows) {
-        const uint64_t s = a.row_ptr[row], e = a.row_ptr[row + 1];
+        const uint64_t s = a.row_src ? a.row_src[row] : a.row_ptr[row], e = s + (a.row_ptr[row + 1] - a.row_ptr[row]);
         uint32_t fp = a.L.n_top;
         for (uint64_t k = s + lane; k < e; k += 32) {
-            const uint32_t c = a.col[k];
+            const uint32_t c = a.col_map ? a.col_map[a.col[k]] : a.col[k];
             if (c < a.L.n_top && c < fp) fp = c;
             if (prep_in_window(a.L, row, c)) continue;
             atomicAdd(&hist[lay_tile(a.L, c)], 1u);
@@ -69,14 +71,14 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
     }
     if (lane == 0) a.seg[(uint64_t)nt * nr + row] = a.cnt[(uint64_t)(row + 1) * nt];  // row end
     __syncwarp();
-    const uint64_t s = a.row_ptr[row], e = a.row_ptr[row + 1];
+    const uint64_t s = a.row_src ? a.row_src[row] : a.row_ptr[row], e = s + (a.row_ptr[row + 1] - a.row_ptr[row]);
     const uint32_t* cf = a.pool + a.coeff_off[a.coeff_id[row]];
     const uint32_t lt = (1u << lane) - 1u;
     for (uint64_t base = s; base < e; base += 32) {
         const uint64_t k = base + lane;
         uint32_t bin = 0xffffffffu, off = 0, val = 0;
         if (k < e) {
-            const uint32_t c = a.col[k];
+            const uint32_t c = a.col_map ? a.col_map[a.col[k]] : a.col[k];
             val = cf[k - s];
             if (a.f.mont_bits) val = fp_mul(val, a.f.rinv_mod_p, a.f);
             if (prep_in_window(a.L, row, c)) {

@@ -49,8 +49,14 @@ class LinalgEngine:
         cid = np.ascontiguousarray(s.coeff_id, dtype=np.uint32)
         clen = np.ascontiguousarray(s.coeff_len, dtype=np.uint32)
         self._keep = (pool, ptrs, row_ptr, col, cid, clen)
-        return _lib.StepIn(s.n_top, s.n_bot, s.n_cols, len(clen), s.nnz, row_ptr.ctypes.data, col.ctypes.data,
-                           cid.ctypes.data, ptrs.ctypes.data, clen.ctypes.data, flags)
+        sin = _lib.StepIn(s.n_top, s.n_bot, s.n_cols, len(clen), s.nnz, row_ptr.ctypes.data, col.ctypes.data,
+                          cid.ctypes.data, ptrs.ctypes.data, clen.ctypes.data, flags)
+        if s.row_src is not None:       # indirect form: rows anywhere in `col`, entries are handles
+            row_src = np.ascontiguousarray(s.row_src, dtype=np.uint64)
+            col_map = np.ascontiguousarray(s.col_map, dtype=np.uint32)
+            self._keep += (row_src, col_map)
+            sin.row_src, sin.col_map, sin.col_map_len, sin.col_idx_len = row_src.ctypes.data, col_map.ctypes.data, len(col_map), len(col)
+        return sin
 
     def _rows(self, out: _lib.StepOut) -> Rows:
         n, nnz = out.n_new, out.nnz_new

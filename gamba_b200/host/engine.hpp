@@ -70,6 +70,13 @@ struct StepMatrix {
     std::vector<uint32_t> coeff_id;     // per row, index into cf_ptr / cf_len
     std::vector<const uint32_t*> cf_ptr;
     std::vector<uint32_t> cf_len;
+    // Indirect form (what the driver produces; gamba_cuda.h): the entries stay where symbolic preprocessing
+    // wrote them, as step-table handles; row r's entries are src[row_src[r] ..), column = col_map[handle].
+    const uint32_t* src = nullptr;
+    uint64_t src_len = 0;
+    std::vector<uint64_t> row_src;
+    std::vector<uint32_t> col_map;
+    uint32_t col_at(uint32_t r, uint64_t j) const { return src ? col_map[src[row_src[r] + j]] : col[row_ptr[r] + j]; }
     uint64_t nnz() const { return row_ptr.empty() ? 0 : row_ptr.back(); }
     uint32_t n_rows() const { return n_top + n_bot; }
     uint32_t n_nonpiv() const { return n_cols - n_top; }
@@ -116,7 +123,17 @@ inline void write_step_file(const std::string& path, const StepMatrix& m) {
                        m.nnz(), (uint64_t)m.cf_len.size(), pool_len};
     std::fwrite(hdr, 8, 8, f);
     std::fwrite(m.row_ptr.data(), 8, m.row_ptr.size(), f);
-    std::fwrite(m.col.data(), 4, m.col.size(), f);
+    if (m.src) {
+        std::vector<uint32_t> tmp;
+        for (uint32_t r = 0; r < m.n_rows(); ++r) {
+            const uint64_t len = m.row_ptr[r + 1] - m.row_ptr[r];
+            tmp.resize(len);
+            for (uint64_t j = 0; j < len; ++j) tmp[j] = m.col_at(r, j);
+            std::fwrite(tmp.data(), 4, len, f);
+        }
+    } else {
+        std::fwrite(m.col.data(), 4, m.col.size(), f);
+    }
     std::fwrite(m.coeff_id.data(), 4, m.coeff_id.size(), f);
     std::fwrite(m.cf_len.data(), 4, m.cf_len.size(), f);
     for (size_t i = 0; i < m.cf_len.size(); ++i) std::fwrite(m.cf_ptr[i], 4, m.cf_len[i], f);

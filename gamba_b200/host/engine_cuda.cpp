@@ -17,6 +17,8 @@ public:
         cfg.p = p; cfg.coeff_bytes = 4; cfg.repr = GAMBA_CUDA_REPR_STANDARD;
         cfg.device = 0; cfg.seed = prm.seed; cfg.rank = 0; cfg.world_size = 1;
         if (gamba_cuda_create(&cfg, &e_)) throw std::runtime_error(std::string("gamba_cuda_create: ") + gamba_cuda_last_error());
+        // the basis' coefficient arrays are immutable for the life of the run: keep them on the device
+        if (gamba_cuda_set_option(e_, "coeff_cache", 1)) throw std::runtime_error(gamba_cuda_last_error());
         if (!std::getenv("GAMBA_NO_PINNED")) {                // step matrices are built in page-locked memory
             host_alloc_hook().alloc = gamba_cuda_host_alloc;
             host_alloc_hook().release = gamba_cuda_host_free;
@@ -51,6 +53,10 @@ private:
         in.n_top = m.n_top; in.n_bot = m.n_bot; in.n_cols = m.n_cols;
         in.n_coeff_arrays = (uint32_t)m.cf_ptr.size(); in.nnz = m.nnz();
         in.row_ptr = m.row_ptr.data(); in.col_idx = m.col.data(); in.coeff_id = m.coeff_id.data();
+        if (m.src) {     // indirect form: no O(nnz) rewrite on the host
+            in.col_idx = m.src; in.col_idx_len = m.src_len; in.row_src = m.row_src.data();
+            in.col_map = m.col_map.data(); in.col_map_len = (uint32_t)m.col_map.size();
+        }
         ptrs_.assign(m.cf_ptr.begin(), m.cf_ptr.end());
         in.coeff_ptr = ptrs_.data(); in.coeff_len = m.cf_len.data(); in.flags = flags;
         gamba_cuda_step_out o{};

@@ -147,7 +147,7 @@ void F4::update(uint32_t h) {
     auto same = [&](const NP& a, const NP& b) { return std::memcmp(ex_of(a), ex_of(b), st * sizeof(uint16_t)) == 0; };
     upd_t_[1] += now_s() - tu; tu = now_s();
     // increasing lcm; equal lcm: coprime first, then older generator first
-    std::sort(np.begin(), np.end(), [&](NP const& a, NP const& b) {
+    parallel_sort(*pool_, np, [&](NP const& a, NP const& b) {
         if (keys_ok && a.key != b.key) return a.key < b.key;
         const int c = cx_.cmp(ex_of(a), ex_of(b));
         if (c != 0) return c < 0;
@@ -412,35 +412,31 @@ void F4::convert() {
     for (uint32_t h = 0; h < nc; ++h) h2c[h] = newcol[colof[h]];
 
     M_.p = p_; M_.n_top = ntop; M_.n_bot = (uint32_t)bot.size(); M_.n_cols = nc;
+    // Indirect hand-over (include/gamba_cuda.h): the rows stay where they were generated (row_mon_, as
+    // step-table handles); the engine gets their offsets in block-form order and the handle -> column map.
     M_.row_ptr.assign(nrows + 1, 0);
-    M_.col.resize(row_mon_.size());
+    M_.row_src.assign(nrows, 0);
     M_.coeff_id.assign(nrows, 0); M_.cf_ptr.clear(); M_.cf_len.clear();
     static std::vector<int32_t> gmap;
     gmap.assign(G_.size(), -1);
-    std::vector<uint32_t> rows(top);
-    rows.insert(rows.end(), bot.begin(), bot.end());
     uint64_t w = 0;
-    for (size_t i = 0; i < nrows; ++i) {
-        const uint32_t r = rows[i];
+    uint32_t i = 0;
+    auto place = [&](uint32_t r) {
         w += row_off_[r + 1] - row_off_[r];
         M_.row_ptr[i + 1] = w;
+        M_.row_src[i] = row_off_[r];
         const uint32_t g = row_gen_[r];
         if (gmap[g] < 0) {
             gmap[g] = (int32_t)M_.cf_ptr.size();
             M_.cf_ptr.push_back(G_[g].cf.data());
             M_.cf_len.push_back((uint32_t)G_[g].cf.size());
         }
-        M_.coeff_id[i] = (uint32_t)gmap[g];
-    }
-    pool_->parallel_for(nrows, 64, [&](size_t i0, size_t i1) {
-    for (size_t i = i0; i < i1; ++i) {
-        const uint32_t r = rows[i];
-        uint32_t* dst = &M_.col[M_.row_ptr[i]];
-        const uint32_t* src = &row_mon_[row_off_[r]];
-        const uint64_t len = row_off_[r + 1] - row_off_[r];
-        for (uint64_t k = 0; k < len; ++k) dst[k] = h2c[src[k]];
-    }
-    });
+        M_.coeff_id[i++] = (uint32_t)gmap[g];
+    };
+    for (uint32_t r : top) place(r);
+    for (uint32_t r : bot) place(r);
+    M_.src = row_mon_.data(); M_.src_len = row_mon_.size();
+    M_.col_map.swap(h2c);
     stats.t_convert += now_s() - t0;
     stats.max_rows = std::max<uint64_t>(stats.max_rows, nrows);
     stats.max_cols = std::max<uint64_t>(stats.max_cols, nc);

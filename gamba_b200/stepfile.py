@@ -21,6 +21,9 @@ class Step:
     coeff_id: np.ndarray    # uint32 [n_rows]
     coeff_len: np.ndarray   # uint32 [n_arrays]
     pool: np.ndarray        # uint32, the coefficient arrays back to back
+    # indirect form of the ABI (include/gamba_cuda.h): `col` then holds caller handles, stored anywhere
+    row_src: np.ndarray | None = None   # uint64 [n_rows]: where row r's entries start in `col`
+    col_map: np.ndarray | None = None   # uint32: handle -> block-form column
 
     @property
     def nnz(self) -> int:
@@ -50,6 +53,28 @@ class Rows:
     def same_as(self, other: "Rows") -> bool:
         return (self.n_new == other.n_new and np.array_equal(self.row_ptr, other.row_ptr)
                 and np.array_equal(self.col, other.col) and np.array_equal(self.val, other.val))
+
+
+def to_indirect(s: Step, seed: int = 1) -> Step:
+    """The same step in the ABI's indirect form: rows stored in a random order with gaps between them,
+    entries as handles under a random relabelling of the columns."""
+    rng = np.random.default_rng(seed)
+    n_rows = s.n_rows
+    rp = s.row_ptr.astype(np.int64)
+    lens = np.diff(rp)
+    order = rng.permutation(n_rows)
+    gaps = rng.integers(0, 3, size=n_rows)
+    starts = np.zeros(n_rows, dtype=np.int64)
+    pos = 0
+    for r in order:
+        pos += int(gaps[r]); starts[r] = pos; pos += int(lens[r])
+    handle_of_col = rng.permutation(s.n_cols).astype(np.uint32)     # column c is called handle_of_col[c]
+    col_map = np.empty(s.n_cols, dtype=np.uint32); col_map[handle_of_col] = np.arange(s.n_cols, dtype=np.uint32)
+    store = rng.integers(0, s.n_cols, size=pos + 2, dtype=np.int64).astype(np.uint32)   # garbage in the gaps
+    for r in range(n_rows):
+        store[starts[r]: starts[r] + lens[r]] = handle_of_col[s.col[rp[r]: rp[r + 1]]]
+    return Step(s.p, s.n_top, s.n_bot, s.n_cols, s.row_ptr, store, s.coeff_id, s.coeff_len, s.pool,
+                row_src=starts.astype(np.uint64), col_map=col_map)
 
 
 def load_step(path: str) -> Step:

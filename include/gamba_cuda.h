@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define GAMBA_CUDA_ABI_VERSION 1
+#define GAMBA_CUDA_ABI_VERSION 2
 
 #define GAMBA_CUDA_REPR_STANDARD   0u
 #define GAMBA_CUDA_REPR_MONTGOMERY 1u
@@ -80,6 +80,17 @@ typedef struct gamba_cuda_step_in {
     const void* const* coeff_ptr;      /* [n_coeff_arrays], elements coeff_bytes wide         */
     const uint32_t* coeff_len;         /* [n_coeff_arrays]                                    */
     uint32_t flags;
+    /* Optional indirect form (all zero / NULL = the direct form above). It lets a driver hand its rows over
+       where symbolic preprocessing left them (matrix_f4 keeps rows as monomial handles and numbers the
+       columns afterwards, source/matrix.hpp:603-673) without rewriting O(nnz) data on the host:
+         row_src  [n_top+n_bot]  row r's entries are col_idx[row_src[r] .. row_src[r] + len(r)), with
+                                 len(r) = row_ptr[r+1] - row_ptr[r]; rows may lie anywhere, in any order
+         col_map  [col_map_len]  col_idx holds caller handles h; the block-form column is col_map[h]
+         col_idx_len             number of entries of col_idx to copy (>= nnz when rows are not packed)  */
+    uint32_t col_map_len;
+    const uint64_t* row_src;
+    const uint32_t* col_map;
+    uint64_t col_idx_len;
 } gamba_cuda_step_in;
 
 typedef struct gamba_cuda_step_out {
@@ -157,6 +168,9 @@ int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
 /* Options: "tile_cols", "ctas_per_sm" (0 = automatic), "echelon_mma" (default 1: blocked echelon with int8
    tensor-core trailing updates; 0: one rank-1 update per pivot),
+   "coeff_cache" (default 0; 1: coefficient arrays stay on the device across steps, keyed by host pointer - the
+   caller promises they are immutable while the engine lives, as the reference's basis storage is,
+   source/matrix.hpp:189-193; setting the option again drops the cache),
    "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
    margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);

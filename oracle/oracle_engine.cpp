@@ -35,9 +35,10 @@ void OracleEngine::reduce_step(const StepMatrix& m, NewRows& out) {
         const uint32_t row = ntop + r;
         const uint32_t* cf = m.cf_ptr[m.coeff_id[row]];
         uint32_t lo = ncols;
-        for (uint64_t k = m.row_ptr[row], j = 0; k < m.row_ptr[row + 1]; ++k, ++j) {
-            acc[m.col[k]] = cf[j];
-            if (m.col[k] < lo) lo = m.col[k];
+        for (uint64_t j = 0, n = m.row_ptr[row + 1] - m.row_ptr[row]; j < n; ++j) {
+            const uint32_t c = m.col_at(row, j);
+            acc[c] = cf[j];
+            if (c < lo) lo = c;
         }
         for (uint32_t c = lo; c < ntop; ++c) {
             uint64_t v = acc[c] % p;
@@ -46,9 +47,10 @@ void OracleEngine::reduce_step(const StepMatrix& m, NewRows& out) {
             const uint32_t* pc = m.cf_ptr[m.coeff_id[c]];
             const uint64_t a = m.row_ptr[c], b = m.row_ptr[c + 1];
             fma_top += b - a;
-            for (uint64_t k = a + 1, j = 1; k < b; ++k, ++j) {
-                uint64_t x = acc[m.col[k]] + mult * pc[j];
-                acc[m.col[k]] = x >= P2 ? x - P2 : x;
+            for (uint64_t j = 1; j < b - a; ++j) {
+                const uint32_t cc = m.col_at(c, j);
+                uint64_t x = acc[cc] + mult * pc[j];
+                acc[cc] = x >= P2 ? x - P2 : x;
             }
         }
         std::vector<uint32_t> d(nnp);

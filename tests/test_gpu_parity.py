@@ -237,3 +237,18 @@ def test_31bit_prime_with_several_non_pivot_tiles(step_dirs, engines):
     eng = engines(2147483647)
     assert check_dir(d, eng) >= 2
     assert eng.counters()["n_tiles"] >= 3
+
+
+@pytest.mark.parametrize("p", [32003, 2147483647])
+def test_indirect_hand_over_form(built, engines, p):
+    """ABI v2: rows stored anywhere (row_src), entries as caller handles (col_map) — the form the driver uses
+    so that it never rewrites O(nnz) data (reference: rows are monomial handles, source/matrix.hpp:183-187)."""
+    from gamba_b200.stepfile import to_indirect
+    from oracle import oracle
+    s = synthetic_step(600, 800, 0.05, p, seed=13, top_frac=0.85, share=6)
+    want, _, _ = oracle.reduce(s)
+    eng = engines(p)
+    assert eng.reduce(s).same_as(want)
+    assert eng.reduce(to_indirect(s, seed=2)).same_as(want)
+    eng.stage(to_indirect(s, seed=3))
+    assert eng.reduce_staged().same_as(want)
