@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -243,11 +244,27 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
     row_mon_.resize(row_off_.back());
     row_gen_.insert(row_gen_.end(), gens.begin(), gens.end());
     row_top_.insert(row_top_.end(), tops.begin(), tops.end());
+    {   // contiguous term data of the generators of this batch (once per generator)
+        std::vector<uint32_t> need;
+        for (uint32_t g : gens) if (G_[g].hv.empty()) { G_[g].hv.resize(1); need.push_back(g); }
+        pool_->parallel_for(need.size(), 4, [&](size_t a, size_t b) {
+            for (size_t x = a; x < b; ++x) {
+                Poly& f = G_[need[x]];
+                const size_t n = f.mon.size();
+                f.ex.resize(n * st); f.hv.resize(n);
+                for (size_t k = 0; k < n; ++k) {
+                    std::memcpy(&f.ex[k * st], bt_.e(f.mon[k]), st * sizeof(uint16_t));
+                    f.hv[k] = bt_.hv[f.mon[k]];
+                }
+            }
+        });
+    }
     // Sub-batches: the table must have room for every term of a batch being NEW (no growth inside the
     // parallel region), while almost all terms are hits - so a batch is capped near the table's size.
     for (size_t b0 = 0; b0 < nb;) {
         double tA = now_s();
-        const uint64_t cap = std::max<uint64_t>(1u << 20, st_.size());
+        static const uint64_t cap_min = std::getenv("GAMBA_ROWGEN_CAP") ? std::strtoull(std::getenv("GAMBA_ROWGEN_CAP"), nullptr, 10) : (1u << 20);
+        const uint64_t cap = std::max<uint64_t>(cap_min, st_.size());
         size_t b1 = b0; uint64_t bt = 0;
         while (b1 < nb && (b1 == b0 || bt + G_[gens[b1]].mon.size() <= cap)) bt += G_[gens[b1++]].mon.size();
         st_.reserve_more(bt);
@@ -259,10 +276,11 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
                 const uint32_t hq = hqs[i];
                 uint32_t* out = &row_mon_[row_off_[r0 + i]];
                 uint16_t tmp[258];
-                for (size_t k = 0; k < f.mon.size(); ++k) {
-                    const uint16_t* a = bt_.e(f.mon[k]);
+                const uint16_t* a = f.ex.data();
+                const uint32_t* fh = f.hv.data();
+                for (size_t k = 0, n = f.mon.size(); k < n; ++k, a += st) {
                     for (int j = 0; j < st; ++j) tmp[j] = (uint16_t)(a[j] + q[j]);
-                    out[k] = st_.insert_mt(tmp, bt_.hv[f.mon[k]] + hq);
+                    out[k] = st_.insert_mt(tmp, fh[k] + hq);
                 }
             }
         });

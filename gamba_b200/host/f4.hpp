@@ -51,6 +51,10 @@ private:
     struct Poly {
         std::vector<uint32_t> mon;  // basis-table handles, decreasing
         std::vector<uint32_t> cf;   // residues in [0,p), cf[0] == 1
+        // term data laid out contiguously for row generation (filled on first use as a reducer or pair row):
+        // streaming reads instead of two random accesses into the basis table per term
+        std::vector<uint16_t> ex;   // [terms][stride]
+        std::vector<uint32_t> hv;   // [terms]
         uint32_t deg = 0;
         uint64_t lm_mask = 0;
         bool redundant = false;

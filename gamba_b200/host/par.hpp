@@ -13,10 +13,6 @@
 
 namespace gb {
 
-// Busy-wait step without PAUSE: under KVM, PAUSE loops trigger pause-loop exits that deschedule the vCPU
-// (measured here: 0.5 ms per parallel region with PAUSE, ~10 us without).
-static inline void cpu_relax() { asm volatile("" ::: "memory"); }
-
 class ThreadPool {
 public:
     explicit ThreadPool(int n) : n_(std::max(1, n)) {
@@ -30,6 +26,9 @@ public:
     int size() const { return n_; }
 
     // fn(begin, end) over [0, n) in chunks of `grain`, handed out dynamically; returns when all are done.
+    // The caller waits for stragglers WITHOUT the PAUSE instruction: under KVM a PAUSE loop on the critical
+    // thread triggers pause-loop exits that deschedule its vCPU (measured: 10x slower regions); idle
+    // workers do use PAUSE, where such an exit costs nothing.
     // Workers spin for a short while between regions (the driver's phases issue many regions of well under a
     // millisecond back to back; a condition-variable wake-up alone costs more than such a region) and
     // only then go to sleep, so they cost nothing while the GPU works.
@@ -49,7 +48,7 @@ public:
         }
         work(f);
         for (unsigned spins = 0; busy_.load(std::memory_order_acquire) != 0; ++spins) {
-            if (spins < (1u << 20)) cpu_relax(); else std::this_thread::yield();
+            if (spins < (1u << 20)) asm volatile("" ::: "memory"); else std::this_thread::yield();
         }
         job_ = nullptr;
     }
@@ -67,7 +66,7 @@ private:
         for (;;) {
             unsigned spins = 0;
             while (gen_.load(std::memory_order_acquire) == seen) {
-                if (++spins < 2000000) { cpu_relax(); continue; }
+                if (++spins < 20000) { __builtin_ia32_pause(); continue; }
                 std::unique_lock<std::mutex> lk(m_);
                 sleepers_.fetch_add(1, std::memory_order_release);
                 cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
