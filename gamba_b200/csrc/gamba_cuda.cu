@@ -23,6 +23,7 @@
 #include "kernels_echelon_mma.cuh"
 #include "kernels_elim.cuh"
 #include "kernels_prep.cuh"
+#include "kernels_schur.cuh"
 #include "layout.cuh"
 
 namespace gcu {
@@ -77,7 +78,7 @@ struct gamba_cuda_engine {
     gcu::Fp f{};
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6]{};
+    cudaEvent_t ev[8]{};
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
@@ -85,6 +86,10 @@ struct gamba_cuda_engine {
     int64_t opt_coeff_cache = 0;     // keep coefficient arrays on the device across steps (caller: immutable arrays)
     std::unordered_map<const void*, std::pair<uint64_t, uint32_t>> cache;   // host pointer -> (offset in d_pool, length)
     uint64_t cache_used = 0;
+    int64_t opt_schur = 1;           // 1: D' = D + M B on the tensor cores when the limb planes fit, 0: sparse path
+    int64_t opt_schur_max_gb = 64;   // budget for the Mx and Bt limb planes
+    int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
+    int64_t opt_schur_kchunk = 0;    // k-steps between accumulator folds (0 = the exactness bound; tests lower it)
     int64_t opt_mc = 0;              // Monte-Carlo combinations instead of the rows themselves
     int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
     int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
@@ -105,6 +110,9 @@ struct gamba_cuda_engine {
     // elimination / echelon state
     gcu::DevBuf d_dprime, d_row_nz, d_list_k, d_list_m, d_queue_stats;
     gcu::DevBuf d_em_live, d_em_xa, d_em_pbt;
+    gcu::DevBuf d_mx, d_bt;
+    bool bt_built = false;
+    double t_sparse_dev = 0, t_schur_dev = 0;
     gcu::DevBuf d_lead, d_nz_list, d_piv_row, d_piv_col, d_is_piv, d_counts, d_out_ptr, d_out_col, d_out_val;
     uint32_t n_local = 0, n_local_max = 0, n_gather_rows = 0;
     bool eliminated = false;
@@ -182,7 +190,7 @@ struct StepHdr { uint32_t n_top, n_bot, n_cols, n_arr; uint64_t nnz, pool_len, n
 
 void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     const double t0 = wall_s();
-    staged = false; eliminated = false;
+    staged = false; eliminated = false; bt_built = false;
     const bool use_bcast = cfg.world_size > 1 && bcast_fn != nullptr;
     const bool have = !use_bcast || cfg.rank == 0;       // this rank uploads the step from its host buffers
     if (have && !in) throw std::runtime_error("no step passed (only ranks > 0 of a broadcasting group may pass NULL)");
@@ -403,12 +411,60 @@ void gamba_cuda_engine::eliminate() {
     ea.mc_seed = cfg.seed * 0x9e3779b97f4a7c15ull + mc_draw;
     if (mc_k) { GCU_CHECK(cudaMemcpyAsync(&ea.mc_first, d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); GCU_CHECK(cudaStreamSynchronize(stream)); }
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
+
+    // Schur mode: the B half of the elimination is a dense product on the tensor cores (kernels_schur.cuh)
+    const uint32_t nl = f.small ? 2u : 4u;
+    const uint32_t sc_bm = f.small ? schur_bm<2>() : schur_bm<4>(), sc_bn = f.small ? schur_bn<2>() : schur_bn<4>();
+    const uint32_t kp = (L.n_top + SC_BK - 1) / SC_BK * SC_BK;
+    const uint32_t m_tiles = (n_local + sc_bm - 1) / sc_bm, n_tiles = (L.n_nonpiv + sc_bn - 1) / sc_bn;
+    const uint64_t mx_plane = (uint64_t)m_tiles * sc_bm * kp, bt_plane = (uint64_t)n_tiles * sc_bn * kp;
+    const bool schur = opt_schur && n_local && L.n_nonpiv && L.n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
+                       (double)nl * (mx_plane + bt_plane) <= (double)opt_schur_max_gb * 1e9 &&
+                       (uint64_t)m_tiles * n_tiles < (1ull << 31);
     GCU_CHECK(cudaEventRecord(ev[2], stream));
+    if (schur) {
+        d_mx.ensure(nl * mx_plane);
+        GCU_CHECK(cudaMemsetAsync(d_mx.p, 0, nl * mx_plane, stream));
+        ea.mx = d_mx.as<uint8_t>(); ea.mx_plane = mx_plane; ea.mx_kp = kp; ea.mx_nl = nl;
+        if (!bt_built) {
+            d_bt.ensure(nl * bt_plane);
+            GCU_CHECK(cudaMemsetAsync(d_bt.p, 0, nl * bt_plane, stream));
+            BtArgs ba{};
+            ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
+            ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
+            schur_bt_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(ba);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 1;
+            bt_built = true;
+        }
+    }
+    GCU_CHECK(cudaEventRecord(ev[6], stream));
     if (n_local && L.n_nonpiv) {
         kern<<<elim_grid, ELIM_CTA_THREADS, smem, stream>>>(ea);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 1;
     }
+    GCU_CHECK(cudaEventRecord(ev[7], stream));
+    if (schur) {
+        SchurArgs sa{};
+        sa.f = f; sa.mx = d_mx.as<uint8_t>(); sa.bt = d_bt.as<uint8_t>(); sa.mx_plane = mx_plane; sa.bt_plane = bt_plane;
+        sa.kp = kp; sa.n_rows = n_local; sa.n_cols = L.n_nonpiv; sa.ld = L.ld_dprime;
+        sa.d = dloc; sa.row_nz = nzloc; sa.m_tiles = m_tiles; sa.n_tiles = n_tiles;
+        sa.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); sa.k_first = ea.mc_first;
+        sa.row_begin = rank; sa.row_step = world;
+        const uint32_t kc_max = f.small ? schur_kchunk<2>() : schur_kchunk<4>();
+        sa.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, kc_max) : kc_max;
+        if (f.small) {
+            GCU_CHECK(cudaFuncSetAttribute(schur_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem<2>()));
+            schur_mma_kernel<2><<<m_tiles * n_tiles, schur_threads<2>(), schur_smem<2>(), stream>>>(sa);
+        } else {
+            GCU_CHECK(cudaFuncSetAttribute(schur_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem<4>()));
+            schur_mma_kernel<4><<<m_tiles * n_tiles, schur_threads<4>(), schur_smem<4>(), stream>>>(sa);
+        }
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 1;
+        ctr.schur_macs = (uint64_t)n_local * L.n_top * L.n_nonpiv;
+    } else ctr.schur_macs = 0;
     GCU_CHECK(cudaEventRecord(ev[3], stream));
     eliminated = true;
 }
@@ -515,6 +571,9 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     GCU_CHECK(cudaStreamSynchronize(stream));
     float ms = 0;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_elim_dev = ms * 1e-3;
+    GCU_CHECK(cudaEventElapsedTime(&ms, ev[6], ev[7])); t_sparse_dev = ms * 1e-3;
+    t_schur_dev = t_elim_dev - t_sparse_dev;
+    ctr.seconds_sparse_last = t_sparse_dev; ctr.seconds_schur_last = t_schur_dev;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[4], ev[5])); t_ech_dev = ms * 1e-3;
     ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
     ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
@@ -664,6 +723,10 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
         else if (k == "echelon_mma") e->opt_echelon_mma = value;
         else if (k == "coeff_cache") { e->opt_coeff_cache = value; e->cache.clear(); e->cache_used = 0; }
+        else if (k == "schur") e->opt_schur = value;
+        else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
+        else if (k == "schur_min_top") e->opt_schur_min_top = value;
+        else if (k == "schur_kchunk") e->opt_schur_kchunk = value;
         else if (k == "mc") e->opt_mc = value;
         else if (k == "mc_k") e->opt_mc_k = value;
         else if (k == "rank_hint") e->last_rank = value;

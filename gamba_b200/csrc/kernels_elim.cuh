@@ -75,6 +75,11 @@ struct ElimArgs {
     uint32_t mc_first;           // smallest pivot column present in any row to reduce
     uint64_t mc_seed;
     unsigned long long* stats;   // [0] pivot rows applied, [1] multiply-adds done, [2] fma_top
+    // Schur mode (kernels_schur.cuh): the non-pivot tiles are NOT eliminated here; the multipliers are
+    // recorded as u8 limb planes mx[limb][local row][k] and D' = D + M B runs on the tensor cores
+    uint8_t* mx;                 // NULL = eliminate the non-pivot tiles here (sparse path)
+    uint64_t mx_plane;
+    uint32_t mx_kp, mx_nl;
 };
 
 // multiplier of row r in combination q: uniform in [1, p) (splitmix64 finaliser)
@@ -267,12 +272,13 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             __syncthreads();
             // deferred pass over the pivots found in earlier tiles
             // (batches of 32 pivots are dealt to the warps; they commute, no barrier between them)
-            for (uint32_t base0 = 0; base0 < nlist; base0 += 32 * ELIM_CTA_WARPS) {
+            const uint32_t ndefer = (a.mx && t >= L.n_tiles_piv) ? 0u : nlist;     // Schur mode: B half on the tensor cores
+            for (uint32_t base0 = 0; base0 < ndefer; base0 += 32 * ELIM_CTA_WARPS) {
                 if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
                 absorbed += 32 * ELIM_CTA_WARPS;
                 const uint32_t i = base0 + warp * 32 + lane;
                 uint32_t s = 0, len = 0, m = 0;
-                if (i < nlist) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; len = seg_e[k] - s; }
+                if (i < ndefer) { const uint32_t k = lk[i]; m = lm[i]; s = seg_s[k]; len = seg_e[k] - s; }
                 fma += len;
                 elim_apply_segments<SMALLP>(acc_sa, ring_sa, a, s, len, m, __ballot_sync(0xffffffffu, len != 0), lane);
             }
@@ -316,6 +322,10 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                         if (warp == 0) {
                             const uint32_t i = nlist + __popc(nzm & lt);
                             lk[i] = k0 + lane; lm[i] = m;
+                            if (a.mx) {
+                                uint8_t* mp = a.mx + (uint64_t)li * a.mx_kp + k0 + lane;
+                                for (uint32_t l = 0; l < a.mx_nl; ++l) mp[l * a.mx_plane] = (uint8_t)(m >> (8 * l));
+                            }
                             fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
                         }
                     }
@@ -339,7 +349,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             }
         }
         const int any = __syncthreads_or(nz ? 1 : 0);
-        if (tid == 0) a.row_nz[li] = any ? 1u : 0u;
+        if (tid == 0 && !a.mx) a.row_nz[li] = any ? 1u : 0u;      // Schur mode: the product kernel sets the flag
         npiv += tid == 0 ? nlist : 0;
     }
     for (int o = 16; o; o >>= 1) fma += __shfl_xor_sync(0xffffffffu, fma, o);

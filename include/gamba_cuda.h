@@ -163,6 +163,9 @@ typedef struct gamba_cuda_counters {
                                           step ran exactly)                                         */
     uint32_t mc_attempts;              /* ... and how many draws it took to meet the rank margin      */
     double seconds_stage_last;         /* wall time of the last staging: H2D (or broadcast) + staging kernels */
+    double seconds_sparse_last;        /* CUDA-event time of elim_kernel alone (the sparse triangular solve), last step */
+    double seconds_schur_last;         /* ... of the tensor-core product D' = D + M B (limb planes + schur kernel)     */
+    uint64_t schur_macs;               /* mod-p multiply-adds of that product: rows x n_top x n_nonpiv (0 = sparse path) */
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
@@ -171,6 +174,8 @@ int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
    "coeff_cache" (default 0; 1: coefficient arrays stay on the device across steps, keyed by host pointer - the
    caller promises they are immutable while the engine lives, as the reference's basis storage is,
    source/matrix.hpp:189-193; setting the option again drops the cache),
+   "schur" (default 1: the B half of the elimination, D' = D + M B, runs as a dense limb-split product on the
+   tensor cores whenever its operands fit "schur_max_gb" (default 64) GB of HBM; 0: sparse path for both halves),
    "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
    margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);

@@ -252,3 +252,77 @@ def test_indirect_hand_over_form(built, engines, p):
     assert eng.reduce(to_indirect(s, seed=2)).same_as(want)
     eng.stage(to_indirect(s, seed=3))
     assert eng.reduce_staged().same_as(want)
+
+
+# ---- tensor-core product D' = D + M B (kernels_schur.cuh) ------------------------------------------
+
+def schur_engine(p, **opts):
+    from gamba_b200 import LinalgEngine
+    eng = LinalgEngine(p)
+    eng.set_option("schur_min_top", 1)     # default 1024: the small test steps would take the sparse path
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    return eng
+
+
+@pytest.mark.parametrize("p", [251, 32003, 65521, 65537, 2147483647])
+def test_schur_product_synthetic(built, p):
+    """The B half of the elimination as a limb-split int8 product: 2 limbs for p < 2^16, 4 above; ragged
+    tile edges (rows, columns and k not multiples of the tile), bit-exact against the oracle."""
+    from oracle import oracle
+    eng = schur_engine(p)
+    for (nr, nc, dens, seed) in [(400, 520, 0.06, 5), (900, 1300, 0.03, 8), (333, 777, 0.05, 9)]:
+        s = synthetic_step(nr, nc, dens, p, seed=seed, top_frac=0.85, share=7)
+        want, fma_top, _ = oracle.reduce(s)
+        assert eng.reduce(s).same_as(want), (p, nr, nc)
+        c = eng.counters()
+        assert c["schur_macs"] == s.n_bot * s.n_top * s.n_nonpiv and c["fma_top"] == fma_top
+    eng.close()
+
+
+@pytest.mark.parametrize("p", [32003, 2147483647])
+def test_schur_accumulator_folds(built, p):
+    """s32 accumulators are folded into D' every `kchunk` k-steps (the exactness bound is 256 / 128 k-steps of
+    64): forced down to 1 and 3 here so that small steps take many folds."""
+    from oracle import oracle
+    s = synthetic_step(1200, 1500, 0.03, p, seed=17, top_frac=0.9, share=9)
+    want, _, _ = oracle.reduce(s)
+    for kc in (1, 3):
+        eng = schur_engine(p, schur_kchunk=kc)
+        assert eng.reduce(s).same_as(want), kc
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["cyclic7-15", "cyclic7-31", "kat9-16", "eco10-31", "cyclic7-8"])
+def test_schur_every_step_matches_oracle(step_dirs, name):
+    d = step_dirs(name)
+    s0 = load_step(sorted(glob.glob(os.path.join(d, "step_*.bin")))[0])
+    eng = schur_engine(s0.p)
+    assert check_dir(d, eng) > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["cyclic8-15", "cyclic8-31", "kat10-15"])
+def test_sparse_path_still_matches_oracle(step_dirs, name):
+    """Option schur=0: both halves of the elimination in elim_kernel (the path for operands beyond schur_max_gb)."""
+    from gamba_b200 import LinalgEngine
+    d = step_dirs(name, ("--dump-min-nnz", "100000"))
+    s0 = load_step(sorted(glob.glob(os.path.join(d, "step_*.bin")))[0])
+    eng = LinalgEngine(s0.p)
+    eng.set_option("schur", 0)
+    assert check_dir(d, eng) >= 5
+    assert eng.counters()["schur_macs"] == 0
+    eng.close()
+
+
+def test_schur_with_monte_carlo_combinations(step_dirs):
+    eng = schur_engine(32003, mc=1)
+    d = step_dirs("cyclic8-15", ("--dump-min-nnz", "100000"))
+    assert check_dir(d, eng) >= 5
+    eng.close()
+
+
+def test_schur_with_small_tiles(step_dirs):
+    eng = schur_engine(32003, tile_cols=256)
+    assert check_dir(step_dirs("cyclic7-15"), eng) > 0
+    eng.close()

@@ -33,7 +33,7 @@ def main():
         c = eng.counters()
         hits = c["pivots_applied"] / max(1, s.n_bot)
         print(f"{os.path.basename(f)} {s.n_top}+{s.n_bot} x {s.n_cols} nonpiv {s.n_nonpiv} nnz {s.nnz} new {r.n_new} T={c['tile_cols']} nt={c['n_tiles']} "
-              f"elim {best['seconds_eliminate'] * 1e3:.2f} ms ech {best['seconds_echelon'] * 1e3:.2f} ms hits/row {hits:.0f} "
+              f"elim {best['seconds_eliminate'] * 1e3:.2f} ms (sparse {c['seconds_sparse_last'] * 1e3:.2f} schur {c['seconds_schur_last'] * 1e3:.2f}) ech {best['seconds_echelon'] * 1e3:.2f} ms hits/row {hits:.0f} "
               f"fma_applied {c['fma_applied']:.3e} fma_top {c['fma_top']:.3e} Gfma/s {c['fma_top'] / best['seconds_eliminate'] / 1e9:.1f}", flush=True)
 
 
