@@ -22,6 +22,7 @@
 #include "kernels_echelon.cuh"
 #include "kernels_echelon_mma.cuh"
 #include "kernels_elim.cuh"
+#include "kernels_elim_block.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_schur.cuh"
 #include "layout.cuh"
@@ -82,11 +83,16 @@ struct gamba_cuda_engine {
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
+    int64_t opt_elim_warps = 0;      // 4 or 8 warps per row to reduce (0 = automatic)
+    int elim_warps = 8;
     int64_t opt_echelon_mma = 1;     // 1: blocked echelon on the tensor cores, 0: per-pivot kernel
     int64_t opt_coeff_cache = 0;     // keep coefficient arrays on the device across steps (caller: immutable arrays)
     std::unordered_map<const void*, std::pair<uint64_t, uint32_t>> cache;   // host pointer -> (offset in d_pool, length)
     uint64_t cache_used = 0;
     int64_t opt_schur = 1;           // 1: D' = D + M B on the tensor cores when the limb planes fit, 0: sparse path
+    int64_t opt_block = 1;           // blocked sparse solve (kernels_elim_block.cuh): 0 never, 1 when the multipliers are dense, 2 always
+    double last_density = 0;         // pivots hit per row / n_top of the previous step (predictor for this one)
+    bool use_schur = false, use_block = false;   // decided per staged step (plan_step)
     int64_t opt_schur_max_gb = 64;   // budget for the Mx and Bt limb planes
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
     int64_t opt_schur_kchunk = 0;    // k-steps between accumulator folds (0 = the exactness bound; tests lower it)
@@ -102,7 +108,7 @@ struct gamba_cuda_engine {
     uint32_t flags = 0;
     uint64_t nnz = 0;
     gcu::DevBuf d_row_ptr, d_col, d_coeff_id, d_coeff_off, d_pool, d_row_src, d_col_map;
-    gcu::DevBuf d_cnt, d_seg, d_ent, d_diag, d_dnz, d_first, d_scan_tmp;
+    gcu::DevBuf d_seg, d_ent, d_diag, d_dnz, d_first, d_scan_tmp;
     gcu::HostBuf h_pool, h_off;
     uint64_t h2d_bytes = 0;
     double t_stage_wall = 0, t_prep_dev = 0;
@@ -110,7 +116,7 @@ struct gamba_cuda_engine {
     // elimination / echelon state
     gcu::DevBuf d_dprime, d_row_nz, d_list_k, d_list_m, d_queue_stats;
     gcu::DevBuf d_em_live, d_em_xa, d_em_pbt;
-    gcu::DevBuf d_mx, d_bt;
+    gcu::DevBuf d_mx, d_bt, d_mt;
     bool bt_built = false;
     double t_sparse_dev = 0, t_schur_dev = 0;
     gcu::DevBuf d_lead, d_nz_list, d_piv_row, d_piv_col, d_is_piv, d_counts, d_out_ptr, d_out_col, d_out_val;
@@ -161,11 +167,35 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     // Tile width from the number of rows (= warps) wanted in flight per SM: the kernel is
     // latency-bound, shared memory per SM / (warps per SM) is what one accumulator tile gets.
     const uint32_t gran = WINDOW;
-    const uint32_t ctas = (uint32_t)std::max<int64_t>(1, opt_ctas_per_sm > 0 ? opt_ctas_per_sm : 4);
+    // 4 CTAs of 8 warps per SM. Measured with the Schur product on (tools/tune_ctas.sh, cyclic9-15 and kat14-15):
+    // more resident rows with narrower tiles are slower (6: +10 %, 8: +25 %, 12-16 with 4 warps: 2x) - the
+    // deferred passes then stream the pivot rows in pieces of a few entries per tile.
+    uint32_t ctas = 4;
+    elim_warps = ELIM_CTA_WARPS;
+    if (opt_ctas_per_sm > 0) { ctas = (uint32_t)opt_ctas_per_sm; elim_warps = ctas > 8 ? 4 : ELIM_CTA_WARPS; }
+    if (opt_elim_warps == 4 || opt_elim_warps == 8) elim_warps = (int)opt_elim_warps;
+    ctas = std::min<uint32_t>(ctas, 64u / elim_warps);
     const size_t per_cta = std::min<size_t>(((size_t)smem_per_sm / ctas) - 1024 - 64, (size_t)max_smem_optin - 64);
     const uint32_t words_per_col = f.small ? 1u : 2u;   // kernels_elim.cuh: Acc<SMALLP>::WORDS
-    const size_t cta_words = per_cta / sizeof(uint32_t) - (size_t)ELIM_CTA_WARPS * ELIM_SCRATCH_WORDS;
+    const size_t cta_words = per_cta / sizeof(uint32_t) - (size_t)elim_warps * ELIM_SCRATCH_WORDS;
     uint32_t tmax = (uint32_t)((cta_words - 4) / words_per_col - 1) / gran * gran;
+    // Schur mode: the B half of the elimination is a dense product on the tensor cores (kernels_schur.cuh), and
+    // (unless Monte-Carlo combinations are on) the A half runs R rows per CTA over narrower tiles
+    {
+        const uint32_t world = std::max(1u, cfg.world_size);
+        const uint32_t nloc = (n_bot + world - 1) / world;
+        const uint32_t nl = f.small ? 2u : 4u;
+        const uint32_t sc_bm = f.small ? schur_bm<2>() : schur_bm<4>(), sc_bn = f.small ? schur_bn<2>() : schur_bn<4>();
+        const uint64_t kp = (n_top + SC_BK - 1) / SC_BK * SC_BK;
+        const uint64_t mt_ = (nloc + sc_bm - 1) / sc_bm, nt_ = (L.n_nonpiv + sc_bn - 1) / sc_bn;
+        use_schur = opt_schur && nloc && L.n_nonpiv && n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
+                    (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kp <= (double)opt_schur_max_gb * 1e9 && mt_ * nt_ < (1ull << 31);
+        // R rows per CTA pay when most pivot rows hit most rows (katsura/eco: 60-70 % of the multipliers are non-zero):
+        // every entry of A is then streamed once per block of rows. With sparse multipliers (cyclic9: 10-40 %) the
+        // row-per-CTA kernel, which only touches the pivot rows a row needs, is faster (tools/blk_variants.sh).
+        use_block = use_schur && !opt_mc && (opt_block >= 2 || (opt_block == 1 && n_top >= 32768 && last_density >= 0.5));
+        if (use_block) tmax = BLK_TMAX;
+    }
     if (opt_tile_cols > 0) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
     auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
     // pivot tiles of equal width; the non-pivot range is cut with the same width
@@ -220,7 +250,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     choose_layout(hd.n_top, hd.n_bot, hd.n_cols);
     flags = hd.flags; nnz = hd.nnz;
     if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
-    if (nnz + 3ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
+    if (nnz + 1ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
 
     double tq = wall_s(); dbg_[0] += tq - t0;
@@ -307,22 +337,21 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     dbg_[2] += wall_s() - tq; tq = wall_s();
     const uint64_t n_cnt = (uint64_t)n_rows * L.n_tiles + 1;
     const uint64_t n_diag = std::max<uint64_t>((uint64_t)L.n_windows * WINDOW * WINDOW, 1);
-    d_cnt.ensure(n_cnt * sizeof(uint32_t));
-    d_seg.ensure(std::max<uint64_t>((uint64_t)(L.n_tiles + 1) * n_rows, 1) * sizeof(uint32_t));
-    d_ent.ensure((nnz + 3ull * n_rows * L.n_tiles + 4) * sizeof(uint2));   // segments padded to 4 entries
+    d_seg.ensure(n_cnt * sizeof(uint32_t));
+    d_ent.ensure((nnz + 1ull * n_rows * L.n_tiles + 4) * sizeof(uint2));   // segments padded to an even number of entries
     d_diag.ensure(n_diag * sizeof(uint32_t));
     d_dnz.ensure(std::max<uint32_t>(L.n_windows, 1) * sizeof(uint32_t));
     d_first.ensure((std::max<uint32_t>(L.n_bot, 1) + 1) * sizeof(uint32_t));
     dbg_[3] += wall_s() - tq; tq = wall_s();
     GCU_CHECK(cudaEventRecord(ev[0], stream));
-    GCU_CHECK(cudaMemsetAsync(d_cnt.p, 0, n_cnt * sizeof(uint32_t), stream));
+    GCU_CHECK(cudaMemsetAsync(d_seg.p, 0, n_cnt * sizeof(uint32_t), stream));
     GCU_CHECK(cudaMemsetAsync(d_diag.p, 0, n_diag * sizeof(uint32_t), stream));
 
     PrepArgs pa{};
     pa.L = L; pa.f = f;
     pa.row_ptr = d_row_ptr.as<uint64_t>(); pa.col = d_col.as<uint32_t>(); pa.coeff_id = d_coeff_id.as<uint32_t>();
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
-    pa.cnt = d_cnt.as<uint32_t>(); pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
+    pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
     pa.diag = d_diag.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
     pa.row_src = hd.has_row_src ? d_row_src.as<uint64_t>() : nullptr;
     pa.col_map = hd.col_map_len ? d_col_map.as<uint32_t>() : nullptr;
@@ -338,9 +367,9 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         prep_count_kernel<<<nblk, 256, sh, stream>>>(pa);
         GCU_CHECK(cudaGetLastError());
         size_t tmp_bytes = 0;
-        GCU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pa.cnt, pa.cnt, (int64_t)n_cnt, stream));
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pa.seg, pa.seg, (int64_t)n_cnt, stream));
         d_scan_tmp.ensure(tmp_bytes);
-        GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, pa.cnt, pa.cnt, (int64_t)n_cnt, stream));
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, pa.seg, pa.seg, (int64_t)n_cnt, stream));
         prep_fill_kernel<<<nblk, 256, sh, stream>>>(pa);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 3;
@@ -371,11 +400,13 @@ void gamba_cuda_engine::eliminate() {
 
     const uint32_t words_per_col = f.small ? 1u : 2u;
     const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
-    const size_t smem = (acc_words + (size_t)ELIM_CTA_WARPS * ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
-    auto kern = f.small ? elim_kernel<true> : elim_kernel<false>;
+    const size_t smem = (acc_words + (size_t)elim_warps * ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
+    const int elim_threads = elim_warps * 32;
+    auto kern = elim_warps == 4 ? (f.small ? elim_kernel<true, 4> : elim_kernel<false, 4>)
+                                : (f.small ? elim_kernel<true, 8> : elim_kernel<false, 8>);
     GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ELIM_CTA_THREADS, smem));
+    GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, elim_threads, smem));
     if (occ < 1) throw std::runtime_error("elimination kernel does not fit on an SM");
     if (opt_ctas_per_sm > 0) occ = std::min<int>(occ, (int)opt_ctas_per_sm);
     elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
@@ -383,8 +414,10 @@ void gamba_cuda_engine::eliminate() {
 
     d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.ld_dprime, 1) * sizeof(uint32_t));
     d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
-    d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
-    d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
+    if (!(use_schur && use_block)) {     // the blocked kernel keeps its multipliers in d_mt instead
+        d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
+        d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
+    }
     d_queue_stats.ensure(64);
     GCU_CHECK(cudaMemsetAsync(d_queue_stats.p, 0, 64, stream));
     GCU_CHECK(cudaMemsetAsync(d_row_nz.p, 0, std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t), stream));
@@ -418,9 +451,8 @@ void gamba_cuda_engine::eliminate() {
     const uint32_t kp = (L.n_top + SC_BK - 1) / SC_BK * SC_BK;
     const uint32_t m_tiles = (n_local + sc_bm - 1) / sc_bm, n_tiles = (L.n_nonpiv + sc_bn - 1) / sc_bn;
     const uint64_t mx_plane = (uint64_t)m_tiles * sc_bm * kp, bt_plane = (uint64_t)n_tiles * sc_bn * kp;
-    const bool schur = opt_schur && n_local && L.n_nonpiv && L.n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
-                       (double)nl * (mx_plane + bt_plane) <= (double)opt_schur_max_gb * 1e9 &&
-                       (uint64_t)m_tiles * n_tiles < (1ull << 31);
+    const bool schur = use_schur && n_local;
+    const bool block = schur && use_block;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (schur) {
         d_mx.ensure(nl * mx_plane);
@@ -439,8 +471,30 @@ void gamba_cuda_engine::eliminate() {
         }
     }
     GCU_CHECK(cudaEventRecord(ev[6], stream));
-    if (n_local && L.n_nonpiv) {
-        kern<<<elim_grid, ELIM_CTA_THREADS, smem, stream>>>(ea);
+    if (block) {
+        // R rows per CTA, 2 CTAs per SM (kernels_elim_block.cuh); D is scattered into the zeroed D' block
+        const uint32_t R = f.small ? BlkRows<true>::R : BlkRows<false>::R;
+        const size_t bsmem = f.small ? blk_smem_bytes<true>(L.n_windows) : blk_smem_bytes<false>(L.n_windows);
+        auto bk = f.small ? elim_block_kernel<true> : elim_block_kernel<false>;
+        GCU_CHECK(cudaFuncSetAttribute(bk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        int bocc = 0;
+        GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bocc, bk, BLK_THREADS, bsmem));
+        if (bocc < 1) throw std::runtime_error("blocked elimination kernel does not fit on an SM");
+        const uint32_t n_blocks = (n_local + R - 1) / R;
+        const int bgrid = std::max(1, std::min<int>(prop.multiProcessorCount * bocc, (int)n_blocks));
+        d_mt.ensure((uint64_t)bgrid * std::max(1u, L.n_windows) * R * 32 * sizeof(uint32_t));
+        GCU_CHECK(cudaMemsetAsync(dloc, 0, (uint64_t)n_local * L.ld_dprime * sizeof(uint32_t), stream));
+        BlkArgs b{};
+        b.L = L; b.f = f; b.mu32 = ea.mu32; b.negp = ea.negp; b.norm_every = ea.norm_every;
+        b.seg = ea.seg; b.ent = ea.ent; b.diag = ea.diag; b.dnz = ea.dnz; b.first_piv = ea.first_piv;
+        b.dprime = dloc; b.mt = d_mt.as<uint32_t>(); b.queue = ea.queue;
+        b.row_begin = rank; b.row_step = world; b.n_local = n_local; b.row_ptr = ea.row_ptr; b.stats = ea.stats;
+        b.mx = ea.mx; b.mx_plane = ea.mx_plane; b.mx_kp = ea.mx_kp; b.mx_nl = ea.mx_nl;
+        bk<<<bgrid, BLK_THREADS, bsmem, stream>>>(b);
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 1;
+    } else if (n_local && L.n_nonpiv) {
+        kern<<<elim_grid, elim_threads, smem, stream>>>(ea);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 1;
     }
@@ -578,6 +632,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
     ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
     ctr.fma_top = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[2];
+    if (n_local && L.n_top && !mc_k) last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top);
     ctr.steps += 1;
 
     if ((flags & GAMBA_CUDA_STEP_FINAL) && npiv != L.n_bot)
@@ -721,9 +776,11 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         const std::string k = key ? key : "";
         if (k == "tile_cols") e->opt_tile_cols = value;
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
+        else if (k == "elim_warps") e->opt_elim_warps = value;
         else if (k == "echelon_mma") e->opt_echelon_mma = value;
         else if (k == "coeff_cache") { e->opt_coeff_cache = value; e->cache.clear(); e->cache_used = 0; }
         else if (k == "schur") e->opt_schur = value;
+        else if (k == "block") e->opt_block = value;
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;
         else if (k == "schur_kchunk") e->opt_schur_kchunk = value;

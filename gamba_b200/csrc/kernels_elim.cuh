@@ -46,8 +46,8 @@
 
 namespace gcu {
 
-constexpr int ELIM_CTA_WARPS = 8;
-constexpr int ELIM_CTA_THREADS = ELIM_CTA_WARPS * 32;
+constexpr int ELIM_CTA_WARPS = 8;         // warps per row to reduce (template parameter WARPS: 8, or 4 when many rows
+                                          // must be resident per SM - the walk over the windows is latency-bound)
 constexpr int ELIM_DEPTH = 4;             // cp.async ring slots per warp (512 B each)
 constexpr int ELIM_SCRATCH_WORDS = ELIM_DEPTH * 128;   // per warp: the ring
 
@@ -134,7 +134,7 @@ template <> struct Acc<false> {  // p < 2^31: lo/hi pair of u32 lanes per column
 };
 
 // Bring every lane of the tile back below p (delayed reduction: done rarely).
-template <bool SMALLP>
+template <bool SMALLP, int ELIM_CTA_THREADS>
 __device__ __forceinline__ void elim_normalise(uint32_t* acc, uint32_t tw, const ElimArgs& a) {
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < tw; i += ELIM_CTA_THREADS) Acc<SMALLP>::set(acc, i, Acc<SMALLP>::get(acc, i, a));
@@ -204,8 +204,8 @@ __device__ __forceinline__ void elim_apply_segments(uint32_t acc_sa, uint32_t ri
             uint4 q;          // padding entries carry value 0 and the sink column: adding 0 there is harmless
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
                          : "r"(ring_lane + (cn & (ELIM_DEPTH - 1)) * 512) : "memory");
-            Acc<SMALLP>::add(acc_sa, q.x, Acc<SMALLP>::mulred(cc.m, q.y, a));
-            Acc<SMALLP>::add(acc_sa, q.z, Acc<SMALLP>::mulred(cc.m, q.w, a));
+            Acc<SMALLP>::add(acc_sa, q.x & 0xffffu, Acc<SMALLP>::mulred(cc.m, q.y, a));   // bits 16-20: window slot of the pivot row
+            Acc<SMALLP>::add(acc_sa, q.z & 0xffffu, Acc<SMALLP>::mulred(cc.m, q.w, a));
         }
         cc.off += 64;
         ++cn;
@@ -213,8 +213,9 @@ __device__ __forceinline__ void elim_apply_segments(uint32_t acc_sa, uint32_t ri
     cp_async_wait<0>();
 }
 
-template <bool SMALLP>
-__global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
+template <bool SMALLP, int ELIM_CTA_WARPS>
+__global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
+    constexpr int ELIM_CTA_THREADS = ELIM_CTA_WARPS * 32;
     extern __shared__ __align__(16) unsigned char elim_smem[];
     __shared__ uint32_t s_q;
     const Layout& L = a.L;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
         for (uint32_t t = t_first; t < L.n_tiles; ++t) {
             const uint32_t t0 = lay_tile_start(L, t), tw = lay_tile_width(L, t);
             const uint32_t* seg_s = a.seg + (uint64_t)t * nr;
-            const uint32_t* seg_e = seg_s + nr;
+            const uint32_t* seg_e = seg_s + 1;          // tile-major table: a segment ends where the next row's starts
             // the previous tile is read (last window / write-out of D') by other threads than those that
             // zero the same words here (two words per column for p >= 2^16): cyclic9-31 lost updates without this
             __syncthreads();
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                 for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x, en.y); }
             } else {                // Monte-Carlo: combination number r of all the rows to reduce
                 for (uint32_t base0 = 0; base0 < a.mc_rows; base0 += 32 * ELIM_CTA_WARPS) {
-                    if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
+                    if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP, ELIM_CTA_THREADS>(acc, tw, a); absorbed = 1; }
                     absorbed += 32 * ELIM_CTA_WARPS;
                     const uint32_t i = base0 + warp * 32 + lane;
                     uint32_t s = 0, len = 0, m = 0;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
             // (batches of 32 pivots are dealt to the warps; they commute, no barrier between them)
             const uint32_t ndefer = (a.mx && t >= L.n_tiles_piv) ? 0u : nlist;     // Schur mode: B half on the tensor cores
             for (uint32_t base0 = 0; base0 < ndefer; base0 += 32 * ELIM_CTA_WARPS) {
-                if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
+                if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP, ELIM_CTA_THREADS>(acc, tw, a); absorbed = 1; }
                 absorbed += 32 * ELIM_CTA_WARPS;
                 const uint32_t i = base0 + warp * 32 + lane;
                 uint32_t s = 0, len = 0, m = 0;
@@ -309,8 +310,8 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                             const int i1 = need ? __ffs(need) - 1 : -1; if (need) need &= need - 1;
                             const uint32_t m0 = __ldg(dg + i0 * WINDOW);
                             const uint32_t m1 = i1 >= 0 ? __ldg(dg + i1 * WINDOW) : 0u;
-                            xa = fp_mac<false>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);
-                            if (i1 >= 0) xa = fp_mac<false>(xa, __shfl_sync(0xffffffffu, av, i1), m1, p2);
+                            xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);     // p < 2^16: 32 products fit 64 bits
+                            if (i1 >= 0) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i1), m1, p2);
                         }
                         x = fp_reduce64(xa, a.f);
                     }
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(ELIM_CTA_THREADS) elim_kernel(ElimArgs a) {
                         }
                     }
                     nlist += __popc(nzm);
-                    if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP>(acc, tw, a); absorbed = 1; }
+                    if (absorbed + 32 > a.norm_every) { elim_normalise<SMALLP, ELIM_CTA_THREADS>(acc, tw, a); absorbed = 1; }
                     absorbed += 32;
                     // the window's non-zero pivot rows are dealt to the warps by rank
                     const uint32_t len = x ? e - s : 0u;

@@ -15,8 +15,8 @@ struct PrepArgs {
     const uint32_t* coeff_id;
     const uint64_t* coeff_off;
     const uint32_t* pool;
-    uint32_t* cnt;        // [n_rows * n_tiles + 1] row-major: counts, then (after the scan) starts
-    uint32_t* seg;        // [(n_tiles + 1) * n_rows] tile-major starts (layout.cuh)
+    uint32_t* seg;        // [n_tiles * n_rows + 1] tile-major: counts, then (after the exclusive scan) segment starts;
+                          // (row, tile) ends where the next element starts (layout.cuh)
     uint2* ent;
     uint32_t* diag;       // [n_windows][32][32]
     uint32_t* dnz;        // [n_windows]
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) prep_count_kernel(PrepArgs a) {
             atomicAdd(&hist[lay_tile(a.L, c)], 1u);
         }
         __syncwarp();
-        for (uint32_t b = lane; b < nt; b += 32) a.cnt[(uint64_t)row * nt + b] = (hist[b] + 3u) & ~3u;  // padded to 32 B
+        for (uint32_t b = lane; b < nt; b += 32) a.seg[(uint64_t)b * a.L.n_rows + row] = (hist[b] + 1u) & ~1u;  // padded to 16 B
         if (row >= a.L.n_top) {
             for (int o = 16; o; o >>= 1) fp = min(fp, __shfl_xor_sync(0xffffffffu, fp, o));
             if (lane == 0) { a.first_piv[row - a.L.n_top] = fp; atomicMin(a.first_min, fp); }
@@ -64,13 +64,9 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
     const uint32_t nt = a.L.n_tiles, nr = a.L.n_rows;
     if (row >= nr) return;
     uint32_t* cur = sh_cur + warp * nt;
-    for (uint32_t b = lane; b < nt; b += 32) {
-        const uint32_t st = a.cnt[(uint64_t)row * nt + b];
-        cur[b] = st;
-        a.seg[(uint64_t)b * nr + row] = st;
-    }
-    if (lane == 0) a.seg[(uint64_t)nt * nr + row] = a.cnt[(uint64_t)(row + 1) * nt];  // row end
+    for (uint32_t b = lane; b < nt; b += 32) cur[b] = a.seg[(uint64_t)b * nr + row];
     __syncwarp();
+    const uint32_t jbits = row < a.L.n_top ? (row % WINDOW) << 16 : 0u;   // pivot rows: position in their window
     const uint64_t s = a.row_src ? a.row_src[row] : a.row_ptr[row], e = s + (a.row_ptr[row + 1] - a.row_ptr[row]);
     const uint32_t* cf = a.pool + a.coeff_off[a.coeff_id[row]];
     const uint32_t lt = (1u << lane) - 1u;
@@ -93,16 +89,16 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
         const uint32_t peers = __match_any_sync(0xffffffffu, bin);
         if (bin != 0xffffffffu) {
             const uint32_t pos = cur[bin] + __popc(peers & lt);
-            a.ent[pos] = make_uint2(off, val);
+            a.ent[pos] = make_uint2(off | jbits, val);
         }
         __syncwarp();
         if (bin != 0xffffffffu && (peers >> lane) <= 1u) cur[bin] += __popc(peers);  // highest lane of the group
         __syncwarp();
     }
-    // pad every (row, tile) segment to a multiple of 4 entries with zero-valued entries aimed at the
-    // sink lane (index tile_cols) of the accumulator tile
+    // pad every (row, tile) segment to an even number of entries (16 B) with a zero-valued entry aimed at
+    // the sink lane (index tile_cols) of the accumulator tile
     for (uint32_t b = lane; b < nt; b += 32)
-        for (uint32_t pos = cur[b]; pos & 3u; ++pos) a.ent[pos] = make_uint2(a.L.tile_cols, 0u);
+        if (cur[b] & 1u) a.ent[cur[b]] = make_uint2(a.L.tile_cols | jbits, 0u);
 }
 
 // One warp per window: replace the strictly-upper block N (A_ww = I + N, diagonal implicit) by the

@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(256) schur_bt_kernel(BtArgs a) {
     if (k >= L.n_top) return;
     const uint32_t nr = L.n_rows;
     for (uint32_t t = L.n_tiles_piv; t < L.n_tiles; ++t) {
-        const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)(t + 1) * nr + k];
+        const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
         const uint32_t c0 = (t - L.n_tiles_piv) * L.tile_cols;
         for (uint32_t i = s + lane; i < e; i += 32) {
             const uint2 en = __ldg(a.ent + i);
             if (en.y == 0) continue;                       // padding
-            uint8_t* dst = a.bt + (uint64_t)(c0 + en.x) * a.kp + k;
+            uint8_t* dst = a.bt + (uint64_t)(c0 + (en.x & 0xffffu)) * a.kp + k;
             for (uint32_t l = 0; l < a.nl; ++l) dst[l * a.bt_plane] = (uint8_t)(en.y >> (8 * l));
         }
     }

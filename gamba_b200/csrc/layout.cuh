@@ -8,15 +8,15 @@
 // the column range is cut into TILES of T columns (T * 8 B of shared memory per
 // warp) and a warp sweeps the tiles left to right.
 //
-// Pivot rows (A|B) and rows to reduce (C|D) are therefore stored re-tiled:
-//   ent[]      (tile-relative column, value) pairs, grouped per row by tile,
-//              ascending column inside a tile; every (row, tile) segment starts on
-//              a 32-byte boundary and is padded to a multiple of 4 entries with
-//              (tile_cols, 0) — a zero aimed at the tile's sink lane — so that a
-//              lane can stream its segment with 32-byte sector loads
-//   seg[]      seg[t * n_rows + row] = first entry of (row, tile t); plane n_tiles
-//              holds the row end. Tile-major so that 32 consecutive pivot rows
-//              (one window) or a run of applied pivots read coalesced.
+// Pivot rows (A|B) and rows to reduce (C|D) are therefore stored re-tiled, TILE-MAJOR:
+//   ent[]      (tile-relative column | position of the pivot row in its window << 16, value) pairs; all
+//              segments of tile 0 in row order, then tile 1, ...: the pivot rows of one window - or of
+//              any run of windows - restricted to one tile are ONE contiguous range, which the blocked
+//              elimination kernel streams with full lanes whatever the length of the single segments
+//              (4-60 entries). Ascending column inside a segment; segments are padded to an even
+//              number of entries (16 B) with (tile_cols, 0) - a zero aimed at the tile's sink lane.
+//   seg[]      seg[t * n_rows + row] = first entry of (row, tile t); the segment ends where the next
+//              element of seg[] starts (one extra element closes the table).
 //   diag[]     for every WINDOW of 32 consecutive pivot columns the INVERSE of the
 //              dense unit upper-triangular 32x32 block A[w*32+i][w*32+j]; the
 //              in-window entries are NOT in ent[]. dnz[w] bit i is set iff row i

@@ -176,6 +176,9 @@ int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
    source/matrix.hpp:189-193; setting the option again drops the cache),
    "schur" (default 1: the B half of the elimination, D' = D + M B, runs as a dense limb-split product on the
    tensor cores whenever its operands fit "schur_max_gb" (default 64) GB of HBM; 0: sparse path for both halves),
+   "block" (with "schur": the sparse half of the elimination for R rows per CTA from one pass over the pivot rows,
+   kernels_elim_block.cuh; 0 never, 1 (default) for steps with >= 32768 pivot rows once the previous step had
+   more than half of its multipliers non-zero, 2 always), "elim_warps", "schur_min_top", "schur_kchunk" (tuning / tests),
    "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
    margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);

@@ -260,6 +260,7 @@ def schur_engine(p, **opts):
     from gamba_b200 import LinalgEngine
     eng = LinalgEngine(p)
     eng.set_option("schur_min_top", 1)     # default 1024: the small test steps would take the sparse path
+    eng.set_option("block", 2)             # default 1: blocked elimination only for big steps with dense multipliers
     for k, v in opts.items():
         eng.set_option(k, v)
     return eng
@@ -293,12 +294,34 @@ def test_schur_accumulator_folds(built, p):
         eng.close()
 
 
+@pytest.mark.parametrize("block", [1, 0])
 @pytest.mark.parametrize("name", ["cyclic7-15", "cyclic7-31", "kat9-16", "eco10-31", "cyclic7-8"])
-def test_schur_every_step_matches_oracle(step_dirs, name):
+def test_schur_every_step_matches_oracle(step_dirs, name, block):
+    """block=1: R rows per CTA (kernels_elim_block.cuh); block=0: one row per CTA (kernels_elim.cuh) - both
+    hand the multipliers to the tensor-core product."""
     d = step_dirs(name)
     s0 = load_step(sorted(glob.glob(os.path.join(d, "step_*.bin")))[0])
-    eng = schur_engine(s0.p)
+    eng = schur_engine(s0.p, block=block)
     assert check_dir(d, eng) > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["cyclic8-15", "cyclic8-31", "kat10-15", "eco11-16"])
+def test_blocked_elimination_larger_steps(step_dirs, name):
+    """Several column tiles of 3392 columns and rows with different first pivots in one block of rows."""
+    d = step_dirs(name, ("--dump-min-nnz", "100000"))
+    s0 = load_step(sorted(glob.glob(os.path.join(d, "step_*.bin")))[0])
+    eng = schur_engine(s0.p)
+    assert check_dir(d, eng) >= 5
+    assert eng.counters()["schur_macs"] > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("tile", [64, 256])
+def test_blocked_elimination_small_tiles(step_dirs, tile):
+    eng = schur_engine(32003, tile_cols=tile)
+    assert check_dir(step_dirs("cyclic7-15"), eng) > 0
+    assert eng.counters()["n_tiles"] >= 4
     eng.close()
 
 
