@@ -11,8 +11,10 @@ gamba_cuda_reduce over that batch of matrices.
           gamba_cuda_reduce_staged in the timed region: kernels + result D2H)
   e2e     the same through gamba_cuda_reduce with pinned HOST buffers: H2D + staging kernels +
           elimination + echelon + D2H all inside the timed region
-  roofline  elimination kernel: algorithmic bytes (fma_top*(4+w) + nnz_in*(4+w)
-          + n_bot*n_nonpiv*8) / CUDA-event time of that kernel / measured HBM peak
+  roofline  elimination stage (C|D by A|B = elim_kernel for the multipliers + the tensor-core product
+          D' = D + M B): algorithmic bytes (fma_top*(4+w) + nnz_in*(4+w) + n_bot*n_nonpiv*8)
+          / CUDA-event time of the stage / measured HBM peak; `parts` splits the time and gives the
+          product's int8 multiply-add rate against the measured IMMA peak
   cpu_baseline  the CPU oracle (a port: the reference's engine is closed source) on a bounded sample
 
 `--impl reference` times the oracle port on bounded samples of the same workload (1 thread: the
@@ -51,7 +53,7 @@ def measured_peaks():
 def measured_traffic():
     """DRAM bytes per elimination-kernel launch from the committed ncu capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01b_elim_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01c_elim_traffic.json")) as f:
             return float(json.load(f)["mean_dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         return None
@@ -276,6 +278,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             e.reduce_staged()
     sync()
     elim_s = [0.0] * len(steps); ech_s = [0.0] * len(steps); dev_s = 0.0
+    sparse_s = 0.0; schur_s = 0.0; schur_imma = 0.0
     fma_top = [0] * len(steps)
     l0 = launches()
     with ClockSampler(local_rank) as clk:
@@ -286,7 +289,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 e.reduce_staged()
                 elim_s[i] += e.last["seconds_eliminate"]; ech_s[i] += e.last["seconds_echelon"]
                 dev_s += e.last["seconds_eliminate"] + e.last["seconds_echelon"]
-                fma_top[i] = e.counters()["fma_top"]
+                c_ = e.counters()
+                fma_top[i] = c_["fma_top"]
+                sparse_s += c_["seconds_sparse_last"]; schur_s += c_["seconds_schur_last"]
+                schur_imma += c_["schur_macs"] * (4 if steps[i].p < 65536 else 16)   # limb products per mod-p multiply-add
         sync()
         t_res = time.perf_counter() - t0
     n_launch = launches() - l0
@@ -329,7 +335,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": total_nnz * args.steps / t_res, "unit": "nnz/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 residues mod p=%d (32-bit delayed-reduction lanes; u8 limbs on the tensor cores in the echelon)" % steps[0].p, "data": "synthetic (generated system, no dataset)",
+            "dtype": "u32 residues mod p=%d (32-bit delayed-reduction lanes in the sparse solve; u8 limbs -> s32 on the tensor cores in the Schur product and the echelon)" % steps[0].p, "data": "synthetic (generated system, no dataset)",
             "config": {"workload": f"{wl_desc} ({len(steps)} matrices, "
                                    f"{total_nnz} nnz per pass, largest {max(s.n_rows for s in steps)} x {max(s.n_cols for s in steps)})",
                        "parallelism": (f"C|D rows sharded r % {world}, step uploaded by rank 0 and replicated by NCCL broadcast, "
@@ -340,10 +346,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": n_launch,
             "clocks": clocks,
-            "roofline": {"kernel": "elim_kernel (C|D by A|B)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "elimination stage C|D by A|B: elim_kernel / elim_block_kernel (sparse solve for the multipliers) + "
+                                   "schur_bt_kernel + schur_mma_kernel (D' = D + M B on the tensor cores)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic() if args.system == "cyclic9-15" else None,
-                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01b_elim_traffic.json (A|B is served from L2)",
+                         "traffic_source": "ncu dram__bytes_read+write of the stage's kernels per matrix, profiles/r01c_elim_traffic.json",
                          "peak_source": peak_src,
+                         "parts": {"sparse_solve_ms_per_step": 1e3 * sparse_s / args.steps, "schur_ms_per_step": 1e3 * schur_s / args.steps,
+                                   "schur_tensor": {"achieved": schur_imma / max(schur_s, 1e-12) / 1e12, "peak": 570.5, "unit": "int8 TMAC/s",
+                                                    "frac": schur_imma / max(schur_s, 1e-12) / 1e12 / 570.5,
+                                                    "peak_source": "mma.sync m16n8k32 u8 microbenchmark on this GPU, profiles/r01b_mma_microbench.txt "
+                                                                   "(time includes zeroing and filling the limb planes)"}},
                          "bytes_alg_per_launch": alg, "avg_launch_ms": dur * 1e3,
                          "share_of_device_time": sum(elim_s) / max(dev_s, 1e-12),
                          "fma_top_per_pass": int(sum(fma_top))},

@@ -1,11 +1,12 @@
 #!/bin/bash
 # Round profile on one B200 (run under gpurun): plain bench first, then the ncu launch list and one
-# --set full capture of the two device-time leaders, all on the same short command.
+# --set full capture of the device-time leaders, all on the same short command.
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/prof_plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/prof_plain.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/prof_launches.csv $CMD > gpurun_out/prof_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:elim_kernel -s 10 -c 3 -f -o gpurun_out/prof_elim $CMD > gpurun_out/prof_ncu2.log 2>&1
+tail -c 2500 gpurun_out/prof_plain.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/prof_launches.csv $CMD > gpurun_out/prof_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"elim_kernel|schur_mma|schur_bt" -s 20 -c 9 -f -o gpurun_out/prof_elim $CMD > gpurun_out/prof_ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:echelon_mma -s 10 -c 3 -f -o gpurun_out/prof_ech $CMD > gpurun_out/prof_ncu3.log 2>&1
 ls -la gpurun_out/prof_*
