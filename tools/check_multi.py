@@ -31,6 +31,9 @@ def main():
             e.set_allgather(gather)
             if bcast:
                 e.set_broadcast(bcast)
+            for kv in filter(None, os.environ.get("CHECK_MULTI_OPTS", "").split(",")):   # e.g. schur_min_top=1,block=2
+                k, v = kv.split("=")
+                e.set_option(k, int(v))
         # with the broadcast only rank 0 hands the step over; the others receive it over NCCL
         got = e.reduce(s if (rank == 0 or not bcast) else None, final=f.endswith("step_final.bin"))
         n += 1
