@@ -38,15 +38,20 @@ namespace gcu {
 
 static thread_local std::string g_last_error;
 
+// Device buffers come from the stream-ordered memory pool of the device (release threshold raised to "never"
+// at create): growing a buffer is a pool operation ordered on the engine's stream, not a cudaFree (which
+// synchronises the device) plus a cudaMalloc (milliseconds per GB) - 2 s of a kat15-15 run before.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) GCU_CHECK(cudaFree(p));
+        if (p) GCU_CHECK(cudaFreeAsync(p, g_alloc_stream));
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 2 + 256;   // matrices grow from step to step: few, generous reallocations
-        GCU_CHECK(cudaMalloc(&p, want));
+        GCU_CHECK(cudaMallocAsync(&p, want, g_alloc_stream));
         cap = want;
     }
     template <class T> T* as() const { return static_cast<T*>(p); }
@@ -668,9 +673,12 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
     ctr.mc_attempts = 0;
     for (;;) {
         mc_k = k; ++mc_draw; ++ctr.mc_attempts;
+        double tq = wall_s();
         eliminate();
         exchange();
+        dbg_[5] += wall_s() - tq; tq = wall_s();
         echelon(out);
+        dbg_[6] += wall_s() - tq;
         acc_elim += t_elim_dev; acc_ech += t_ech_dev;
         if (mc_k && out->n_new + 32 > mc_k) {          // margin not met: more combinations, or exact
             k = mc_k * 2;
@@ -720,6 +728,10 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
             GCU_CHECK(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)cfg->device));
             GCU_CHECK(cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, (int)cfg->device));
             GCU_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+            cudaMemPool_t pool = nullptr;
+            GCU_CHECK(cudaDeviceGetDefaultMemPool(&pool, (int)cfg->device));
+            uint64_t keep = ~0ull;                       // freed blocks stay in the pool for the next step
+            GCU_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
             for (auto& ev : e->ev) GCU_CHECK(cudaEventCreate(&ev));
             e->ctr.sm_count = (uint32_t)e->prop.multiProcessorCount;
         } catch (...) { delete e; throw; }
@@ -737,12 +749,13 @@ void* gamba_cuda_host_alloc(size_t bytes) {
 void gamba_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int gamba_cuda_stage(gamba_cuda_engine* e, const gamba_cuda_step_in* in) {
-    return guarded([&] { GCU_CHECK(cudaSetDevice((int)e->cfg.device)); e->stage(in); });
+    return guarded([&] { GCU_CHECK(cudaSetDevice((int)e->cfg.device)); gcu::g_alloc_stream = e->stream; e->stage(in); });
 }
 
 int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out) {
     return guarded([&] {
         GCU_CHECK(cudaSetDevice((int)e->cfg.device));
+        gcu::g_alloc_stream = e->stream;
         const double t0 = gcu::wall_s();
         e->run_reduce(out);
         out->seconds_total = gcu::wall_s() - t0;
@@ -752,6 +765,7 @@ int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out) {
 int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_cuda_step_out* out) {
     return guarded([&] {
         GCU_CHECK(cudaSetDevice((int)e->cfg.device));
+        gcu::g_alloc_stream = e->stream;
         const double t0 = gcu::wall_s();
         e->stage(in);
         e->run_reduce(out);
