@@ -25,6 +25,7 @@
 #include "kernels_elim_block.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_schur.cuh"
+#include "kernels_schur_tc.cuh"
 #include "layout.cuh"
 
 namespace gcu {
@@ -77,6 +78,32 @@ static double wall_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// 2-D byte tensor [rows][cols] (cols contiguous) with a box of box_rows x box_cols and the 128-byte swizzle the
+// tcgen05 operand descriptors of kernels_schur_tc.cuh expect. cuTensorMapEncodeTiled is a driver entry point:
+// fetched through the runtime so that the library does not link libcuda.
+static CUtensorMap make_tmap_u8(void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        GCU_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<encode_fn>(fn);
+    }
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return m;
+}
+
 }  // namespace gcu
 
 struct gamba_cuda_engine {
@@ -95,6 +122,7 @@ struct gamba_cuda_engine {
     std::unordered_map<const void*, std::pair<uint64_t, uint32_t>> cache;   // host pointer -> (offset in d_pool, length)
     uint64_t cache_used = 0;
     int64_t opt_schur = 1;           // 1: D' = D + M B on the tensor cores when the limb planes fit, 0: sparse path
+    int64_t opt_schur_tc = 1;        // 1: tcgen05/TMA product kernel, 0: mma.sync version
     int64_t opt_block = 1;           // blocked sparse solve (kernels_elim_block.cuh): 0 never, 1 when the multipliers are dense, 2 always
     double last_density = 0;         // pivots hit per row / n_top of the previous step (predictor for this one)
     bool use_schur = false, use_block = false;   // decided per staged step (plan_step)
@@ -190,7 +218,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         const uint32_t world = std::max(1u, cfg.world_size);
         const uint32_t nloc = (n_bot + world - 1) / world;
         const uint32_t nl = f.small ? 2u : 4u;
-        const uint32_t sc_bm = f.small ? schur_bm<2>() : schur_bm<4>(), sc_bn = f.small ? schur_bn<2>() : schur_bn<4>();
+        const uint32_t sc_bm = 128, sc_bn = 128;     // the limb planes are padded to 128 rows (tile of either product kernel)
         const uint64_t kp = (n_top + SC_BK - 1) / SC_BK * SC_BK;
         const uint64_t mt_ = (nloc + sc_bm - 1) / sc_bm, nt_ = (L.n_nonpiv + sc_bn - 1) / sc_bn;
         use_schur = opt_schur && nloc && L.n_nonpiv && n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
@@ -454,8 +482,9 @@ void gamba_cuda_engine::eliminate() {
     const uint32_t nl = f.small ? 2u : 4u;
     const uint32_t sc_bm = f.small ? schur_bm<2>() : schur_bm<4>(), sc_bn = f.small ? schur_bn<2>() : schur_bn<4>();
     const uint32_t kp = (L.n_top + SC_BK - 1) / SC_BK * SC_BK;
-    const uint32_t m_tiles = (n_local + sc_bm - 1) / sc_bm, n_tiles = (L.n_nonpiv + sc_bn - 1) / sc_bn;
-    const uint64_t mx_plane = (uint64_t)m_tiles * sc_bm * kp, bt_plane = (uint64_t)n_tiles * sc_bn * kp;
+    const uint32_t mp = (n_local + 127u) / 128u * 128u, np = (L.n_nonpiv + 127u) / 128u * 128u;   // rows per limb plane
+    const uint32_t m_tiles = mp / sc_bm, n_tiles = np / sc_bn;
+    const uint64_t mx_plane = (uint64_t)mp * kp, bt_plane = (uint64_t)np * kp;
     const bool schur = use_schur && n_local;
     const bool block = schur && use_block;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
@@ -513,7 +542,24 @@ void gamba_cuda_engine::eliminate() {
         sa.row_begin = rank; sa.row_step = world;
         const uint32_t kc_max = f.small ? schur_kchunk<2>() : schur_kchunk<4>();
         sa.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, kc_max) : kc_max;
-        if (f.small) {
+        if (opt_schur_tc) {
+            // tcgen05 + TMA version (kernels_schur_tc.cuh): the limb planes as 2-D byte tensors [NL * rows][kp]
+            TcArgs ta{};
+            ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = np; ta.n_rows = n_local; ta.n_cols = L.n_nonpiv; ta.ld = L.ld_dprime;
+            ta.d = dloc; ta.row_nz = nzloc; ta.m_tiles = mp / TC_BM; ta.n_tiles = np / (f.small ? TcCfg<2>::BN : TcCfg<4>::BN);
+            ta.first_piv = sa.first_piv; ta.k_first = sa.k_first; ta.row_begin = rank; ta.row_step = world;
+            const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
+            ta.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
+            CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
+            CUtensorMap map_bt = make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, f.small ? TcCfg<2>::BN : TcCfg<4>::BN);
+            if (f.small) {
+                GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
+                schur_tc_kernel<2><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<2>(), stream>>>(map_mx, map_bt, ta);
+            } else {
+                GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
+                schur_tc_kernel<4><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<4>(), stream>>>(map_mx, map_bt, ta);
+            }
+        } else if (f.small) {
             GCU_CHECK(cudaFuncSetAttribute(schur_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem<2>()));
             schur_mma_kernel<2><<<m_tiles * n_tiles, schur_threads<2>(), schur_smem<2>(), stream>>>(sa);
         } else {
@@ -795,6 +841,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "coeff_cache") { e->opt_coeff_cache = value; e->cache.clear(); e->cache_used = 0; }
         else if (k == "schur") e->opt_schur = value;
         else if (k == "block") e->opt_block = value;
+        else if (k == "schur_tc") e->opt_schur_tc = value;
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;
         else if (k == "schur_kchunk") e->opt_schur_kchunk = value;

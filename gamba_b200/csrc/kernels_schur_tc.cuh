@@ -1,0 +1,233 @@
+// D' = D + M * B on the 5th-generation tensor cores: tcgen05.mma kind::i8 with the accumulators in tensor
+// memory, operands brought in by TMA. Same contract, operands and limb technique as schur_mma_kernel
+// (kernels_schur.cuh, the mma.sync version, kept as the comparator and fallback: option schur_tc=0);
+// the legacy warp-level IMMA path tops out at 570 int8 TMAC/s on a B200 (profiles/r01b_mma_microbench.txt),
+// a quarter of what tcgen05 issues.
+//
+// One CTA (192 threads) per 128 x BN tile of D' (BN = 128 for 2 limbs, 64 for 4):
+//   warp 0      TMA producer: per k-step of 128 bytes, NL boxes of Mx (128 rows x 128 B) and NL boxes of Bt
+//               (BN rows x 128 B) into a ring of shared-memory stages (SWIZZLE_128B), completion on full[stage]
+//   warp 1      allocates the 512 columns of tensor memory; one lane issues, per k-step, 4 (K = 32 each) x NL^2
+//               tcgen05.mma  acc[la+lb] += Mx_la * Bt_lb^T  (2*NL-1 accumulators of 128 lanes x BN s32 columns);
+//               tcgen05.commit releases the stage (empty[stage]) and, at the end of a k-chunk, signals acc_full
+//   warps 2-5   epilogue: tcgen05.ld the accumulators (warp w owns lanes 32*(w%4)..), recombine the limb weights,
+//               Barrett, read-modify-write the CTA's tile of D', then acc_empty lets the next k-chunk start.
+// s32 accumulators are exact for 2^31 / (NL * 255^2) k's: a k-chunk is 128 (NL=2) / 64 (NL=4) k-steps.
+#pragma once
+#include <cuda.h>
+
+#include "kernels_schur.cuh"
+
+namespace gcu {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 128;                       // bytes of k per stage and row: one 128-byte swizzle atom
+constexpr int TC_THREADS = 192;
+template <int NL> struct TcCfg;
+template <> struct TcCfg<2> { static constexpr int BN = 128, STAGES = 3, KCHUNK = 128; };
+template <> struct TcCfg<4> { static constexpr int BN = 64, STAGES = 2, KCHUNK = 64; };
+template <int NL> __host__ __device__ constexpr uint32_t tc_stage_bytes() { return (uint32_t)NL * (TC_BM + TcCfg<NL>::BN) * TC_BK; }
+template <int NL> __host__ __device__ constexpr size_t tc_smem_bytes() { return (size_t)TcCfg<NL>::STAGES * tc_stage_bytes<NL>() + 1024 /*alignment*/ + 256 /*barriers*/; }
+
+struct TcArgs {
+    Fp f;
+    uint32_t kp, mp, np;        // k extent (bytes per row of the planes), rows per limb plane of Mx / Bt
+    uint32_t n_rows, n_cols, ld;
+    uint32_t* d;
+    uint32_t* row_nz;
+    uint32_t m_tiles, n_tiles;
+    const uint32_t* first_piv;
+    uint32_t row_begin, row_step, k_first;
+    uint32_t kchunk;            // k-steps between two folds (<= TcCfg<NL>::KCHUNK)
+};
+
+// ---- PTX wrappers (sm_100a) -------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "TC_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra TC_DONE_%=;\n\t"
+        "bra TC_WAIT_%=;\n\t"
+        "TC_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {      // arrives on `bar` when all tcgen05.mma issued so far have completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {     // 32 lanes x 16 columns of 32 bits
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory operand descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row atoms 1024 bytes apart
+// (cute/arch/mma_sm100_desc.hpp: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | layout 2 << 61)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int NL>
+__global__ void __launch_bounds__(TC_THREADS, 1) schur_tc_kernel(const __grid_constant__ CUtensorMap map_mx,
+                                                                 const __grid_constant__ CUtensorMap map_bt, TcArgs a) {
+    using C = TcCfg<NL>;
+    constexpr int BN = C::BN, STAGES = C::STAGES, NA = 2 * NL - 1;
+    constexpr uint32_t STAGE_BYTES = tc_stage_bytes<NL>();
+    constexpr uint32_t A_LIMB = TC_BM * TC_BK, B_LIMB = BN * TC_BK;
+    // instruction descriptor (kind::i8): D = s32, A = B = u8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    extern __shared__ unsigned char tc_smem_raw[];
+    __shared__ uint32_t s_tmem, s_kmin;
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B atoms are 1024-byte aligned
+    const uint32_t bars = base + STAGES * STAGE_BYTES;               // full[STAGES], empty[STAGES], acc_full, acc_empty
+    auto full_bar = [&](uint32_t s) { return bars + 8 * s; };
+    auto empty_bar = [&](uint32_t s) { return bars + 8 * (STAGES + s); };
+    const uint32_t acc_full = bars + 8 * (2 * STAGES), acc_empty = bars + 8 * (2 * STAGES + 1);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t mt = blockIdx.x % a.m_tiles, nt = blockIdx.x / a.m_tiles;
+    const uint32_t row0 = mt * TC_BM, col0 = nt * BN;
+
+    if (tid == 0) {
+        for (uint32_t s = 0; s < (uint32_t)STAGES; ++s) { tc_mbar_init(full_bar(s), 1); tc_mbar_init(empty_bar(s), 1); }
+        tc_mbar_init(acc_full, 1); tc_mbar_init(acc_empty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_kmin = 0xffffffffu;
+    }
+    if (warp == 1) {                                                 // 512 columns of tensor memory for this CTA
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    // first pivot column any row of the tile has: everything left of it is zero in Mx
+    if (tid < (uint32_t)TC_BM) {
+        const uint32_t li = row0 + tid;
+        if (li < a.n_rows) atomicMin(&s_kmin, a.first_piv ? a.first_piv[a.row_begin + li * a.row_step] : a.k_first);
+    }
+    __syncthreads();
+    const uint32_t ks_end = (a.kp + TC_BK - 1) / TC_BK;
+    const uint32_t ks_begin = min(s_kmin / TC_BK, ks_end);
+    const uint32_t n_ks = ks_end - ks_begin;
+    const uint32_t n_chunks = n_ks ? (n_ks + a.kchunk - 1) / a.kchunk : 0;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (uint32_t i = 0; i < n_ks; ++i) {
+                const uint32_t s = i % STAGES, ph = (i / STAGES) & 1;
+                tc_mbar_wait(empty_bar(s), ph ^ 1);
+                tc_mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                const uint32_t dst = base + s * STAGE_BYTES;
+                const int32_t k0 = (int32_t)((ks_begin + i) * TC_BK);
+#pragma unroll
+                for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + l * A_LIMB, &map_mx, full_bar(s), k0, (int32_t)(l * a.mp + row0));
+#pragma unroll
+                for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_bt, full_bar(s), k0, (int32_t)(l * a.np + col0));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (uint32_t i = 0; i < n_ks; ++i) {
+                const uint32_t s = i % STAGES, ph = (i / STAGES) & 1;
+                const uint32_t in_chunk = i % a.kchunk, chunk = i / a.kchunk;
+                if (in_chunk == 0 && chunk > 0) { tc_mbar_wait(acc_empty, (chunk - 1) & 1); tc_fence_after(); }   // epilogue drained the accumulators
+                tc_mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + NL * A_LIMB;
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 32; ++kk)
+#pragma unroll
+                    for (int la = 0; la < NL; ++la)
+#pragma unroll
+                        for (int lb = 0; lb < NL; ++lb) {
+                            // the first product into an accumulator of a k-chunk overwrites it
+                            const uint32_t first = (in_chunk == 0 && kk == 0 && (la == 0 || lb == NL - 1)) ? 1u : 0u;
+                            tc_mma_i8(tmem + (uint32_t)(la + lb) * BN, tc_smem_desc(sa + la * A_LIMB + kk * 32),
+                                      tc_smem_desc(sb + lb * B_LIMB + kk * 32), IDESC, first ^ 1u);
+                        }
+                tc_commit(empty_bar(s));                             // the stage is free once these products have read it
+                if (in_chunk + 1 == a.kchunk || i + 1 == n_ks) tc_commit(acc_full);
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5, warp w owns the tensor-memory lanes 32 * (w % 4) .. + 31 =====
+        const uint32_t quarter = warp & 3u;
+        const uint32_t row = row0 + quarter * 32 + lane;
+        const bool row_ok = row < a.n_rows;
+        uint32_t* drow = a.d + (uint64_t)(row_ok ? row : 0) * a.ld;
+        uint32_t any = 0;
+        for (uint32_t chunk = 0; chunk < n_chunks; ++chunk) {
+            tc_mbar_wait(acc_full, chunk & 1);
+            tc_fence_after();
+            for (uint32_t c0 = 0; c0 < (uint32_t)BN; c0 += 16) {
+                uint32_t v[NA][16];
+#pragma unroll
+                for (int s = 0; s < NA; ++s) tc_ld16(tmem + ((quarter * 32u) << 16) + (uint32_t)s * BN + c0, v[s]);
+                tc_ld_wait();
+                const uint32_t col = col0 + c0;
+                if (row_ok && col < a.n_cols) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) {
+                        if (col + e >= a.n_cols) break;
+                        uint32_t* ptr = drow + col + e;
+                        uint4 cin = *reinterpret_cast<const uint4*>(ptr);       // ld is a multiple of 4: the vector stays inside the row
+                        uint32_t o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t ci = j == 0 ? cin.x : j == 1 ? cin.y : j == 2 ? cin.z : cin.w;
+                            uint64_t sum;
+                            if (NL == 2) {
+                                sum = (uint64_t)v[0][e + j] + ((uint64_t)v[1][e + j] << 8) + ((uint64_t)v[2][e + j] << 16) + ci;
+                                o[j] = fp_reduce64(sum, a.f);
+                            } else {
+                                const uint64_t lo = (uint64_t)v[0][e + j] + ((uint64_t)v[1][e + j] << 8) + ((uint64_t)v[2][e + j] << 16) + ((uint64_t)v[3][e + j] << 24);
+                                const uint64_t hi = (uint64_t)v[4 % NA][e + j] + ((uint64_t)v[5 % NA][e + j] << 8) + ((uint64_t)v[6 % NA][e + j] << 16);
+                                o[j] = fp_reduce64(lo + ci + ((uint64_t)fp_reduce64(hi, a.f) << 32), a.f);
+                            }
+                            if (col + e + j >= a.n_cols) o[j] = ci;              // padding columns of the pitch keep their content
+                        }
+                        *reinterpret_cast<uint4*>(ptr) = make_uint4(o[0], o[1], o[2], o[3]);
+                        if (chunk + 1 == n_chunks) any |= o[0] | o[1] | o[2] | o[3];
+                    }
+                }
+            }
+            tc_fence_before();
+            tc_mbar_arrive(acc_empty);
+        }
+        if (n_chunks == 0 && row_ok)                                  // nothing to add: the flag comes from D alone
+            for (uint32_t c = col0; c < min(col0 + (uint32_t)BN, a.n_cols); ++c) any |= drow[c];
+        if (row_ok && any) a.row_nz[row] = 1u;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace gcu
