@@ -123,8 +123,19 @@ struct gamba_cuda_engine {
     uint64_t cache_used = 0;
     int64_t opt_schur = 1;           // 1: D' = D + M B on the tensor cores when the limb planes fit, 0: sparse path
     int64_t opt_schur_tc = 1;        // 1: tcgen05/TMA product kernel, 0: mma.sync version
+    int64_t opt_panel = 1;           // 1 (when it is predicted to pay) / 2 (always): blocked triangular solve - per column tile, the earlier pivots' contribution is a
+                                     //    tcgen05 product and elim_kernel only walks the tile's own windows (needs schur_tc)
+    bool use_panel = false;
+    uint32_t PANEL_T = 2048;         // column tile of the panel mode: ~8 KB of accumulator, every row of a step resident at once
+    int64_t opt_panel_t = 0;         // 0 = chosen per step so that the panel products fill whole waves of CTAs
+    int64_t opt_panel_max_top = 100000;   // operands of K^2 / 2 bytes per limb: a cap besides the cost estimate in choose_layout
+    gcu::DevBuf d_at, d_at_off, d_cd;
+    std::vector<uint64_t> at_off;
+    uint64_t at_bytes = 0;
     int64_t opt_block = 1;           // blocked sparse solve (kernels_elim_block.cuh): 0 never, 1 when the multipliers are dense, 2 always
     double last_density = 0;         // pivots hit per row / n_top of the previous step (predictor for this one)
+    double last_a = 0, cur_a = 0;    // entries of A per pivot row (outside the diagonal blocks): previous step, staged step
+    bool have_history = false;
     bool use_schur = false, use_block = false;   // decided per staged step (plan_step)
     int64_t opt_schur_max_gb = 64;   // budget for the Mx and Bt limb planes
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
@@ -206,7 +217,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     uint32_t ctas = 4;
     elim_warps = ELIM_CTA_WARPS;
     if (opt_ctas_per_sm > 0) { ctas = (uint32_t)opt_ctas_per_sm; elim_warps = ctas > 8 ? 4 : ELIM_CTA_WARPS; }
-    if (opt_elim_warps == 4 || opt_elim_warps == 8) elim_warps = (int)opt_elim_warps;
+    if (opt_elim_warps == 2 || opt_elim_warps == 4 || opt_elim_warps == 8) elim_warps = (int)opt_elim_warps;
     ctas = std::min<uint32_t>(ctas, 64u / elim_warps);
     const size_t per_cta = std::min<size_t>(((size_t)smem_per_sm / ctas) - 1024 - 64, (size_t)max_smem_optin - 64);
     const uint32_t words_per_col = f.small ? 1u : 2u;   // kernels_elim.cuh: Acc<SMALLP>::WORDS
@@ -228,8 +239,42 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // row-per-CTA kernel, which only touches the pivot rows a row needs, is faster (tools/blk_variants.sh).
         use_block = use_schur && !opt_mc && (opt_block >= 2 || (opt_block == 1 && n_top >= 32768 && last_density >= 0.5));
         if (use_block) tmax = BLK_TMAX;
+        // Panel mode: tiles of PANEL_T columns; operands of panel t: [nl][PANEL_T][t * PANEL_T] bytes, K^2/2 * nl in total
+        use_panel = false;
+        if (opt_panel_t > 0) PANEL_T = (uint32_t)opt_panel_t;
+        else {      // m_tiles x (T / BN) output tiles per panel product: pick T in [1024, 3072] that fills whole waves of SMs
+            const uint32_t bn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN, sms = (uint32_t)prop.multiProcessorCount;
+            double best = -1;
+            for (uint32_t T = 1024; T <= 3072; T += 128) {
+                const uint64_t tiles = mt_ * (T / bn);
+                const double eff = (double)tiles / (double)((tiles + sms - 1) / sms * sms);
+                if (eff >= best - 1e-9) { best = eff; PANEL_T = T; }
+            }
+        }
+        // Panel or sparse? The products cost n_bot K^2 / 2 dense multiply-adds whatever the matrix holds, the sparse kernel
+        // only touches the pivot rows a row hits: predicted from the previous step (F4 steps change slowly) with measured
+        // rates - row-per-CTA kernel 3e11 entries/s, products 1.2e15 int8 multiply-adds/s, ~4 us per window of the walk,
+        // ~60 us per panel (cyclic9: panels win 1.5-3x; kat12: 60 % dense multipliers but 86 entries per row of A, sparse wins 3x)
+        bool panel_pays = opt_panel >= 2;
+        if (opt_panel == 1 && have_history) {
+            const double est_sparse = (double)nloc * last_density * n_top * last_a * 0.5 / 3e11;
+            const double est_panel = (double)(mt_ * sc_bm) * n_top * (double)n_top * 0.5 * nl * nl / 1.2e15 + n_top / 32.0 * 4e-6 +
+                                     (double)n_top / PANEL_T * 6e-5;
+            panel_pays = est_panel < est_sparse;
+        }
+        if (use_schur && opt_schur_tc && panel_pays && !opt_mc && opt_block < 2 && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
+            const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T;
+            const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2);
+            if (at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kp <= (double)opt_schur_max_gb * 1e9) {
+                use_panel = true; use_block = false; tmax = PANEL_T;
+                // little work per window, and every row of the step should be resident at once (the walk is a chain of
+                // dependent steps): 2 warps per row when more than 9 rows per SM are wanted (48-56 registers per thread)
+                elim_warps = 4;     // 2 warps per row (every row resident) measured no faster: tools/tc_check.sh
+                if (opt_elim_warps == 2 || opt_elim_warps == 4 || opt_elim_warps == 8) elim_warps = (int)opt_elim_warps;
+            }
+        }
     }
-    if (opt_tile_cols > 0) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
+    if (opt_tile_cols > 0 && !use_panel) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
     auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
     // pivot tiles of equal width; the non-pivot range is cut with the same width
     uint32_t ntp = n_top ? (n_top + tmax - 1) / tmax : 0;
@@ -239,6 +284,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         t = std::max(t, up((L.n_nonpiv + ntn - 1) / ntn));
     }
     t = std::min(t, tmax);
+    if (use_panel) t = PANEL_T;          // the products address the operands by tile: fixed width, multiple of 128
     L.tile_cols = t;
     L.n_tiles_piv = (n_top + t - 1) / t;
     L.n_tiles_nonpiv = (L.n_nonpiv + t - 1) / t;
@@ -412,8 +458,17 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
             ctr.kernel_launches += 1;
         }
     }
+    // nnz of A (for the next step's choice between the sparse kernels and the panel products)
+    h_misc.ensure(64);
+    d_counts.ensure(256);
+    if (n_rows && L.n_top) {
+        prep_nnz_a_kernel<<<1, 32, 0, stream>>>(pa, reinterpret_cast<unsigned long long*>(d_counts.as<char>() + 128));
+        GCU_CHECK(cudaGetLastError());
+        GCU_CHECK(cudaMemcpyAsync(h_misc.as<char>() + 48, d_counts.as<char>() + 128, 8, cudaMemcpyDeviceToHost, stream));
+    }
     GCU_CHECK(cudaEventRecord(ev[1], stream));
     GCU_CHECK(cudaStreamSynchronize(stream));
+    if (n_rows && L.n_top) { cur_a = (double)*reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 48) / L.n_top; }
     float ms = 0;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
     t_prep_dev = ms * 1e-3;
@@ -435,7 +490,8 @@ void gamba_cuda_engine::eliminate() {
     const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
     const size_t smem = (acc_words + (size_t)elim_warps * ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
     const int elim_threads = elim_warps * 32;
-    auto kern = elim_warps == 4 ? (f.small ? elim_kernel<true, 4> : elim_kernel<false, 4>)
+    auto kern = elim_warps == 2 ? (f.small ? elim_kernel<true, 2> : elim_kernel<false, 2>)
+              : elim_warps == 4 ? (f.small ? elim_kernel<true, 4> : elim_kernel<false, 4>)
                                 : (f.small ? elim_kernel<true, 8> : elim_kernel<false, 8>);
     GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -447,7 +503,7 @@ void gamba_cuda_engine::eliminate() {
 
     d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.ld_dprime, 1) * sizeof(uint32_t));
     d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
-    if (!(use_schur && use_block)) {     // the blocked kernel keeps its multipliers in d_mt instead
+    if (!(use_schur && (use_block || use_panel))) {     // the blocked kernel keeps its multipliers in d_mt, the panel mode needs no lists
         d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
         d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
     }
@@ -477,6 +533,7 @@ void gamba_cuda_engine::eliminate() {
     ea.mc_seed = cfg.seed * 0x9e3779b97f4a7c15ull + mc_draw;
     if (mc_k) { GCU_CHECK(cudaMemcpyAsync(&ea.mc_first, d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); GCU_CHECK(cudaStreamSynchronize(stream)); }
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
+    ea.t_lo = 0; ea.t_hi = L.n_tiles;
 
     // Schur mode: the B half of the elimination is a dense product on the tensor cores (kernels_schur.cuh)
     const uint32_t nl = f.small ? 2u : 4u;
@@ -487,6 +544,7 @@ void gamba_cuda_engine::eliminate() {
     const uint64_t mx_plane = (uint64_t)mp * kp, bt_plane = (uint64_t)np * kp;
     const bool schur = use_schur && n_local;
     const bool block = schur && use_block;
+    const bool panel = schur && use_panel;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (schur) {
         d_mx.ensure(nl * mx_plane);
@@ -498,6 +556,16 @@ void gamba_cuda_engine::eliminate() {
             BtArgs ba{};
             ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
             ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
+            if (panel) {     // operands of the panel products: tile t takes [nl][T][t * T] bytes
+                at_off.assign(L.n_tiles_piv + 1, 0);
+                for (uint32_t t = 1; t <= L.n_tiles_piv; ++t) at_off[t] = at_off[t - 1] + (t > 1 ? (uint64_t)nl * PANEL_T * (uint64_t)(t - 1) * PANEL_T : 0);
+                at_bytes = at_off[L.n_tiles_piv];
+                d_at.ensure(std::max<uint64_t>(at_bytes, 16));
+                d_at_off.ensure(at_off.size() * sizeof(uint64_t));
+                GCU_CHECK(cudaMemsetAsync(d_at.p, 0, std::max<uint64_t>(at_bytes, 16), stream));
+                GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+                ba.at = d_at.as<uint8_t>(); ba.at_off = d_at_off.as<uint64_t>();
+            }
             schur_bt_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(ba);
             GCU_CHECK(cudaGetLastError());
             ctr.kernel_launches += 1;
@@ -505,7 +573,47 @@ void gamba_cuda_engine::eliminate() {
         }
     }
     GCU_CHECK(cudaEventRecord(ev[6], stream));
-    if (block) {
+    if (panel) {
+        // Blocked triangular solve: per pivot tile t, what the pivots of the earlier tiles add to the rows is a tcgen05
+        // product cd = M[:, < t T] * A[< t T, tile t]; elim_kernel then only walks the windows of tile t.
+        const uint32_t ntp = L.n_tiles_piv, T = PANEL_T;
+        const uint32_t bn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN;
+        d_cd.ensure((uint64_t)mp * T * sizeof(uint32_t));
+        d_mt.ensure((uint64_t)(L.n_tiles + 2) * sizeof(uint32_t));              // one row-queue counter per launch
+        GCU_CHECK(cudaMemsetAsync(d_mt.p, 0, (uint64_t)(L.n_tiles + 2) * sizeof(uint32_t), stream));
+        const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
+        ea.panel = 1; ea.cd_ld = T;
+        for (uint32_t t = 0; t <= ntp; ++t) {
+            if (t > 0 && t < ntp) {
+                GCU_CHECK(cudaMemsetAsync(d_cd.p, 0, (uint64_t)n_local * T * sizeof(uint32_t), stream));
+                TcArgs ta{};
+                const uint32_t tw = lay_tile_width(L, t);
+                ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = T; ta.n_rows = n_local; ta.n_cols = tw; ta.ld = T;
+                ta.d = d_cd.as<uint32_t>(); ta.row_nz = nullptr; ta.m_tiles = mp / TC_BM; ta.n_tiles = (tw + bn - 1) / bn;
+                ta.first_piv = d_first.as<uint32_t>(); ta.k_first = 0; ta.row_begin = rank; ta.row_step = world;
+                const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
+                ta.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
+                ta.k_end = t * T;
+                const CUtensorMap map_at = make_tmap_u8(d_at.as<uint8_t>() + at_off[t], (uint64_t)t * T, (uint64_t)nl * T, TC_BK, bn);
+                if (f.small) {
+                    GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
+                    schur_tc_kernel<2><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<2>(), stream>>>(map_mx, map_at, ta);
+                } else {
+                    GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
+                    schur_tc_kernel<4><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<4>(), stream>>>(map_mx, map_at, ta);
+                }
+                GCU_CHECK(cudaGetLastError());
+                ctr.kernel_launches += 1;
+            }
+            // t < ntp: the windows of pivot tile t; t == ntp: the non-pivot tiles (D scattered into D')
+            ea.t_lo = t; ea.t_hi = t < ntp ? t + 1 : L.n_tiles;
+            ea.cd = (t > 0 && t < ntp) ? d_cd.as<uint32_t>() : nullptr;
+            ea.queue = d_mt.as<uint32_t>() + t;
+            kern<<<elim_grid, elim_threads, smem, stream>>>(ea);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 1;
+        }
+    } else if (block) {
         // R rows per CTA, 2 CTAs per SM (kernels_elim_block.cuh); D is scattered into the zeroed D' block
         const uint32_t R = f.small ? BlkRows<true>::R : BlkRows<false>::R;
         const size_t bsmem = f.small ? blk_smem_bytes<true>(L.n_windows) : blk_smem_bytes<false>(L.n_windows);
@@ -550,6 +658,7 @@ void gamba_cuda_engine::eliminate() {
             ta.first_piv = sa.first_piv; ta.k_first = sa.k_first; ta.row_begin = rank; ta.row_step = world;
             const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
             ta.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
+            ta.k_end = kp;
             CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
             CUtensorMap map_bt = make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, f.small ? TcCfg<2>::BN : TcCfg<4>::BN);
             if (f.small) {
@@ -683,7 +792,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
     ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
     ctr.fma_top = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[2];
-    if (n_local && L.n_top && !mc_k) last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top);
+    if (n_local && L.n_top && !mc_k) { last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top); last_a = cur_a; have_history = true; }
     ctr.steps += 1;
 
     if ((flags & GAMBA_CUDA_STEP_FINAL) && npiv != L.n_bot)
@@ -842,6 +951,9 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "schur") e->opt_schur = value;
         else if (k == "block") e->opt_block = value;
         else if (k == "schur_tc") e->opt_schur_tc = value;
+        else if (k == "panel") e->opt_panel = value;
+        else if (k == "panel_t") { if (value && (value < 128 || value % 128 || value > 8192)) throw std::runtime_error("panel_t must be a multiple of 128 in [128, 8192]"); e->opt_panel_t = value; }
+        else if (k == "panel_max_top") e->opt_panel_max_top = value;
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;
         else if (k == "schur_kchunk") e->opt_schur_kchunk = value;

@@ -80,6 +80,12 @@ struct ElimArgs {
     uint8_t* mx;                 // NULL = eliminate the non-pivot tiles here (sparse path)
     uint64_t mx_plane;
     uint32_t mx_kp, mx_nl;
+    // Panel mode (kernels_schur_tc.cuh as a blocked triangular solve): one launch walks the windows of the column
+    // tiles [t_lo, t_hi) only; what the pivots of EARLIER tiles add to tile t_lo was computed on the tensor cores,
+    // cd[local row][tile-relative column] = sum_k M[row][k] A[k][col], so there is no deferred pass and no list
+    uint32_t t_lo, t_hi;         // 0, n_tiles outside panel mode
+    const uint32_t* cd;          // NULL outside panel mode (and for the first pivot tile)
+    uint32_t cd_ld, panel;
 };
 
 // multiplier of row r in combination q: uniform in [1, p) (splitmix64 finaliser)
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
     const uint64_t p2 = a.f.p2;
     uint32_t* lk = a.list_k + (uint64_t)blockIdx.x * L.n_top;
     uint32_t* lm = a.list_m + (uint64_t)blockIdx.x * L.n_top;
-    unsigned long long fma = 0, npiv = 0, fma_top = 0;
+    unsigned long long fma = 0, npiv = 0, fma_top = 0, fma_top_pend = 0;
 
     for (;;) {
         __syncthreads();
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
         uint32_t nlist = 0;
         bool nz = false;
 
-        for (uint32_t t = t_first; t < L.n_tiles; ++t) {
+        for (uint32_t t = max(t_first, a.t_lo); t < a.t_hi; ++t) {
             const uint32_t t0 = lay_tile_start(L, t), tw = lay_tile_width(L, t);
             const uint32_t* seg_s = a.seg + (uint64_t)t * nr;
             const uint32_t* seg_e = seg_s + 1;          // tile-major table: a segment ends where the next row's starts
@@ -257,7 +263,14 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
             for (uint32_t i = tid; i < acc_words; i += ELIM_CTA_THREADS) acc[i] = 0;
             __syncthreads();
             uint32_t absorbed = 1;   // rows added into this tile since the last normalisation
-            if (a.mc_rows == 0) {   // the row itself
+            if (a.cd && t < L.n_tiles_piv) {   // panel mode: the earlier pivots' contribution, then the row's own entries on top
+                const uint32_t* cdr = a.cd + (uint64_t)li * a.cd_ld;
+                for (uint32_t i = tid; i < tw; i += ELIM_CTA_THREADS) Acc<SMALLP>::set(acc, i, __ldcg(cdr + i));
+                __syncthreads();
+                const uint32_t s = seg_s[grow], e = seg_e[grow];
+                for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::add(acc_sa, en.x, en.y); }
+                absorbed = 2;
+            } else if (a.mc_rows == 0) {   // the row itself
                 const uint32_t s = seg_s[grow], e = seg_e[grow];
                 for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x, en.y); }
             } else {                // Monte-Carlo: combination number r of all the rows to reduce
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
             __syncthreads();
             // deferred pass over the pivots found in earlier tiles
             // (batches of 32 pivots are dealt to the warps; they commute, no barrier between them)
-            const uint32_t ndefer = (a.mx && t >= L.n_tiles_piv) ? 0u : nlist;     // Schur mode: B half on the tensor cores
+            const uint32_t ndefer = ((a.mx && t >= L.n_tiles_piv) || a.panel) ? 0u : nlist;     // Schur mode: B half on the tensor cores
             for (uint32_t base0 = 0; base0 < ndefer; base0 += 32 * ELIM_CTA_WARPS) {
                 if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP, ELIM_CTA_THREADS>(acc, tw, a); absorbed = 1; }
                 absorbed += 32 * ELIM_CTA_WARPS;
@@ -288,29 +301,59 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
             if (t < L.n_tiles_piv) {
                 const uint32_t nwin = (tw + WINDOW - 1) / WINDOW;
                 uint32_t g = (t == t_first ? (first - t0) / WINDOW : 0);
-                // segment pointers of the window's 32 pivot rows, fetched one window ahead
+                // segment pointers of the window's 32 pivot rows, fetched one window ahead; so are the row flags of the
+                // window's inverse diagonal block and this lane's column of its first 4 flagged rows (the walk is a chain
+                // of dependent steps: every global load on it costs ~1 us per window)
                 uint32_t ps = 0, pe = 0;
                 if (g < nwin && t0 + g * WINDOW + lane < L.n_top) { ps = seg_s[t0 + g * WINDOW + lane]; pe = seg_e[t0 + g * WINDOW + lane]; }
+                uint32_t dzA = 0, dzB = 0, pvA0 = 0, pvA1 = 0, pvA2 = 0, pvA3 = 0;
+                auto fetch_diag = [&](uint32_t win, uint32_t dz, uint32_t& v0, uint32_t& v1, uint32_t& v2, uint32_t& v3) {
+                    const uint32_t* dg = a.diag + (uint64_t)win * WINDOW * WINDOW + lane;
+                    uint32_t rest = dz;
+                    v0 = v1 = v2 = v3 = 0;
+                    if (rest) { v0 = __ldg(dg + (__ffs(rest) - 1) * WINDOW); rest &= rest - 1; }
+                    if (rest) { v1 = __ldg(dg + (__ffs(rest) - 1) * WINDOW); rest &= rest - 1; }
+                    if (rest) { v2 = __ldg(dg + (__ffs(rest) - 1) * WINDOW); rest &= rest - 1; }
+                    if (rest) { v3 = __ldg(dg + (__ffs(rest) - 1) * WINDOW); }
+                };
+                if (g < nwin) {
+                    const uint32_t win = (t0 + g * WINDOW) / WINDOW;
+                    dzA = a.dnz[win];
+                    if (g + 1 < nwin) dzB = a.dnz[win + 1];
+                    fetch_diag(win, dzA, pvA0, pvA1, pvA2, pvA3);
+                }
                 for (; g < nwin; ++g) {
                     // every warp derives the window's multipliers itself (identical results, no broadcast)
                     const uint32_t k0 = t0 + g * WINDOW;
                     const uint32_t c = g * WINDOW + lane;
                     const uint32_t s = ps, e = pe;
                     if (g + 1 < nwin && k0 + WINDOW + lane < L.n_top) { ps = seg_s[k0 + WINDOW + lane]; pe = seg_e[k0 + WINDOW + lane]; }
+                    const uint32_t dz = dzA, pv0 = pvA0, pv1 = pvA1, pv2 = pvA2, pv3 = pvA3;
+                    dzA = dzB;
+                    if (g + 1 < nwin) fetch_diag(k0 / WINDOW + 1, dzA, pvA0, pvA1, pvA2, pvA3);
+                    dzB = g + 2 < nwin ? a.dnz[k0 / WINDOW + 2] : 0u;
+                    fma_top += fma_top_pend; fma_top_pend = 0;
                     const uint32_t av = c < tw ? Acc<SMALLP>::get(acc, c, a) : 0u;
                     const uint32_t nza = __ballot_sync(0xffffffffu, av != 0);
                     if (nza == 0) continue;           // CTA-uniform: all warps read the same lanes
                     uint32_t x = av;
-                    uint32_t need = nza & a.dnz[k0 / WINDOW];
+                    const uint32_t need = nza & dz;
                     if (need) {   // x = a * (I + M): add a_i * M[i][lane] for the flagged rows i
                         const uint32_t* dg = a.diag + (uint64_t)(k0 / WINDOW) * WINDOW * WINDOW + lane;
                         uint64_t xa = av;
-                        while (need) {
-                            const int i0 = __ffs(need) - 1; need &= need - 1;
-                            const int i1 = need ? __ffs(need) - 1 : -1; if (need) need &= need - 1;
+                        uint32_t rest = dz;
+                        int i;
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv0, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv1, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv2, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv3, p2); }
+                        rest &= need;
+                        while (rest) {                // more than 4 flagged rows: the others on demand (p < 2^16: 32 products fit 64 bits)
+                            const int i0 = __ffs(rest) - 1; rest &= rest - 1;
+                            const int i1 = rest ? __ffs(rest) - 1 : -1; if (rest) rest &= rest - 1;
                             const uint32_t m0 = __ldg(dg + i0 * WINDOW);
                             const uint32_t m1 = i1 >= 0 ? __ldg(dg + i1 * WINDOW) : 0u;
-                            xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);     // p < 2^16: 32 products fit 64 bits
+                            xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);
                             if (i1 >= 0) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i1), m1, p2);
                         }
                         x = fp_reduce64(xa, a.f);
@@ -322,12 +365,12 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
                         m = p - x;
                         if (warp == 0) {
                             const uint32_t i = nlist + __popc(nzm & lt);
-                            lk[i] = k0 + lane; lm[i] = m;
+                            if (!a.panel) { lk[i] = k0 + lane; lm[i] = m; }
                             if (a.mx) {
                                 uint8_t* mp = a.mx + (uint64_t)li * a.mx_kp + k0 + lane;
                                 for (uint32_t l = 0; l < a.mx_nl; ++l) mp[l * a.mx_plane] = (uint8_t)(m >> (8 * l));
                             }
-                            fma_top += a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];
+                            fma_top_pend = a.row_ptr[k0 + lane + 1] - a.row_ptr[k0 + lane];   // consumed one window later: off the chain
                         }
                     }
                     nlist += __popc(nzm);
@@ -356,6 +399,7 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
     for (int o = 16; o; o >>= 1) fma += __shfl_xor_sync(0xffffffffu, fma, o);
     if (lane == 0 && fma) atomicAdd(a.stats + 1, fma);
     if (npiv) atomicAdd(a.stats + 0, npiv);
+    fma_top += fma_top_pend;
     if (warp == 0 && fma_top) atomicAdd(a.stats + 2, fma_top);
 }
 

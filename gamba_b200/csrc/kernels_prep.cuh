@@ -101,6 +101,16 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
         if (cur[b] & 1u) a.ent[cur[b]] = make_uint2(a.L.tile_cols | jbits, 0u);
 }
 
+// Number of (padded) entries of the pivot rows inside the pivot tiles = nnz of A without the diagonal blocks:
+// per tile the pivot rows' entries are the contiguous range [seg[t*nr], seg[t*nr + n_top]). One warp.
+__global__ void prep_nnz_a_kernel(PrepArgs a, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (uint32_t t = threadIdx.x; t < a.L.n_tiles_piv; t += 32)
+        s += a.seg[(uint64_t)t * a.L.n_rows + a.L.n_top] - a.seg[(uint64_t)t * a.L.n_rows];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = s;
+}
+
 // One warp per window: replace the strictly-upper block N (A_ww = I + N, diagonal implicit) by the
 // strictly-upper part M of (I + N)^-1 = I + M, lane = column:  M[i] = -N[i] - sum_{j>i} N[i][j] * M[j].
 __global__ void __launch_bounds__(256) prep_diag_inverse_kernel(PrepArgs a) {

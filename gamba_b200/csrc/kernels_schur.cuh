@@ -53,6 +53,10 @@ struct BtArgs {
     uint8_t* bt;                // [nl][np][kp]
     uint64_t bt_plane;
     uint32_t kp, nl;
+    // panel mode: the part of A right of a pivot row's own tile goes to per-tile operands as well:
+    // at + at_off[t] is [nl][tile_cols][kp_t] with kp_t = t * tile_cols (only pivots of earlier tiles reach tile t)
+    uint8_t* at;                // NULL: B only
+    const uint64_t* at_off;     // [n_tiles_piv] byte offsets
 };
 
 // One warp per pivot row k: its entries in the non-pivot tiles become column k of Bt. Consecutive
@@ -63,6 +67,19 @@ __global__ void __launch_bounds__(256) schur_bt_kernel(BtArgs a) {
     const uint32_t k = blockIdx.x * 8 + warp;
     if (k >= L.n_top) return;
     const uint32_t nr = L.n_rows;
+    if (a.at) {
+        for (uint32_t t = k / L.tile_cols + 1; t < L.n_tiles_piv; ++t) {
+            const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
+            const uint64_t kpt = (uint64_t)t * L.tile_cols, plane = kpt * L.tile_cols;
+            uint8_t* base = a.at + a.at_off[t] + k;
+            for (uint32_t i = s + lane; i < e; i += 32) {
+                const uint2 en = __ldg(a.ent + i);
+                if (en.y == 0) continue;                   // padding
+                uint8_t* dst = base + (uint64_t)(en.x & 0xffffu) * kpt;
+                for (uint32_t l = 0; l < a.nl; ++l) dst[l * plane] = (uint8_t)(en.y >> (8 * l));
+            }
+        }
+    }
     for (uint32_t t = L.n_tiles_piv; t < L.n_tiles; ++t) {
         const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
         const uint32_t c0 = (t - L.n_tiles_piv) * L.tile_cols;

@@ -39,6 +39,7 @@ struct TcArgs {
     const uint32_t* first_piv;
     uint32_t row_begin, row_step, k_first;
     uint32_t kchunk;            // k-steps between two folds (<= TcCfg<NL>::KCHUNK)
+    uint32_t k_end;             // contraction depth in bytes (multiple of 16); kp for the Schur product, t * tile_cols for panel t
 };
 
 // ---- PTX wrappers (sm_100a) -------------------------------------------------------------------------------
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) schur_tc_kernel(const __grid_co
         if (li < a.n_rows) atomicMin(&s_kmin, a.first_piv ? a.first_piv[a.row_begin + li * a.row_step] : a.k_first);
     }
     __syncthreads();
-    const uint32_t ks_end = (a.kp + TC_BK - 1) / TC_BK;
+    const uint32_t ks_end = (a.k_end + TC_BK - 1) / TC_BK;
     const uint32_t ks_begin = min(s_kmin / TC_BK, ks_end);
     const uint32_t n_ks = ks_end - ks_begin;
     const uint32_t n_chunks = n_ks ? (n_ks + a.kchunk - 1) / a.kchunk : 0;
@@ -221,9 +222,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) schur_tc_kernel(const __grid_co
             tc_fence_before();
             tc_mbar_arrive(acc_empty);
         }
-        if (n_chunks == 0 && row_ok)                                  // nothing to add: the flag comes from D alone
+        if (n_chunks == 0 && row_ok && a.row_nz)                                  // nothing to add: the flag comes from D alone
             for (uint32_t c = col0; c < min(col0 + (uint32_t)BN, a.n_cols); ++c) any |= drow[c];
-        if (row_ok && any) a.row_nz[row] = 1u;
+        if (row_ok && any && a.row_nz) a.row_nz[row] = 1u;
     }
     tc_fence_before();
     __syncthreads();

@@ -349,3 +349,47 @@ def test_schur_with_small_tiles(step_dirs):
     eng = schur_engine(32003, tile_cols=256)
     assert check_dir(step_dirs("cyclic7-15"), eng) > 0
     eng.close()
+
+
+# ---- panel mode: blocked triangular solve, earlier pivots' contribution on the tensor cores ---------------
+
+def panel_engine(p, panel_t=128, **opts):
+    from gamba_b200 import LinalgEngine
+    eng = LinalgEngine(p)
+    eng.set_option("schur_min_top", 1)
+    eng.set_option("panel", 2)             # default 1: only where the cost estimate from the previous step says it pays
+    eng.set_option("panel_t", panel_t)     # default: 1024-3072, the test steps would be a single panel
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    return eng
+
+
+@pytest.mark.parametrize("p", [251, 32003, 65521, 2147483647])
+def test_panel_mode_synthetic(built, p):
+    from oracle import oracle
+    eng = panel_engine(p)
+    for (nr, nc, dens, seed) in [(900, 1300, 0.03, 8), (1500, 1900, 0.02, 3), (333, 777, 0.05, 9)]:
+        s = synthetic_step(nr, nc, dens, p, seed=seed, top_frac=0.85, share=7)
+        want, fma_top, _ = oracle.reduce(s)
+        assert eng.reduce(s).same_as(want), (p, nr, nc)
+        c = eng.counters()
+        assert c["fma_top"] == fma_top and c["n_tiles"] >= 3
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["cyclic7-15", "cyclic7-31", "kat9-16", "eco10-31", "cyclic8-15", "kat10-15"])
+def test_panel_mode_every_step_matches_oracle(step_dirs, name):
+    d = step_dirs(name) if name not in ("cyclic8-15", "kat10-15") else step_dirs(name, ("--dump-min-nnz", "100000"))
+    s0 = load_step(sorted(glob.glob(os.path.join(d, "step_*.bin")))[0])
+    eng = panel_engine(s0.p, panel_t=256 if name in ("cyclic8-15", "kat10-15") else 128)
+    assert check_dir(d, eng) > 0
+    eng.close()
+
+
+def test_panel_mode_accumulator_folds(built):
+    from oracle import oracle
+    s = synthetic_step(1500, 1900, 0.02, 32003, seed=23, top_frac=0.9, share=9)
+    want, _, _ = oracle.reduce(s)
+    eng = panel_engine(32003, schur_kchunk=1)
+    assert eng.reduce(s).same_as(want)
+    eng.close()

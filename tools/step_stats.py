@@ -24,6 +24,7 @@ def main():
             for k, v in opts:
                 eng.set_option(k, int(v))
         eng.stage(s)
+        eng.reduce_staged(); eng.stage(s)      # kernels are chosen from the previous step's measurements
         best = None
         for _ in range(2):
             r = eng.reduce_staged()
