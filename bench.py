@@ -288,7 +288,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             for i, e in enumerate(engines):
-                e.reduce_staged()
+                e.reduce_staged(copy=False)     # the result stays in the engine-owned host buffers the C ABI hands out
                 elim_s[i] += e.last["seconds_eliminate"]; ech_s[i] += e.last["seconds_echelon"]
                 dev_s += e.last["seconds_eliminate"] + e.last["seconds_echelon"]
                 c_ = e.counters()
@@ -309,7 +309,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     h2d = d2h = 0
     for _ in range(args.steps):
         for e, s in zip(engines, steps):
-            e.reduce(mine(s))
+            e.reduce(mine(s), copy=False)
             h2d += e.last["h2d_bytes"]; d2h += e.last["d2h_bytes"]
     sync()
     t_e2e = time.perf_counter() - t0
@@ -348,17 +348,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": n_launch,
             "clocks": clocks,
-            "roofline": {"kernel": "elimination stage C|D by A|B: elim_kernel / elim_block_kernel (sparse solve for the multipliers) + "
-                                   "schur_bt_kernel + schur_mma_kernel (D' = D + M B on the tensor cores)",
+            "roofline": {"kernel": "elimination stage C|D by A|B: elim_kernel (walk of the pivot windows) + schur_tc_kernel per column "
+                                   "tile (earlier pivots' contribution, tcgen05) for the multipliers M; schur_bt_kernel + schur_tc_kernel "
+                                   "for D' = D + M B",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic() if args.system == "cyclic9-15" else None,
                          "traffic_source": "ncu dram__bytes_read+write of the stage's kernels per matrix, profiles/r01c_elim_traffic.json",
                          "peak_source": peak_src,
                          "parts": {"sparse_solve_ms_per_step": 1e3 * sparse_s / args.steps, "schur_ms_per_step": 1e3 * schur_s / args.steps,
-                                   "schur_tensor": {"achieved": schur_imma / max(schur_s, 1e-12) / 1e12, "peak": 570.5, "unit": "int8 TMAC/s",
-                                                    "frac": schur_imma / max(schur_s, 1e-12) / 1e12 / 570.5,
-                                                    "peak_source": "mma.sync m16n8k32 u8 microbenchmark on this GPU, profiles/r01b_mma_microbench.txt "
-                                                                   "(time includes zeroing and filling the limb planes)"}},
+                                   "schur_tensor": {"achieved": schur_imma / max(schur_s, 1e-12) / 1e12, "peak": 2250.0, "unit": "int8 TMAC/s",
+                                                    "frac": schur_imma / max(schur_s, 1e-12) / 1e12 / 2250.0,
+                                                    "peak_source": "nominal dense int8 of tcgen05 on B200 (4.5 POP/s = 2x the bf16 rate; MEASURED_PEAKS.json "
+                                                                   "has cuBLAS bf16 at 1648 TFLOP/s = 1648 int8-equivalent TMAC/s); the time includes "
+                                                                   "zeroing the multiplier planes"}},
                          "bytes_alg_per_launch": alg, "avg_launch_ms": dur * 1e3,
                          "share_of_device_time": sum(elim_s) / max(dev_s, 1e-12),
                          "fma_top_per_pass": int(sum(fma_top))},

@@ -253,13 +253,14 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         }
         // Panel or sparse? The products cost n_bot K^2 / 2 dense multiply-adds whatever the matrix holds, the sparse kernel
         // only touches the pivot rows a row hits: predicted from the previous step (F4 steps change slowly) with measured
-        // rates - row-per-CTA kernel 3e11 entries/s, products 1.2e15 int8 multiply-adds/s, ~4 us per window of the walk,
-        // ~60 us per panel (cyclic9: panels win 1.5-3x; kat12: 60 % dense multipliers but 86 entries per row of A, sparse wins 3x)
+        // rates (tools/step_stats.py on cyclic9-15 / kat12-15): row-per-CTA kernel 2.1e11 entries/s, products 1.2e15 int8
+        // multiply-adds/s, a window of the walk 2 us + 0.5 us per pivot it hits, ~40 us per panel
+        // (cyclic9: panels win 1.5-3x; kat12: 60 % dense multipliers but 86 entries per row of A, sparse wins 3x)
         bool panel_pays = opt_panel >= 2;
         if (opt_panel == 1 && have_history) {
-            const double est_sparse = (double)nloc * last_density * n_top * last_a * 0.5 / 3e11;
-            const double est_panel = (double)(mt_ * sc_bm) * n_top * (double)n_top * 0.5 * nl * nl / 1.2e15 + n_top / 32.0 * 4e-6 +
-                                     (double)n_top / PANEL_T * 6e-5;
+            const double est_sparse = (double)nloc * last_density * n_top * last_a * 0.5 / 2.1e11;
+            const double est_panel = (double)(mt_ * sc_bm) * n_top * (double)n_top * 0.5 * nl * nl / 1.2e15 +
+                                     n_top / 32.0 * (2e-6 + last_density * 1.6e-5) + (double)n_top / PANEL_T * 4e-5;
             panel_pays = est_panel < est_sparse;
         }
         if (use_schur && opt_schur_tc && panel_pays && !opt_mc && opt_block < 2 && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
@@ -887,6 +888,24 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
             GCU_CHECK(cudaDeviceGetDefaultMemPool(&pool, (int)cfg->device));
             uint64_t keep = ~0ull;                       // freed blocks stay in the pool for the next step
             GCU_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            // Put some memory into the pool up front (one allocation, released straight back to the pool): the first
+            // steps of a run then grow their buffers without a trip to the driver each time.
+            // GAMBA_POOL_PREWARM_GB (default 6, capped at a quarter of the free memory; 0 = off)
+            {
+                size_t free_b = 0, total_b = 0;
+                GCU_CHECK(cudaMemGetInfo(&free_b, &total_b));
+                const char* pw = std::getenv("GAMBA_POOL_PREWARM_GB");
+                const double want_gb = pw ? std::atof(pw) : 6.0;
+                uint64_t have = 0;
+                GCU_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &have));
+                const size_t want = (size_t)std::min<double>(want_gb * 1e9, (double)free_b / 4);
+                if (want > have + (64u << 20)) {
+                    void* warm = nullptr;
+                    if (cudaMallocAsync(&warm, want - have, e->stream) == cudaSuccess) GCU_CHECK(cudaFreeAsync(warm, e->stream));
+                    else cudaGetLastError();
+                    GCU_CHECK(cudaStreamSynchronize(e->stream));
+                }
+            }
             for (auto& ev : e->ev) GCU_CHECK(cudaEventCreate(&ev));
             e->ctr.sm_count = (uint32_t)e->prop.multiProcessorCount;
         } catch (...) { delete e; throw; }

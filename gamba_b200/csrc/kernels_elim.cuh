@@ -340,23 +340,29 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
                     const uint32_t need = nza & dz;
                     if (need) {   // x = a * (I + M): add a_i * M[i][lane] for the flagged rows i
                         const uint32_t* dg = a.diag + (uint64_t)(k0 / WINDOW) * WINDOW * WINDOW + lane;
-                        uint64_t xa = av;
+                        // four independent partial sums: the chain of dependent 64-bit multiply-adds is what a window waits for
+                        uint64_t xa0 = av, xa1 = 0, xa2 = 0, xa3 = 0;
                         uint32_t rest = dz;
                         int i;
-                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv0, p2); }
-                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv1, p2); }
-                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv2, p2); }
-                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i), pv3, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa0 = fp_mac<SMALLP>(xa0, __shfl_sync(0xffffffffu, av, i), pv0, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa1 = fp_mac<SMALLP>(xa1, __shfl_sync(0xffffffffu, av, i), pv1, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa2 = fp_mac<SMALLP>(xa2, __shfl_sync(0xffffffffu, av, i), pv2, p2); }
+                        if (rest) { i = __ffs(rest) - 1; rest &= rest - 1; if ((need >> i) & 1u) xa3 = fp_mac<SMALLP>(xa3, __shfl_sync(0xffffffffu, av, i), pv3, p2); }
                         rest &= need;
-                        while (rest) {                // more than 4 flagged rows: the others on demand (p < 2^16: 32 products fit 64 bits)
-                            const int i0 = __ffs(rest) - 1; rest &= rest - 1;
-                            const int i1 = rest ? __ffs(rest) - 1 : -1; if (rest) rest &= rest - 1;
-                            const uint32_t m0 = __ldg(dg + i0 * WINDOW);
-                            const uint32_t m1 = i1 >= 0 ? __ldg(dg + i1 * WINDOW) : 0u;
-                            xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i0), m0, p2);
-                            if (i1 >= 0) xa = fp_mac<SMALLP>(xa, __shfl_sync(0xffffffffu, av, i1), m1, p2);
+                        while (rest) {                // more than 4 flagged rows: the others on demand, 4 independent loads at a time
+                            int ii[4]; uint32_t mm[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                ii[u] = rest ? __ffs(rest) - 1 : -1;
+                                if (rest) rest &= rest - 1;
+                                mm[u] = ii[u] >= 0 ? __ldg(dg + ii[u] * WINDOW) : 0u;
+                            }
+                            if (ii[0] >= 0) xa0 = fp_mac<SMALLP>(xa0, __shfl_sync(0xffffffffu, av, ii[0]), mm[0], p2);   // p < 2^16: 32 products fit 64 bits
+                            if (ii[1] >= 0) xa1 = fp_mac<SMALLP>(xa1, __shfl_sync(0xffffffffu, av, ii[1]), mm[1], p2);
+                            if (ii[2] >= 0) xa2 = fp_mac<SMALLP>(xa2, __shfl_sync(0xffffffffu, av, ii[2]), mm[2], p2);
+                            if (ii[3] >= 0) xa3 = fp_mac<SMALLP>(xa3, __shfl_sync(0xffffffffu, av, ii[3]), mm[3], p2);
                         }
-                        x = fp_reduce64(xa, a.f);
+                        x = fp_reduce64(xa0 + xa1 + xa2 + xa3, a.f);   // each partial sum < p^2 < 2^62
                     }
                     const uint32_t nzm = __ballot_sync(0xffffffffu, x != 0);
                     if (nzm == 0) continue;           // CTA-uniform

@@ -58,30 +58,34 @@ class LinalgEngine:
             sin.row_src, sin.col_map, sin.col_map_len, sin.col_idx_len = row_src.ctypes.data, col_map.ctypes.data, len(col_map), len(col)
         return sin
 
-    def _rows(self, out: _lib.StepOut) -> Rows:
+    def _rows(self, out: _lib.StepOut, copy: bool = True) -> Rows:
+        """copy=False: the arrays are views of the engine-owned result buffers (valid until the next call on the
+        engine), which is what the C ABI hands out; the default copies them."""
         n, nnz = out.n_new, out.nnz_new
         dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.coeff_bytes]
 
         def arr(ptr, count, dtype):
             if count == 0:
                 return np.zeros(0, dtype=dtype)
-            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (count,)).copy()
+            v = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (count,))
+            return v.copy() if copy else v
         self.last = {k: getattr(out, k) for k, _ in _lib.StepOut._fields_ if not k.endswith(("ptr", "rel", "coeff"))}
+        val = arr(out.coeff, nnz, dt)
         return Rows(n, arr(out.row_ptr, n + 1, np.uint64), arr(out.col_rel, nnz, np.uint32),
-                    arr(out.coeff, nnz, dt).astype(np.uint32))
+                    val if val.dtype == np.uint32 else val.astype(np.uint32))
 
     def _check(self, rc: int, what: str):
         if rc:
             raise RuntimeError(f"{what}: " + self.lib.gamba_cuda_last_error().decode())
 
     # -- the reference-facing calls ------------------------------------------------
-    def reduce(self, s: Step | None, final: bool = False) -> Rows:
+    def reduce(self, s: Step | None, final: bool = False, copy: bool = True) -> Rows:
         """Host buffers in, host buffers out (H2D + kernels + D2H). `s` may be None on ranks > 0 of a
         broadcasting group (set_broadcast): the step then arrives from rank 0 over NCCL."""
         out = _lib.StepOut()
         sin = C.byref(self._step_in(s, _lib.STEP_FINAL if final else 0)) if s is not None else None
         self._check(self.lib.gamba_cuda_reduce(self.h, sin, C.byref(out)), "gamba_cuda_reduce")
-        return self._rows(out)
+        return self._rows(out, copy)
 
     def reduce_final(self, s: Step) -> Rows:
         return self.reduce(s, final=True)
@@ -90,10 +94,10 @@ class LinalgEngine:
         sin = C.byref(self._step_in(s, _lib.STEP_FINAL if final else 0)) if s is not None else None
         self._check(self.lib.gamba_cuda_stage(self.h, sin), "gamba_cuda_stage")
 
-    def reduce_staged(self) -> Rows:
+    def reduce_staged(self, copy: bool = True) -> Rows:
         out = _lib.StepOut()
         self._check(self.lib.gamba_cuda_reduce_staged(self.h, C.byref(out)), "gamba_cuda_reduce_staged")
-        return self._rows(out)
+        return self._rows(out, copy)
 
     def counters(self) -> dict:
         c = _lib.Counters()
