@@ -273,8 +273,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return s if (rank == 0 or not bcast) else None
     for e, s in zip(engines, steps):
         e.stage(mine(s))
-        e.reduce_staged()      # untimed: the engine picks its kernels for a step from what the previous step measured
-        e.stage(mine(s))       # (F4 steps change slowly); here every matrix has its own engine, so it sees itself first
+        for _ in range(3):     # untimed: the engine picks its kernels for a step from what the previous steps measured
+            e.reduce_staged()  # (F4 steps change slowly: one step per mode, then the calibrated choice); here every
+            e.stage(mine(s))   # matrix has its own engine, so it sees itself first
     for _ in range(args.warmup):
         for e in engines:
             e.reduce_staged()

@@ -136,6 +136,16 @@ struct gamba_cuda_engine {
     double last_density = 0;         // pivots hit per row / n_top of the previous step (predictor for this one)
     double last_a = 0, cur_a = 0;    // entries of A per pivot row (outside the diagonal blocks): previous step, staged step
     bool have_history = false;
+    // Choice between the sparse kernel and the panel products: modelled times (rates measured with tools/step_stats.py).
+    // The sparse kernel's work is  rows x hits x entries of the pivot rows hit: the pivot rows that are hit often are
+    // longer than average (cyclic9: 4x, katsura: 1x) - hitw = applied entries / (rows x hits x mean length / 2), measured
+    // whenever a step runs the sparse kernel (a ratio of counts: meaningful on small steps too), refreshed every 16 steps
+    double hitw = 1;
+    uint32_t since_explore = 0;
+    static double model_sparse(double nloc, double dens, double k, double a) { return nloc * dens * k * a * 0.5 / 2.1e11; }
+    static double model_panel(double mpad, double k, double nl, double dens, double t) {
+        return mpad * k * k * 0.5 * nl * nl / 1.2e15 + k / 32.0 * (2e-6 + dens * 1.6e-5) + k / t * 4e-5;
+    }
     bool use_schur = false, use_block = false;   // decided per staged step (plan_step)
     int64_t opt_schur_max_gb = 64;   // budget for the Mx and Bt limb planes
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
@@ -258,10 +268,10 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // (cyclic9: panels win 1.5-3x; kat12: 60 % dense multipliers but 86 entries per row of A, sparse wins 3x)
         bool panel_pays = opt_panel >= 2;
         if (opt_panel == 1 && have_history) {
-            const double est_sparse = (double)nloc * last_density * n_top * last_a * 0.5 / 2.1e11;
-            const double est_panel = (double)(mt_ * sc_bm) * n_top * (double)n_top * 0.5 * nl * nl / 1.2e15 +
-                                     n_top / 32.0 * (2e-6 + last_density * 1.6e-5) + (double)n_top / PANEL_T * 4e-5;
+            const double est_sparse = hitw * model_sparse(nloc, last_density, n_top, last_a);
+            const double est_panel = model_panel((double)(mt_ * sc_bm), n_top, nl, last_density, PANEL_T);
             panel_pays = est_panel < est_sparse;
+            if (panel_pays && ++since_explore >= 16) { panel_pays = false; since_explore = 0; }   // refresh hitw
         }
         if (use_schur && opt_schur_tc && panel_pays && !opt_mc && opt_block < 2 && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
             const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T;
@@ -546,23 +556,32 @@ void gamba_cuda_engine::eliminate() {
     const bool schur = use_schur && n_local;
     const bool block = schur && use_block;
     const bool panel = schur && use_panel;
-    GCU_CHECK(cudaEventRecord(ev[2], stream));
+    // buffers first: growing one may go to the driver, which must not sit inside the event-timed region
     if (schur) {
         d_mx.ensure(nl * mx_plane);
-        GCU_CHECK(cudaMemsetAsync(d_mx.p, 0, nl * mx_plane, stream));
-        ea.mx = d_mx.as<uint8_t>(); ea.mx_plane = mx_plane; ea.mx_kp = kp; ea.mx_nl = nl;
-        if (!bt_built) {
-            d_bt.ensure(nl * bt_plane);
-            GCU_CHECK(cudaMemsetAsync(d_bt.p, 0, nl * bt_plane, stream));
-            BtArgs ba{};
-            ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
-            ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
-            if (panel) {     // operands of the panel products: tile t takes [nl][T][t * T] bytes
+        if (!bt_built) d_bt.ensure(nl * bt_plane);
+        if (panel) {     // operands of the panel products: tile t takes [nl][T][t * T] bytes
+            if (!bt_built) {
                 at_off.assign(L.n_tiles_piv + 1, 0);
                 for (uint32_t t = 1; t <= L.n_tiles_piv; ++t) at_off[t] = at_off[t - 1] + (t > 1 ? (uint64_t)nl * PANEL_T * (uint64_t)(t - 1) * PANEL_T : 0);
                 at_bytes = at_off[L.n_tiles_piv];
                 d_at.ensure(std::max<uint64_t>(at_bytes, 16));
                 d_at_off.ensure(at_off.size() * sizeof(uint64_t));
+            }
+            d_cd.ensure((uint64_t)mp * PANEL_T * sizeof(uint32_t));
+            d_mt.ensure((uint64_t)(L.n_tiles + 2) * sizeof(uint32_t));              // one row-queue counter per launch
+        }
+    }
+    GCU_CHECK(cudaEventRecord(ev[2], stream));
+    if (schur) {
+        GCU_CHECK(cudaMemsetAsync(d_mx.p, 0, nl * mx_plane, stream));
+        ea.mx = d_mx.as<uint8_t>(); ea.mx_plane = mx_plane; ea.mx_kp = kp; ea.mx_nl = nl;
+        if (!bt_built) {
+            GCU_CHECK(cudaMemsetAsync(d_bt.p, 0, nl * bt_plane, stream));
+            BtArgs ba{};
+            ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
+            ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
+            if (panel) {
                 GCU_CHECK(cudaMemsetAsync(d_at.p, 0, std::max<uint64_t>(at_bytes, 16), stream));
                 GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
                 ba.at = d_at.as<uint8_t>(); ba.at_off = d_at_off.as<uint64_t>();
@@ -579,8 +598,6 @@ void gamba_cuda_engine::eliminate() {
         // product cd = M[:, < t T] * A[< t T, tile t]; elim_kernel then only walks the windows of tile t.
         const uint32_t ntp = L.n_tiles_piv, T = PANEL_T;
         const uint32_t bn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN;
-        d_cd.ensure((uint64_t)mp * T * sizeof(uint32_t));
-        d_mt.ensure((uint64_t)(L.n_tiles + 2) * sizeof(uint32_t));              // one row-queue counter per launch
         GCU_CHECK(cudaMemsetAsync(d_mt.p, 0, (uint64_t)(L.n_tiles + 2) * sizeof(uint32_t), stream));
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
         ea.panel = 1; ea.cd_ld = T;
@@ -793,7 +810,11 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
     ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
     ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
     ctr.fma_top = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[2];
-    if (n_local && L.n_top && !mc_k) { last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top); last_a = cur_a; have_history = true; }
+    if (n_local && L.n_top && !mc_k) {
+        last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top); last_a = cur_a; have_history = true;
+        if (use_schur && !use_block && !use_panel && last_a > 0 && ctr.pivots_applied > 1000)      // the sparse kernel ran: its real work
+            hitw = std::min(16.0, std::max(0.25, (double)ctr.fma_applied / ((double)ctr.pivots_applied * last_a * 0.5)));
+    }
     ctr.steps += 1;
 
     if ((flags & GAMBA_CUDA_STEP_FINAL) && npiv != L.n_bot)

@@ -24,7 +24,8 @@ def main():
             for k, v in opts:
                 eng.set_option(k, int(v))
         eng.stage(s)
-        eng.reduce_staged(); eng.stage(s)      # kernels are chosen from the previous step's measurements
+        for _ in range(3):
+            eng.reduce_staged(); eng.stage(s)      # kernels are chosen from the previous steps' measurements
         best = None
         for _ in range(2):
             r = eng.reduce_staged()

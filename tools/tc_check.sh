@@ -6,4 +6,4 @@ import json
 j=json.loads([l for l in open('gpurun_out/bench_now.json') if l.startswith('{')][-1])
 print('value %.3e e2e %.3e ms %.1f' % (j['value'], j['e2e']['value'], j['ms_per_step']), j['breakdown_ms_per_step'], j['roofline']['parts']['sparse_solve_ms_per_step'], j['roofline']['frac'])
 PY
-E2E_TIMEOUT=300 bash tools/e2e_big.sh cyclic9-15 cyclic9-31 kat12-15 kat13-15 eco13-15 eco14-15 2>&1 | grep -E "^===|linalg \(wall\)|overall|/tmp/sys"
+GAMBA_DEBUG_TIMERS=1 E2E_TIMEOUT=300 bash tools/e2e_big.sh cyclic9-15 cyclic9-31 kat12-15 kat13-15 eco13-15 eco14-15 2>&1 | grep -E "^===|linalg \(wall\)|overall|/tmp/sys|dbg stage|dbg engine"
