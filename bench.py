@@ -53,7 +53,7 @@ def measured_peaks():
 def measured_traffic():
     """DRAM bytes per elimination-kernel launch from the committed ncu capture (profiles/), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_elim_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01d_elim_traffic.json")) as f:
             return float(json.load(f)["mean_dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         return None
@@ -354,7 +354,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                    "for D' = D + M B",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic() if args.system == "cyclic9-15" else None,
-                         "traffic_source": "ncu dram__bytes_read+write of the stage's kernels per matrix, profiles/r01c_elim_traffic.json",
+                         "traffic_source": "ncu dram__bytes_read+write of the stage's kernels per matrix, profiles/r01d_elim_traffic.json",
                          "peak_source": peak_src,
                          "parts": {"sparse_solve_ms_per_step": 1e3 * sparse_s / args.steps, "schur_ms_per_step": 1e3 * schur_s / args.steps,
                                    "schur_tensor": {"achieved": schur_imma / max(schur_s, 1e-12) / 1e12, "peak": 2250.0, "unit": "int8 TMAC/s",
