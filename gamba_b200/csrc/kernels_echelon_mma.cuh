@@ -40,7 +40,10 @@ namespace gcu {
 constexpr int EM_THREADS = 512;
 constexpr int EM_WARPS = EM_THREADS / 32;
 constexpr int EM_B = 32;                    // panel rows = contraction depth of one trailing update
-constexpr int EM_W = 512;                   // window columns of the panel factorisation
+#ifndef GAMBA_EM_W
+#define GAMBA_EM_W 256          // measured on the cyclic9-15 batch (tools/emw_variants.sh): 512: 29.5 ms, 256: 26.9 ms, 128: 29.5 ms per pass
+#endif
+constexpr int EM_W = GAMBA_EM_W;                   // window columns of the panel factorisation
 constexpr int EM_WP = EM_W + EM_B;          // + the transformation block
 constexpr int EM_CW = 128;                  // columns of one trailing-update work item
 constexpr int EM_RG = EM_WARPS * 16;        // live rows of one trailing-update work item
