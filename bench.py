@@ -115,10 +115,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def generate_workload(system: str, min_nnz: int, rank: int, world: int) -> list[str]:
+def generate_workload(system: str, min_nnz: int, rank: int, world: int, max_spairs: int = 2000) -> list[str]:
     """Step matrices of `system` with >= min_nnz non-zeros, produced by the product driver on this box."""
     from gamba_b200 import systems
-    d = os.path.join(WORK_DIR, f"{system}_{min_nnz}")
+    d = os.path.join(WORK_DIR, f"{system}_{min_nnz}" + ("" if max_spairs == 2000 else f"_sp{max_spairs}"))
     done = os.path.join(d, "DONE")
     if rank == 0 and not os.path.exists(done):
         shutil.rmtree(d, ignore_errors=True)
@@ -126,7 +126,8 @@ def generate_workload(system: str, min_nnz: int, rank: int, world: int) -> list[
         inp = systems.write_system(system, os.path.join(d, system + ".txt"))
         t = time.time()
         r = subprocess.run([os.path.join(ROOT, "gamba_b200", "bin", "gamba"), "-i", inp, "-o", os.path.join(d, "out.txt"),
-                            "-v", "1", "--dump-steps", d, "--dump-min-nnz", str(min_nnz)], capture_output=True, text=True)
+                            "-v", "1", "--dump-steps", d, "--dump-min-nnz", str(min_nnz), "--max-spairs", str(max_spairs)],
+                           capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("workload generation failed (no CPU fallback): " + r.stderr[-2000:])
         with open(os.path.join(d, "driver.log"), "w") as f:
@@ -153,8 +154,9 @@ def load_workload(args, rank: int, world: int):
         dens = float(parts[2]) if len(parts) > 2 else 0.005
         p = {"15": 32003, "31": 2147483647}[parts[3] if len(parts) > 3 else "31"]
         return [synthetic_step_large(nr, nc, dens, p)], f"synthetic F4-shaped matrix {nr} x {nc}, density {dens}, p={p}, seed 967557673"
-    files = generate_workload(args.system, args.min_nnz, rank, world)
-    return [load_step(f) for f in files], f"{args.system} F4 step matrices with >= {args.min_nnz} nnz"
+    files = generate_workload(args.system, args.min_nnz, rank, world, args.max_spairs)
+    return [load_step(f) for f in files], (f"{args.system} F4 step matrices with >= {args.min_nnz} nnz" +
+                                           ("" if args.max_spairs == 2000 else f" (--max-spairs {args.max_spairs})"))
 
 
 def bytes_alg(step, fma_top: int) -> float:
@@ -344,7 +346,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                        "parallelism": (f"C|D rows sharded r % {world}, step uploaded by rank 0 and replicated by NCCL broadcast, "
                                        f"NCCL all-gather of D' rows, echelon replicated") if world > 1 else "1 GPU",
                        "l2": "inputs larger than L2 (every pass cycles through all matrices; smallest staged step > 126 MB)",
-                       "max_spairs": 2000, "tile_cols": c["tile_cols"], "acc_bits": c["acc_bits"]},
+                       "max_spairs": args.max_spairs, "tile_cols": c["tile_cols"], "acc_bits": c["acc_bits"]},
             "e2e": {"value": total_nnz * args.steps / t_e2e, "unit": "nnz/s", "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": n_launch,
@@ -404,6 +406,7 @@ def main():
     ap.add_argument("--system", default="cyclic9-15")
     ap.add_argument("--min-nnz", type=int, default=15_000_000)
     ap.add_argument("--max-matrices", type=int, default=0)
+    ap.add_argument("--max-spairs", type=int, default=2000, help="pair cap of the driver run that produces the matrices (0 = none)")
     ap.add_argument("--ref-seconds", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bcast", action="store_true", help="N>1: every rank uploads the step itself (no NCCL broadcast)")
