@@ -41,6 +41,15 @@
 //      (x = a (I+N)^-1, no dependent chain; only rows flagged in dnz are touched),
 //      then apply the pivot rows with x != 0 to the rest of the tile;
 //   4. non-pivot tiles: reduce the lanes mod p and write the row of D'.
+//
+// Three ways of running it (gamba_cuda.cu picks per step):
+//   sparse path   all of the above for both halves of the row (operands of the products too big, option schur=0);
+//   Schur mode    (a.mx) the non-pivot tiles only receive the row's own entries: D' = D + M B is a tensor-core
+//                 product (kernels_schur_tc.cuh), the multipliers are recorded as u8 limb planes;
+//   panel mode    (a.panel) one launch per column tile [t_lo, t_hi): step 2 is replaced by a tensor-core product
+//                 cd = M[:, earlier tiles] * A[earlier tiles, tile] computed before the launch, so only step 3 is
+//                 left - a chain of dependent windows per row, for which the row flags of the inverse diagonal
+//                 block and the lane's column of its first flagged rows are fetched one window ahead.
 #pragma once
 #include "layout.cuh"
 

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define GAMBA_CUDA_ABI_VERSION 2
+#define GAMBA_CUDA_ABI_VERSION 3   /* 3: gamba_cuda_counters grew (seconds_sparse_last, seconds_schur_last, schur_macs) */
 
 #define GAMBA_CUDA_REPR_STANDARD   0u
 #define GAMBA_CUDA_REPR_MONTGOMERY 1u
