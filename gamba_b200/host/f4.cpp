@@ -278,7 +278,20 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
                 uint16_t tmp[258];
                 const uint16_t* a = f.ex.data();
                 const uint32_t* fh = f.hv.data();
-                for (size_t k = 0, n = f.mon.size(); k < n; ++k, a += st) {
+                // A lookup is three dependent cache misses (slot -> hash of the candidate -> its exponents) in a table of
+                // millions of monomials: the slot of term k + 16 and the candidate of term k + 8 are prefetched
+                const uint32_t msk = st_.mask;
+                const uint32_t* sl = st_.slots.data();
+                const size_t n = f.mon.size();
+                for (size_t k = 0; k < n; ++k, a += st) {
+                    if (k + 16 < n) __builtin_prefetch(&sl[(fh[k + 16] + hq) & msk]);
+                    if (k + 8 < n) {
+                        const uint32_t v = __atomic_load_n(&sl[(fh[k + 8] + hq) & msk], __ATOMIC_RELAXED);
+                        if (v != 0 && v != MonoTable::PENDING) {
+                            __builtin_prefetch(&st_.hv[v - 1]);
+                            __builtin_prefetch(&st_.ex[(size_t)(v - 1) * st]);
+                        }
+                    }
                     for (int j = 0; j < st; ++j) tmp[j] = (uint16_t)(a[j] + q[j]);
                     out[k] = st_.insert_mt(tmp, fh[k] + hq);
                 }

@@ -1,3 +1,10 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-for w in 4 8; do echo "== elim_warps=$w"; timeout 300 python tools/step_stats.py cyclic9-15 15000000 elim_warps=$w 2>&1 | grep -o 'step_[0-9]*.bin\|T=[0-9]*\|sparse [0-9.]*' | paste - - -; done
+mkdir -p /tmp/sys
+python - <<'PY'
+import sys; sys.path.insert(0,'.')
+from gamba_b200 import systems
+systems.write_system('kat15-15', '/tmp/sys/kat15-15.txt')
+PY
+( time GAMBA_DEBUG_TIMERS=1 timeout 600 gamba_b200/bin/gamba -i /tmp/sys/kat15-15.txt -o /tmp/sys/k15.out0 -v 1 --max-spairs 0 ) 2>&1 | grep -E "linalg \(wall\)|overall|update .* select|dbg:|real|rror"
+md5sum /tmp/sys/k15.out0
