@@ -36,7 +36,8 @@ class Counters(C.Structure):
                 ("tile_cols", C.c_uint32), ("n_tiles", C.c_uint32), ("acc_bits", C.c_uint32),
                 ("pivots_applied", C.c_uint64), ("fma_applied", C.c_uint64), ("fma_top", C.c_uint64), ("mc_combinations", C.c_uint32), ("mc_attempts", C.c_uint32),
                 ("seconds_stage_last", C.c_double), ("seconds_sparse_last", C.c_double),
-                ("seconds_schur_last", C.c_double), ("schur_macs", C.c_uint64)]
+                ("seconds_schur_last", C.c_double), ("schur_macs", C.c_uint64),
+                ("mc_ech_combinations", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

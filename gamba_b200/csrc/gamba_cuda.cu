@@ -130,6 +130,10 @@ struct gamba_cuda_engine {
     int64_t opt_panel_t = 0;         // 0 = chosen per step so that the panel products fill whole waves of CTAs
     int64_t opt_panel_max_top = 100000;   // operands of K^2 / 2 bytes per limb: a cap besides the cost estimate in choose_layout
     gcu::DevBuf d_at, d_at_off, d_cd;
+    gcu::DevBuf d_mc_s, d_mc_dt, d_mc_dc, d_mc_nz;
+    int64_t opt_mc_ech = 1;          // Monte-Carlo combinations of the rows of D' in front of the echelon (accepted with a rank margin of 32)
+    uint32_t mc_ech_k = 0;           // combinations used by the last echelon (0 = it ran on the rows themselves)
+    uint64_t mc_ech_draw = 0;
     std::vector<uint64_t> at_off;
     uint64_t at_bytes = 0;
     int64_t opt_block = 1;           // blocked sparse solve (kernels_elim_block.cuh): 0 never, 1 when the multipliers are dense, 2 always
@@ -208,7 +212,7 @@ struct gamba_cuda_engine {
     void stage(const gamba_cuda_step_in* in);
     void eliminate();
     void exchange();
-    void echelon(gamba_cuda_step_out* out);
+    void echelon(gamba_cuda_step_out* out, uint32_t mc_rows = 0);
     void run_reduce(gamba_cuda_step_out* out);
 };
 
@@ -712,15 +716,59 @@ void gamba_cuda_engine::exchange() {
     if (bytes_z && gather_fn(gather_user, send_z, d_row_nz.p, bytes_z, stream)) throw std::runtime_error("all-gather of row flags failed");
 }
 
-void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
+void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
     if (!eliminated) throw std::runtime_error("eliminate() has not run");
-    const uint32_t nr = n_gather_rows, nc = L.n_nonpiv;
+    uint32_t nr = n_gather_rows;
+    const uint32_t nc = L.n_nonpiv;
+    uint32_t* ech_d = d_dprime.as<uint32_t>();
+    uint32_t* ech_nz = d_row_nz.as<uint32_t>();
     uint32_t npiv = 0;
     uint64_t nnz_new = 0;
     d_counts.ensure(256);
+    // Monte-Carlo stage: buffers before the timed region
+    const uint32_t mnl = f.small ? 2u : 4u, mbn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN;
+    const uint32_t rp = (nr + 127u) / 128u * 128u, kp_ = (mc_rows + 127u) / 128u * 128u, np_ = (nc + 127u) / 128u * 128u;
+    if (mc_rows) {
+        d_mc_s.ensure((uint64_t)mnl * kp_ * rp);
+        d_mc_dt.ensure((uint64_t)mnl * np_ * rp);
+        d_mc_dc.ensure((uint64_t)kp_ * L.ld_dprime * sizeof(uint32_t));
+        d_mc_nz.ensure((uint64_t)kp_ * sizeof(uint32_t));
+    }
     GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 32, stream));
     GCU_CHECK(cudaMemsetAsync(d_counts.as<char>() + 32, 0xff, 32, stream));
     GCU_CHECK(cudaEventRecord(ev[4], stream));
+    if (mc_rows && nr && nc) {
+        // Dc = S D' on the tensor cores; the echelon then sees mc_rows rows
+        McArgs ma{};
+        ma.n_rows = nr; ma.n_cols = nc; ma.ld = L.ld_dprime; ma.d = d_dprime.as<uint32_t>();
+        ma.dt = d_mc_dt.as<uint8_t>(); ma.s = d_mc_s.as<uint8_t>(); ma.dt_plane = (uint64_t)np_ * rp; ma.s_plane = (uint64_t)kp_ * rp;
+        ma.rp = rp; ma.k = mc_rows; ma.nl = mnl; ma.seed = cfg.seed * 0x9e3779b97f4a7c15ull + 0x5bd1e995u * (++mc_ech_draw);
+        GCU_CHECK(cudaMemsetAsync(d_mc_s.p, 0, (uint64_t)mnl * kp_ * rp, stream));
+        GCU_CHECK(cudaMemsetAsync(d_mc_dt.p, 0, (uint64_t)mnl * np_ * rp, stream));
+        GCU_CHECK(cudaMemsetAsync(d_mc_dc.p, 0, (uint64_t)kp_ * L.ld_dprime * sizeof(uint32_t), stream));
+        GCU_CHECK(cudaMemsetAsync(d_mc_nz.p, 0, (uint64_t)kp_ * sizeof(uint32_t), stream));
+        mc_dt_kernel<<<dim3((nc + 31) / 32, rp / 128), 256, 0, stream>>>(ma);
+        GCU_CHECK(cudaGetLastError());
+        mc_s_kernel<<<(uint32_t)(((uint64_t)mc_rows * (rp / 4) + 255) / 256), 256, 0, stream>>>(ma);
+        GCU_CHECK(cudaGetLastError());
+        TcArgs ta{};
+        ta.f = f; ta.kp = rp; ta.mp = kp_; ta.np = np_; ta.n_rows = mc_rows; ta.n_cols = nc; ta.ld = L.ld_dprime;
+        ta.d = d_mc_dc.as<uint32_t>(); ta.row_nz = d_mc_nz.as<uint32_t>(); ta.m_tiles = kp_ / TC_BM; ta.n_tiles = np_ / mbn;
+        ta.first_piv = nullptr; ta.k_first = 0; ta.row_begin = 0; ta.row_step = 1;
+        ta.kchunk = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK; ta.k_end = rp;
+        const CUtensorMap map_s = make_tmap_u8(d_mc_s.p, rp, (uint64_t)mnl * kp_, TC_BK, TC_BM);
+        const CUtensorMap map_dt = make_tmap_u8(d_mc_dt.p, rp, (uint64_t)mnl * np_, TC_BK, mbn);
+        if (f.small) {
+            GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
+            schur_tc_kernel<2><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<2>(), stream>>>(map_s, map_dt, ta);
+        } else {
+            GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
+            schur_tc_kernel<4><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<4>(), stream>>>(map_s, map_dt, ta);
+        }
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 3;
+        nr = mc_rows; ech_d = d_mc_dc.as<uint32_t>(); ech_nz = d_mc_nz.as<uint32_t>();
+    }
     if (nr && nc) {
         d_lead.ensure((size_t)3 * nr * sizeof(uint32_t));
         d_nz_list.ensure((size_t)nr * sizeof(uint32_t));
@@ -730,7 +778,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
         d_out_ptr.ensure((size_t)(nr + 1) * sizeof(uint64_t));
         EchArgs ea{};
         ea.f = f; ea.n_rows = nr; ea.n_cols = nc; ea.ld = L.ld_dprime;
-        ea.d = d_dprime.as<uint32_t>(); ea.row_nz = d_row_nz.as<uint32_t>();
+        ea.d = ech_d; ea.row_nz = ech_nz;
         ea.lead = d_lead.as<uint32_t>(); ea.inv_lead = d_lead.as<uint32_t>() + (size_t)2 * nr; ea.nz_list = d_nz_list.as<uint32_t>();
         ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
         ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
@@ -779,7 +827,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out) {
             d_out_col.ensure(nnz_new * sizeof(uint32_t));
             d_out_val.ensure(nnz_new * sizeof(uint32_t));
             EmitArgs em{};
-            em.f = f; em.n_cols = nc; em.n_piv = npiv; em.ld = L.ld_dprime; em.d = d_dprime.as<uint32_t>();
+            em.f = f; em.n_cols = nc; em.n_piv = npiv; em.ld = L.ld_dprime; em.d = ech_d;
             em.piv_row = d_piv_row.as<uint32_t>(); em.piv_col = d_piv_col.as<uint32_t>();
             em.is_piv_col = d_is_piv.as<uint8_t>(); em.out_ptr = d_out_ptr.as<uint64_t>();
             em.out_col = d_out_col.as<uint32_t>(); em.out_val = d_out_val.as<uint32_t>();
@@ -854,7 +902,21 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
         eliminate();
         exchange();
         dbg_[5] += wall_s() - tq; tq = wall_s();
-        echelon(out);
+        // Monte-Carlo combinations in front of the echelon: K = predicted rank + margin combinations of the rows of D'
+        // instead of the rows (most of which reduce to zero); accepted only if K - rank >= 32, else the rows themselves
+        uint32_t kk = 0;
+        if (opt_mc_ech && opt_schur_tc && !mc_k && !(flags & GAMBA_CUDA_STEP_FINAL) && last_rank >= 0 && n_gather_rows >= 512 && L.n_nonpiv) {
+            const uint32_t want = ((uint32_t)(last_rank + 32 + last_rank / 8) + 127u) / 128u * 128u;
+            if ((uint64_t)want * 2 <= n_gather_rows) kk = want;
+        }
+        echelon(out, kk);
+        if (kk && out->n_new + 32 > kk) {      // margin not met
+            const double t_first = t_ech_dev;
+            kk = 0;
+            echelon(out, 0);
+            t_ech_dev += t_first; ctr.steps -= 1;
+        }
+        mc_ech_k = kk; ctr.mc_ech_combinations = kk;
         dbg_[6] += wall_s() - tq;
         acc_elim += t_elim_dev; acc_ech += t_ech_dev;
         if (mc_k && out->n_new + 32 > mc_k) {          // margin not met: more combinations, or exact
@@ -997,6 +1059,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;
         else if (k == "schur_kchunk") e->opt_schur_kchunk = value;
+        else if (k == "mc_ech") e->opt_mc_ech = value;
         else if (k == "mc") e->opt_mc = value;
         else if (k == "mc_k") e->opt_mc_k = value;
         else if (k == "rank_hint") e->last_rank = value;

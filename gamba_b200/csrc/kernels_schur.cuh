@@ -92,6 +92,61 @@ __global__ void __launch_bounds__(256) schur_bt_kernel(BtArgs a) {
     }
 }
 
+// ---- Monte-Carlo combinations of the rows of D' before the echelon (README.md:5 of the reference: "Monte-Carlo F4") ----
+// K random combinations  Dc = S D'  (S: K x n_rows, uniform limb bytes) span the row space of D' except with probability
+// ~p^-(K - rank); the echelon then runs on K rows instead of n_rows (85-90 % of which would reduce to zero). The product
+// is one more use of the limb-split tensor-core kernel: S limbs as the left operand, D' limbs transposed as the right one.
+struct McArgs {
+    uint32_t n_rows, n_cols, ld;    // D' : n_rows x n_cols, pitch ld
+    const uint32_t* d;
+    uint8_t* dt;                    // [nl][np][rp]  limbs of D' transposed (row index contiguous)
+    uint8_t* s;                     // [nl][kp][rp]  limbs of the random multipliers
+    uint64_t dt_plane, s_plane;
+    uint32_t rp, k, nl;
+    uint64_t seed;
+};
+
+// 32 columns x 128 rows of D' per CTA (256 threads): coalesced reads along the columns, 4 row-bytes per store
+__global__ void __launch_bounds__(256) mc_dt_kernel(McArgs a) {
+    __shared__ uint32_t tile[128][33];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
+    for (uint32_t i = ty; i < 128; i += 8) {
+        const uint32_t r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < a.n_rows && c < a.n_cols) ? a.d[(uint64_t)r * a.ld + c] : 0u;
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < 32 * 32; w += 256) {
+        const uint32_t cl = w >> 5, word = w & 31;
+        if (c0 + cl >= a.n_cols) continue;
+        const uint32_t v0 = tile[word * 4][cl], v1 = tile[word * 4 + 1][cl], v2 = tile[word * 4 + 2][cl], v3 = tile[word * 4 + 3][cl];
+        for (uint32_t l = 0; l < a.nl; ++l) {
+            const uint32_t sh = 8 * l;
+            const uint32_t packed = ((v0 >> sh) & 0xffu) | (((v1 >> sh) & 0xffu) << 8) | (((v2 >> sh) & 0xffu) << 16) | (((v3 >> sh) & 0xffu) << 24);
+            *reinterpret_cast<uint32_t*>(a.dt + l * a.dt_plane + (uint64_t)(c0 + cl) * a.rp + r0 + word * 4) = packed;
+        }
+    }
+}
+
+// random limb bytes of the K x n_rows multipliers (columns >= n_rows of the padded planes stay zero)
+__global__ void __launch_bounds__(256) mc_s_kernel(McArgs a) {
+    const uint64_t words_per_row = a.rp / 4;
+    const uint64_t idx = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (uint64_t)a.k * words_per_row) return;
+    const uint32_t q = (uint32_t)(idx / words_per_row), r4 = (uint32_t)(idx % words_per_row) * 4;
+    for (uint32_t l = 0; l < a.nl; ++l) {
+        uint64_t z = a.seed + 0x9e3779b97f4a7c15ull * ((((uint64_t)q << 32) | r4) * 4 + l) + 0x632be59bd9b4e019ull;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        z ^= z >> 31;
+        uint32_t w = (uint32_t)z;
+        if (l == a.nl - 1) w &= 0x7f7f7f7fu;           // top limb below 128: the multiplier stays below 2^(8 nl - 1) (any value works mod p)
+        uint32_t keep = 0;
+        for (uint32_t b = 0; b < 4; ++b) if (r4 + b < a.n_rows) keep |= 0xffu << (8 * b);
+        *reinterpret_cast<uint32_t*>(a.s + l * a.s_plane + (uint64_t)q * a.rp + r4) = w & keep;
+    }
+}
+
 struct SchurArgs {
     Fp f;
     const uint8_t* mx;          // [NL][mp][kp]

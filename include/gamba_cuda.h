@@ -166,6 +166,8 @@ typedef struct gamba_cuda_counters {
     double seconds_sparse_last;        /* CUDA-event time of elim_kernel alone (the sparse triangular solve), last step */
     double seconds_schur_last;         /* ... of the tensor-core product D' = D + M B (limb planes + schur kernel)     */
     uint64_t schur_macs;               /* mod-p multiply-adds of that product: rows x n_top x n_nonpiv (0 = sparse path) */
+    uint32_t mc_ech_combinations;      /* random combinations of the rows of D' the last echelon ran on (0 = the rows themselves) */
+    uint32_t reserved0;
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
@@ -179,6 +181,9 @@ int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
    "block" (with "schur": the sparse half of the elimination for R rows per CTA from one pass over the pivot rows,
    kernels_elim_block.cuh; 0 never, 1 (default) for steps with >= 32768 pivot rows once the previous step had
    more than half of its multipliers non-zero, 2 always), "elim_warps", "schur_min_top", "schur_kchunk" (tuning / tests),
+   "mc_ech" (default 1: the echelon runs on K = predicted rank + margin random combinations of the rows of D', formed on the
+   tensor cores, and is accepted only if K - rank >= 32 - otherwise it is repeated on the rows themselves; the result is the
+   canonical RREF either way; "rank_hint" sets the prediction),
    "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
    margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);

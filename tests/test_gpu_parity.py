@@ -393,3 +393,34 @@ def test_panel_mode_accumulator_folds(built):
     eng = panel_engine(32003, schur_kchunk=1)
     assert eng.reduce(s).same_as(want)
     eng.close()
+
+
+# ---- Monte-Carlo combinations in front of the echelon ------------------------------------------------------
+
+@pytest.mark.parametrize("p", [32003, 2147483647])
+def test_mc_echelon_combinations_are_bit_exact(step_dirs, p):
+    """K random combinations of the rows of D' (a tensor-core product) go into the echelon instead of the rows; the
+    canonical RREF must be that of the rows. rank_hint far too small: the margin test must send the step back to the
+    rows themselves; rank_hint = true rank: the combinations are accepted."""
+    from gamba_b200 import LinalgEngine
+    name = "cyclic8-15" if p == 32003 else "cyclic8-31"
+    d = step_dirs(name, ("--dump-min-nnz", "100000"))
+    eng = LinalgEngine(p)
+    used = rejected = 0
+    for f in sorted(glob.glob(os.path.join(d, "step_*.bin"))):
+        if f.endswith("step_final.bin"):
+            continue
+        s = load_step(f)
+        want = load_rows(f.replace("step_", "rows_"))
+        if s.n_bot < 512:
+            continue
+        eng.set_option("rank_hint", want.n_new)
+        assert eng.reduce(s).same_as(want), f
+        used += eng.counters()["mc_ech_combinations"] > 0
+        if want.n_new > 160:
+            eng.set_option("rank_hint", 8)
+            assert eng.reduce(s).same_as(want), f
+            rejected += eng.counters()["mc_ech_combinations"] == 0
+    assert used > 0 and rejected > 0
+    eng.set_option("mc_ech", 0)
+    eng.close()

@@ -1,10 +1,5 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-mkdir -p /tmp/sys
-python - <<'PY'
-import sys; sys.path.insert(0,'.')
-from gamba_b200 import systems
-systems.write_system('kat15-15', '/tmp/sys/kat15-15.txt')
-PY
-( time GAMBA_DEBUG_TIMERS=1 timeout 600 gamba_b200/bin/gamba -i /tmp/sys/kat15-15.txt -o /tmp/sys/k15.out0 -v 1 --max-spairs 0 ) 2>&1 | grep -E "linalg \(wall\)|overall|update .* select|dbg:|real|rror"
-md5sum /tmp/sys/k15.out0
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/tc_pytest.log 2>&1
+echo "pytest rc=$?"; tail -12 gpurun_out/tc_pytest.log
+for m in 1 0; do echo "== mc_ech=$m"; timeout 300 python tools/step_stats.py cyclic9-15 15000000 mc_ech=$m 2>&1 | grep -o 'step_[0-9]*.bin\|new [0-9]*\|elim [0-9.]* ms\|ech [0-9.]* ms' | paste - - - -; done
