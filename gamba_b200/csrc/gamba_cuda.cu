@@ -740,7 +740,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
     if (mc_rows && nr && nc) {
         // Dc = S D' on the tensor cores; the echelon then sees mc_rows rows
         McArgs ma{};
-        ma.n_rows = nr; ma.n_cols = nc; ma.ld = L.ld_dprime; ma.d = d_dprime.as<uint32_t>();
+        ma.n_rows = nr; ma.n_cols = nc; ma.ld = L.ld_dprime; ma.d = d_dprime.as<uint32_t>(); ma.row_nz = d_row_nz.as<uint32_t>();
         ma.dt = d_mc_dt.as<uint8_t>(); ma.s = d_mc_s.as<uint8_t>(); ma.dt_plane = (uint64_t)np_ * rp; ma.s_plane = (uint64_t)kp_ * rp;
         ma.rp = rp; ma.k = mc_rows; ma.nl = mnl; ma.seed = cfg.seed * 0x9e3779b97f4a7c15ull + 0x5bd1e995u * (++mc_ech_draw);
         GCU_CHECK(cudaMemsetAsync(d_mc_s.p, 0, (uint64_t)mnl * kp_ * rp, stream));

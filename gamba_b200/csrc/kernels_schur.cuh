@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256) schur_bt_kernel(BtArgs a) {
 struct McArgs {
     uint32_t n_rows, n_cols, ld;    // D' : n_rows x n_cols, pitch ld
     const uint32_t* d;
+    const uint32_t* row_nz;         // rows flagged zero are skipped (padding rows of the all-gather buffer hold stale data)
     uint8_t* dt;                    // [nl][np][rp]  limbs of D' transposed (row index contiguous)
     uint8_t* s;                     // [nl][kp][rp]  limbs of the random multipliers
     uint64_t dt_plane, s_plane;
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) mc_dt_kernel(McArgs a) {
     const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 128;
     for (uint32_t i = ty; i < 128; i += 8) {
         const uint32_t r = r0 + i, c = c0 + tx;
-        tile[i][tx] = (r < a.n_rows && c < a.n_cols) ? a.d[(uint64_t)r * a.ld + c] : 0u;
+        tile[i][tx] = (r < a.n_rows && c < a.n_cols && a.row_nz[r]) ? a.d[(uint64_t)r * a.ld + c] : 0u;
     }
     __syncthreads();
     for (uint32_t w = threadIdx.x; w < 32 * 32; w += 256) {
