@@ -1,4 +1,3 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
-python __graft_entry__.py smoke 2>&1 | tail -2
+for t in 0 3072 4096 6144; do echo "== panel_t=$t"; timeout 300 python tools/step_stats.py cyclic9-15 15000000 panel_t=$t 2>&1 | grep -o 'step_[0-9]*.bin\|T=[0-9]*\|sparse [0-9.]*' | paste - - - | awk '{s+=$4; printf "%s %s %s | ", $1,$2,$4} END {print "\nSUM sparse", s}'; done
