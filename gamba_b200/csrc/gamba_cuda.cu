@@ -146,7 +146,8 @@ struct gamba_cuda_engine {
     // whenever a step runs the sparse kernel (a ratio of counts: meaningful on small steps too), refreshed every 16 steps
     double hitw = 1;
     uint32_t since_explore = 0;
-    static double model_sparse(double nloc, double dens, double k, double a) { return nloc * dens * k * a * 0.5 / 2.1e11; }
+    // entries/s of the row-per-CTA kernel: 2.1e11 for p < 2^16, 1.3e11 above (two shared-memory REDs per entry)
+    static double model_sparse(double nloc, double dens, double k, double a, bool small) { return nloc * dens * k * a * 0.5 / (small ? 2.1e11 : 1.3e11); }
     static double model_panel(double mpad, double k, double nl, double dens, double t) {
         return mpad * k * k * 0.5 * nl * nl / 1.2e15 + k / 32.0 * (2e-6 + dens * 1.6e-5) + k / t * 4e-5;
     }
@@ -272,7 +273,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // (cyclic9: panels win 1.5-3x; kat12: 60 % dense multipliers but 86 entries per row of A, sparse wins 3x)
         bool panel_pays = opt_panel >= 2;
         if (opt_panel == 1 && have_history) {
-            const double est_sparse = hitw * model_sparse(nloc, last_density, n_top, last_a);
+            const double est_sparse = hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
             const double est_panel = model_panel((double)(mt_ * sc_bm), n_top, nl, last_density, PANEL_T);
             panel_pays = est_panel < est_sparse;
             if (panel_pays && ++since_explore >= 16) { panel_pays = false; since_explore = 0; }   // refresh hitw
