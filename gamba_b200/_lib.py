@@ -37,7 +37,8 @@ class Counters(C.Structure):
                 ("pivots_applied", C.c_uint64), ("fma_applied", C.c_uint64), ("fma_top", C.c_uint64), ("mc_combinations", C.c_uint32), ("mc_attempts", C.c_uint32),
                 ("seconds_stage_last", C.c_double), ("seconds_sparse_last", C.c_double),
                 ("seconds_schur_last", C.c_double), ("schur_macs", C.c_uint64),
-                ("mc_ech_combinations", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("mc_ech_combinations", C.c_uint32), ("solve_mode", C.c_uint32), ("dense_macs", C.c_uint64),
+                ("seconds_inverse_last", C.c_double), ("panel_t", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)

@@ -26,6 +26,7 @@
 #include "kernels_prep.cuh"
 #include "kernels_schur.cuh"
 #include "kernels_schur_tc.cuh"
+#include "kernels_tri.cuh"
 #include "layout.cuh"
 
 namespace gcu {
@@ -111,25 +112,24 @@ struct gamba_cuda_engine {
     gcu::Fp f{};
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8]{};
+    cudaEvent_t ev[10]{};
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
     int64_t opt_ctas_per_sm = 0;
     int64_t opt_elim_warps = 0;      // 4 or 8 warps per row to reduce (0 = automatic)
     int elim_warps = 8;
-    int64_t opt_echelon_mma = 1;     // 1: blocked echelon on the tensor cores, 0: per-pivot kernel
     int64_t opt_coeff_cache = 0;     // keep coefficient arrays on the device across steps (caller: immutable arrays)
     std::unordered_map<const void*, std::pair<uint64_t, uint32_t>> cache;   // host pointer -> (offset in d_pool, length)
     uint64_t cache_used = 0;
     int64_t opt_schur = 1;           // 1: D' = D + M B on the tensor cores when the limb planes fit, 0: sparse path
-    int64_t opt_schur_tc = 1;        // 1: tcgen05/TMA product kernel, 0: mma.sync version
-    int64_t opt_panel = 1;           // 1 (when it is predicted to pay) / 2 (always): blocked triangular solve - per column tile, the earlier pivots' contribution is a
-                                     //    tcgen05 product and elim_kernel only walks the tile's own windows (needs schur_tc)
+    int64_t opt_panel = 1;           // 1 (when it is predicted to pay) / 2 (always): blocked triangular solve on the tensor cores
+                                     //    (kernels_tri.cuh): per pivot tile two tcgen05 products, no walk over the rows
     bool use_panel = false;
-    uint32_t PANEL_T = 2048;         // column tile of the panel mode: ~8 KB of accumulator, every row of a step resident at once
-    int64_t opt_panel_t = 0;         // 0 = chosen per step so that the panel products fill whole waves of CTAs
-    int64_t opt_panel_max_top = 100000;   // operands of K^2 / 2 bytes per limb: a cap besides the cost estimate in choose_layout
-    gcu::DevBuf d_at, d_at_off, d_cd;
+    uint32_t PANEL_T = 2048;         // pivot tile of the blocked solve: 128 * 2^j (the inverse diagonal tiles come from recursive doubling)
+    int64_t opt_panel_t = 0;         // 0 = chosen per step from n_top
+    int64_t opt_panel_max_top = 1000000;  // operands of K^2 / 2 bytes per limb: a cap besides the memory budget and the cost estimate
+    gcu::DevBuf d_at, d_at_off, d_cd, d_cx, d_wr, d_vt, d_adt, d_gx, d_dinv;
+    double t_inv_dev = 0;            // recursive doubling of the inverse diagonal tiles (part of the elimination time)
     gcu::DevBuf d_mc_s, d_mc_dt, d_mc_dc, d_mc_nz;
     int64_t opt_mc_ech = 1;          // Monte-Carlo combinations of the rows of D' in front of the echelon (accepted with a rank margin of 32)
     uint32_t mc_ech_k = 0;           // combinations used by the last echelon (0 = it ran on the rows themselves)
@@ -148,11 +148,16 @@ struct gamba_cuda_engine {
     uint32_t since_explore = 0;
     // entries/s of the row-per-CTA kernel: 2.1e11 for p < 2^16, 1.3e11 above (two shared-memory REDs per entry)
     static double model_sparse(double nloc, double dens, double k, double a, bool small) { return nloc * dens * k * a * 0.5 / (small ? 2.1e11 : 1.3e11); }
-    static double model_panel(double mpad, double k, double nl, double dens, double t) {
-        return mpad * k * k * 0.5 * nl * nl / 1.2e15 + k / 32.0 * (2e-6 + dens * 1.6e-5) + k / t * 4e-5;
+    // blocked solve: products with the earlier tiles (K^2/2) and with the inverse diagonal tiles (K T) at the measured int8
+    // rate, the inverse tiles themselves (K T^2 / 3, small batched products: a third of the rate), zeroing / scattering the
+    // operands (bytes at ~3 TB/s), ~3 launches per tile
+    static double model_panel(double mpad, double k, double nl, double t) {
+        const double rate = 1.2e15;
+        return mpad * (k * k * 0.5 + k * t) * nl * nl / rate + k * t * t / 3.0 * nl * nl / (rate / 3) +
+               (nl * k * k * 0.5 + 3.0 * nl * k * t) / 3e12 + (3.0 * k / t + 12) * 4e-6;
     }
     bool use_schur = false, use_block = false;   // decided per staged step (plan_step)
-    int64_t opt_schur_max_gb = 64;   // budget for the Mx and Bt limb planes
+    int64_t opt_schur_max_gb = 96;   // budget for the limb-plane operands of the products
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
     int64_t opt_schur_kchunk = 0;    // k-steps between accumulator folds (0 = the exactness bound; tests lower it)
     int64_t opt_mc = 0;              // Monte-Carlo combinations instead of the rows themselves
@@ -176,7 +181,6 @@ struct gamba_cuda_engine {
     gcu::DevBuf d_dprime, d_row_nz, d_list_k, d_list_m, d_queue_stats;
     gcu::DevBuf d_em_live, d_em_xa, d_em_pbt;
     gcu::DevBuf d_mx, d_bt, d_mt;
-    bool bt_built = false;
     double t_sparse_dev = 0, t_schur_dev = 0;
     gcu::DevBuf d_lead, d_nz_list, d_piv_row, d_piv_col, d_is_piv, d_counts, d_out_ptr, d_out_col, d_out_val;
     uint32_t n_local = 0, n_local_max = 0, n_gather_rows = 0;
@@ -254,39 +258,27 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // row-per-CTA kernel, which only touches the pivot rows a row needs, is faster (tools/blk_variants.sh).
         use_block = use_schur && !opt_mc && (opt_block >= 2 || (opt_block == 1 && n_top >= 32768 && last_density >= 0.5));
         if (use_block) tmax = BLK_TMAX;
-        // Panel mode: tiles of PANEL_T columns; operands of panel t: [nl][PANEL_T][t * PANEL_T] bytes, K^2/2 * nl in total
+        // Blocked solve on the tensor cores (kernels_tri.cuh): pivot tiles of PANEL_T = 128 * 2^j columns. Operands: At_t
+        // [nl][T][t T] per tile (K^2/2 * nl bytes in total), the inverse diagonal tiles and their scratch (3.25 * nl * K * T)
         use_panel = false;
         if (opt_panel_t > 0) PANEL_T = (uint32_t)opt_panel_t;
-        else {      // m_tiles x (T / BN) output tiles per panel product: pick T in [1024, 3072] that fills whole waves of SMs
-            const uint32_t bn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN, sms = (uint32_t)prop.multiProcessorCount;
-            double best = -1;
-            for (uint32_t T = 1024; T <= 3072; T += 128) {
-                const uint64_t tiles = mt_ * (T / bn);
-                const double eff = (double)tiles / (double)((tiles + sms - 1) / sms * sms);
-                if (eff >= best - 1e-9) { best = eff; PANEL_T = T; }
-            }
-        }
-        // Panel or sparse? The products cost n_bot K^2 / 2 dense multiply-adds whatever the matrix holds, the sparse kernel
-        // only touches the pivot rows a row hits: predicted from the previous step (F4 steps change slowly) with measured
-        // rates (tools/step_stats.py on cyclic9-15 / kat12-15): row-per-CTA kernel 2.1e11 entries/s, products 1.2e15 int8
-        // multiply-adds/s, a window of the walk 2 us + 0.5 us per pivot it hits, ~40 us per panel
-        // (cyclic9: panels win 1.5-3x; kat12: 60 % dense multipliers but 86 entries per row of A, sparse wins 3x)
+        else PANEL_T = n_top >= 12288 ? 2048u : n_top >= 3072 ? 1024u : 512u;
+        // Blocked solve or sparse kernels? The products cost n_bot K^2 / 2 dense multiply-adds whatever the matrix holds, the
+        // sparse kernel only touches the pivot rows a row hits: predicted from the previous step (F4 steps change slowly)
+        // with measured rates: row-per-CTA kernel 2.1e11 entries/s (1.3e11 for p >= 2^16), products 1.2e15 int8 multiply-adds/s
         bool panel_pays = opt_panel >= 2;
         if (opt_panel == 1 && have_history) {
             const double est_sparse = hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
-            const double est_panel = model_panel((double)(mt_ * sc_bm), n_top, nl, last_density, PANEL_T);
+            const double est_panel = model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T);
             panel_pays = est_panel < est_sparse;
             if (panel_pays && ++since_explore >= 16) { panel_pays = false; since_explore = 0; }   // refresh hitw
         }
-        if (use_schur && opt_schur_tc && panel_pays && !opt_mc && opt_block < 2 && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
-            const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T;
-            const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2);
-            if (at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kp <= (double)opt_schur_max_gb * 1e9) {
+        if (use_schur && panel_pays && !opt_mc && opt_block < 2 && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
+            const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T, kt_ = ntp_ * PANEL_T;
+            const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2) + 3.25 * nl * (double)kt_ * PANEL_T;
+            const uint64_t kpp = kt_;
+            if (at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kpp + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9) {
                 use_panel = true; use_block = false; tmax = PANEL_T;
-                // little work per window, and every row of the step should be resident at once (the walk is a chain of
-                // dependent steps): 2 warps per row when more than 9 rows per SM are wanted (48-56 registers per thread)
-                elim_warps = 4;     // 2 warps per row (every row resident) measured no faster: tools/tc_check.sh
-                if (opt_elim_warps == 2 || opt_elim_warps == 4 || opt_elim_warps == 8) elim_warps = (int)opt_elim_warps;
             }
         }
     }
@@ -315,7 +307,7 @@ struct StepHdr { uint32_t n_top, n_bot, n_cols, n_arr; uint64_t nnz, pool_len, n
 
 void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     const double t0 = wall_s();
-    staged = false; eliminated = false; bt_built = false;
+    staged = false; eliminated = false;
     const bool use_bcast = cfg.world_size > 1 && bcast_fn != nullptr;
     const bool have = !use_bcast || cfg.rank == 0;       // this rank uploads the step from its host buffers
     if (have && !in) throw std::runtime_error("no step passed (only ranks > 0 of a broadcasting group may pass NULL)");
@@ -435,6 +427,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     d_seg.ensure(n_cnt * sizeof(uint32_t));
     d_ent.ensure((nnz + 1ull * n_rows * L.n_tiles + 4) * sizeof(uint2));   // segments padded to an even number of entries
     d_diag.ensure(n_diag * sizeof(uint32_t));
+    d_dinv.ensure(n_diag * sizeof(uint32_t));
     d_dnz.ensure(std::max<uint32_t>(L.n_windows, 1) * sizeof(uint32_t));
     d_first.ensure((std::max<uint32_t>(L.n_bot, 1) + 1) * sizeof(uint32_t));
     dbg_[3] += wall_s() - tq; tq = wall_s();
@@ -447,7 +440,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     pa.row_ptr = d_row_ptr.as<uint64_t>(); pa.col = d_col.as<uint32_t>(); pa.coeff_id = d_coeff_id.as<uint32_t>();
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
     pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
-    pa.diag = d_diag.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
+    pa.diag = d_diag.as<uint32_t>(); pa.dinv = d_dinv.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
     pa.row_src = hd.has_row_src ? d_row_src.as<uint64_t>() : nullptr;
     pa.col_map = hd.col_map_len ? d_col_map.as<uint32_t>() : nullptr;
     pa.first_piv = d_first.as<uint32_t>(); pa.first_min = d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1);
@@ -494,6 +487,21 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     staged = true;
 }
 
+// One launch of the limb-split tensor-core product (kernels_schur_tc.cuh)
+template <int EPI>
+static void launch_limb_gemm(bool small, const CUtensorMap& ma, const CUtensorMap& mb, const gcu::TcArgs& ta, uint32_t batches, cudaStream_t st) {
+    using namespace gcu;
+    const dim3 grid(ta.m_tiles * ta.n_tiles, std::max(1u, batches));
+    if (small) {
+        GCU_CHECK(cudaFuncSetAttribute(limb_gemm_tc_kernel<2, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
+        limb_gemm_tc_kernel<2, EPI><<<grid, TC_THREADS, tc_smem_bytes<2>(), st>>>(ma, mb, ta);
+    } else {
+        GCU_CHECK(cudaFuncSetAttribute(limb_gemm_tc_kernel<4, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
+        limb_gemm_tc_kernel<4, EPI><<<grid, TC_THREADS, tc_smem_bytes<4>(), st>>>(ma, mb, ta);
+    }
+    GCU_CHECK(cudaGetLastError());
+}
+
 void gamba_cuda_engine::eliminate() {
     if (!staged) throw std::runtime_error("no staged step");
     const uint32_t world = std::max(1u, cfg.world_size), rank = cfg.rank;
@@ -509,17 +517,27 @@ void gamba_cuda_engine::eliminate() {
     auto kern = elim_warps == 2 ? (f.small ? elim_kernel<true, 2> : elim_kernel<false, 2>)
               : elim_warps == 4 ? (f.small ? elim_kernel<true, 4> : elim_kernel<false, 4>)
                                 : (f.small ? elim_kernel<true, 8> : elim_kernel<false, 8>);
-    GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, elim_threads, smem));
-    if (occ < 1) throw std::runtime_error("elimination kernel does not fit on an SM");
-    if (opt_ctas_per_sm > 0) occ = std::min<int>(occ, (int)opt_ctas_per_sm);
-    elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
+    const uint32_t nl = f.small ? 2u : 4u;
+    const uint32_t bn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN;
+    const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
+    const uint32_t kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
+    const bool schur = use_schur && n_local;
+    const bool block = schur && use_block;
+    const bool panel = schur && use_panel;
+    elim_grid = 1;
+    if (!panel) {
+        GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, elim_threads, smem));
+        if (occ < 1) throw std::runtime_error("elimination kernel does not fit on an SM");
+        if (opt_ctas_per_sm > 0) occ = std::min<int>(occ, (int)opt_ctas_per_sm);
+        elim_grid = std::max(1, std::min<int>(prop.multiProcessorCount * occ, (int)std::max(1u, n_local)));
+    }
     const uint64_t n_slots = (uint64_t)elim_grid;
 
     d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.ld_dprime, 1) * sizeof(uint32_t));
     d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
-    if (!(use_schur && (use_block || use_panel))) {     // the blocked kernel keeps its multipliers in d_mt, the panel mode needs no lists
+    if (!(schur && (block || panel))) {     // the blocked kernel keeps its multipliers in d_mt, the blocked solve needs no lists
         d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
         d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
     }
@@ -537,7 +555,7 @@ void gamba_cuda_engine::eliminate() {
     ea.negp = 0u - f.p;
     // every add is < 2p (p < 2^16, lazy Barrett) or < 2^16 (lo/hi halves): normalise before 2^32 is reached
     ea.norm_every = f.small ? (uint32_t)std::min<uint64_t>(0xffffffffull / (2ull * f.p) - 8 * 32 - 2, 1u << 30) : 65536u - 8 * 32 - 2;
-    ea.seg = d_seg.as<uint32_t>(); ea.ent = d_ent.as<uint2>(); ea.diag = d_diag.as<uint32_t>();
+    ea.seg = d_seg.as<uint32_t>(); ea.ent = d_ent.as<uint2>(); ea.diag = d_dinv.as<uint32_t>();
     ea.dnz = d_dnz.as<uint32_t>();
     ea.first_piv = d_first.as<uint32_t>();
     ea.dprime = dloc; ea.row_nz = nzloc;
@@ -551,88 +569,124 @@ void gamba_cuda_engine::eliminate() {
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
     ea.t_lo = 0; ea.t_hi = L.n_tiles;
 
-    // Schur mode: the B half of the elimination is a dense product on the tensor cores (kernels_schur.cuh)
-    const uint32_t nl = f.small ? 2u : 4u;
-    const uint32_t sc_bm = f.small ? schur_bm<2>() : schur_bm<4>(), sc_bn = f.small ? schur_bn<2>() : schur_bn<4>();
-    const uint32_t kp = (L.n_top + SC_BK - 1) / SC_BK * SC_BK;
+    // Schur mode: the B half of the elimination is a dense product on the tensor cores (kernels_schur_tc.cuh).
+    // k pitch of the limb planes: n_top rounded up to 128 bytes, or to whole pivot tiles for the blocked solve
+    const uint32_t T = PANEL_T, ntp = L.n_tiles_piv;
+    const uint32_t kt = ntp * T;                                    // blocked solve: pivot range padded to whole tiles
+    const uint32_t kp = panel ? kt : (L.n_top + TC_BK - 1) / TC_BK * TC_BK;
+    const uint32_t k_used = (L.n_top + TC_BK - 1) / TC_BK * TC_BK;   // contraction depth of the Schur product
     const uint32_t mp = (n_local + 127u) / 128u * 128u, np = (L.n_nonpiv + 127u) / 128u * 128u;   // rows per limb plane
-    const uint32_t m_tiles = mp / sc_bm, n_tiles = np / sc_bn;
     const uint64_t mx_plane = (uint64_t)mp * kp, bt_plane = (uint64_t)np * kp;
-    const bool schur = use_schur && n_local;
-    const bool block = schur && use_block;
-    const bool panel = schur && use_panel;
+    const uint64_t tri_plane = (uint64_t)kt * T;
     // buffers first: growing one may go to the driver, which must not sit inside the event-timed region
     if (schur) {
         d_mx.ensure(nl * mx_plane);
-        if (!bt_built) d_bt.ensure(nl * bt_plane);
-        if (panel) {     // operands of the panel products: tile t takes [nl][T][t * T] bytes
-            if (!bt_built) {
-                at_off.assign(L.n_tiles_piv + 1, 0);
-                for (uint32_t t = 1; t <= L.n_tiles_piv; ++t) at_off[t] = at_off[t - 1] + (t > 1 ? (uint64_t)nl * PANEL_T * (uint64_t)(t - 1) * PANEL_T : 0);
-                at_bytes = at_off[L.n_tiles_piv];
-                d_at.ensure(std::max<uint64_t>(at_bytes, 16));
-                d_at_off.ensure(at_off.size() * sizeof(uint64_t));
-            }
-            d_cd.ensure((uint64_t)mp * PANEL_T * sizeof(uint32_t));
-            d_mt.ensure((uint64_t)(L.n_tiles + 2) * sizeof(uint32_t));              // one row-queue counter per launch
+        d_bt.ensure(nl * bt_plane);
+        if (panel) {     // operands of the products with the earlier tiles: tile t takes [nl][T][t * T] bytes
+            at_off.assign(ntp + 1, 0);
+            for (uint32_t t = 1; t <= ntp; ++t) at_off[t] = at_off[t - 1] + (t > 1 ? (uint64_t)nl * T * (uint64_t)(t - 1) * T : 0);
+            at_bytes = at_off[ntp];
+            d_at.ensure(std::max<uint64_t>(at_bytes, 16));
+            d_at_off.ensure(at_off.size() * sizeof(uint64_t));
+            d_cd.ensure((uint64_t)mp * T * sizeof(uint32_t));
+            d_cx.ensure((uint64_t)nl * mp * T);
+            d_wr.ensure(nl * tri_plane); d_vt.ensure(nl * tri_plane); d_adt.ensure(nl * tri_plane);
+            d_gx.ensure(std::max<uint64_t>(nl * tri_plane / 4, 16));
         }
     }
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (schur) {
+        // operands of the products, rebuilt for every reduction of the step (they are part of the algorithm, not of the hand-over)
         GCU_CHECK(cudaMemsetAsync(d_mx.p, 0, nl * mx_plane, stream));
         ea.mx = d_mx.as<uint8_t>(); ea.mx_plane = mx_plane; ea.mx_kp = kp; ea.mx_nl = nl;
-        if (!bt_built) {
-            GCU_CHECK(cudaMemsetAsync(d_bt.p, 0, nl * bt_plane, stream));
-            BtArgs ba{};
-            ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
-            ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
-            if (panel) {
-                GCU_CHECK(cudaMemsetAsync(d_at.p, 0, std::max<uint64_t>(at_bytes, 16), stream));
-                GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-                ba.at = d_at.as<uint8_t>(); ba.at_off = d_at_off.as<uint64_t>();
-            }
-            schur_bt_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(ba);
-            GCU_CHECK(cudaGetLastError());
-            ctr.kernel_launches += 1;
-            bt_built = true;
+        GCU_CHECK(cudaMemsetAsync(d_bt.p, 0, nl * bt_plane, stream));
+        BtArgs ba{};
+        ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
+        ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
+        if (panel) {
+            GCU_CHECK(cudaMemsetAsync(d_at.p, 0, std::max<uint64_t>(at_bytes, 16), stream));
+            GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+            ba.at = d_at.as<uint8_t>(); ba.at_off = d_at_off.as<uint64_t>();
+            GCU_CHECK(cudaMemsetAsync(d_adt.p, 0, nl * tri_plane, stream));
+            GCU_CHECK(cudaMemsetAsync(d_wr.p, 0, nl * tri_plane, stream));
+            GCU_CHECK(cudaMemsetAsync(d_vt.p, 0, nl * tri_plane, stream));
+            ba.adt = d_adt.as<uint8_t>(); ba.adt_plane = tri_plane;
         }
+        schur_bt_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(ba);
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 1;
     }
     GCU_CHECK(cudaEventRecord(ev[6], stream));
     if (panel) {
-        // Blocked triangular solve: per pivot tile t, what the pivots of the earlier tiles add to the rows is a tcgen05
-        // product cd = M[:, < t T] * A[< t T, tile t]; elim_kernel then only walks the windows of tile t.
-        const uint32_t ntp = L.n_tiles_piv, T = PANEL_T;
-        const uint32_t bn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN;
-        GCU_CHECK(cudaMemsetAsync(d_mt.p, 0, (uint64_t)(L.n_tiles + 2) * sizeof(uint32_t), stream));
+        // ---- blocked triangular solve on the tensor cores (kernels_tri.cuh) ----
+        // 1. inverse diagonal tiles: 128 x 128 blocks on the CUDA cores, then recursive doubling as batched products
+        {
+            TriBaseArgs tb{};
+            tb.L = L; tb.f = f; tb.seg = d_seg.as<uint32_t>(); tb.ent = d_ent.as<uint2>(); tb.diag = d_diag.as<uint32_t>();
+            tb.wr = d_wr.as<uint8_t>(); tb.vt = d_vt.as<uint8_t>(); tb.plane = tri_plane; tb.kt = kt; tb.nl = nl;
+            const size_t tb_smem = (size_t)(TRI_BASE * (TRI_BASE + 1) + TRI_BASE) * sizeof(uint32_t);
+            GCU_CHECK(cudaFuncSetAttribute(tri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+            tri_base_kernel<<<kt / TRI_BASE, TRI_BASE, tb_smem, stream>>>(tb);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 1;
+        }
+        const CUtensorMap map_wr = make_tmap_u8(d_wr.p, T, (uint64_t)nl * kt, TC_BK, TC_BM);
+        const CUtensorMap map_vt = make_tmap_u8(d_vt.p, T, (uint64_t)nl * kt, TC_BK, bn);
+        const CUtensorMap map_adt = make_tmap_u8(d_adt.p, T, (uint64_t)nl * kt, TC_BK, bn);
+        for (uint32_t s = TRI_BASE; s < T; s *= 2) {
+            const uint32_t nb = kt / (2 * s);
+            const CUtensorMap map_gx = make_tmap_u8(d_gx.p, s, (uint64_t)nl * (kt / 2), TC_BK, TC_BM);
+            TcArgs ga{};          // G = P' Q
+            ga.f = f; ga.mp = kt; ga.np = kt; ga.n_rows = s; ga.n_cols = s; ga.m_tiles = s / TC_BM; ga.n_tiles = s / bn;
+            ga.kchunk = tkc; ga.k_end = s; ga.k_mod = T;
+            ga.a_row0 = 0; ga.a_row_b = 2 * s; ga.a_k0 = 0; ga.a_k_b = 2 * s;
+            ga.b_row0 = s; ga.b_row_b = 2 * s; ga.b_k0 = 0; ga.b_k_b = 2 * s;
+            ga.o1 = d_gx.as<uint8_t>(); ga.o1_plane = (uint64_t)(kt / 2) * s; ga.o1_ld = s; ga.o1_row_b = s;
+            launch_limb_gemm<EPI_LIMBS>(f.small != 0, map_wr, map_adt, ga, nb, stream);
+            TcArgs ha{};          // H = -(G R'), written into Wr and (transposed) Vt
+            ha.f = f; ha.mp = kt / 2; ha.np = kt; ha.n_rows = s; ha.n_cols = s; ha.m_tiles = s / TC_BM; ha.n_tiles = s / bn;
+            ha.kchunk = tkc; ha.k_end = s; ha.k_mod = T; ha.neg = 1;
+            ha.a_row0 = 0; ha.a_row_b = s; ha.a_k0 = 0; ha.a_k_b = 0;
+            ha.b_row0 = s; ha.b_row_b = 2 * s; ha.b_k0 = s; ha.b_k_b = 2 * s;
+            ha.o1 = d_wr.as<uint8_t>(); ha.o1_plane = tri_plane; ha.o1_ld = T; ha.o1_row0 = 0; ha.o1_row_b = 2 * s; ha.o1_col0 = s; ha.o1_col_b = 2 * s;
+            ha.o2 = d_vt.as<uint8_t>(); ha.o2_plane = tri_plane; ha.o2_ld = T; ha.o2_row0 = s; ha.o2_row_b = 2 * s; ha.o2_col0 = 0; ha.o2_col_b = 2 * s;
+            launch_limb_gemm<EPI_LIMBS>(f.small != 0, map_gx, map_vt, ha, nb, stream);
+            ctr.kernel_launches += 2;
+        }
+        GCU_CHECK(cudaEventRecord(ev[8], stream));
+        // 2. tile by tile: cd = C_t + M[:, < tT] A[< tT, tile t], then M[:, tile t] = -cd Inv_t
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
-        ea.panel = 1; ea.cd_ld = T;
-        for (uint32_t t = 0; t <= ntp; ++t) {
-            if (t > 0 && t < ntp) {
-                GCU_CHECK(cudaMemsetAsync(d_cd.p, 0, (uint64_t)n_local * T * sizeof(uint32_t), stream));
-                TcArgs ta{};
-                const uint32_t tw = lay_tile_width(L, t);
-                ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = T; ta.n_rows = n_local; ta.n_cols = tw; ta.ld = T;
-                ta.d = d_cd.as<uint32_t>(); ta.row_nz = nullptr; ta.m_tiles = mp / TC_BM; ta.n_tiles = (tw + bn - 1) / bn;
-                ta.first_piv = d_first.as<uint32_t>(); ta.k_first = 0; ta.row_begin = rank; ta.row_step = world;
-                const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
-                ta.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
-                ta.k_end = t * T;
-                const CUtensorMap map_at = make_tmap_u8(d_at.as<uint8_t>() + at_off[t], (uint64_t)t * T, (uint64_t)nl * T, TC_BK, bn);
-                if (f.small) {
-                    GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
-                    schur_tc_kernel<2><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<2>(), stream>>>(map_mx, map_at, ta);
-                } else {
-                    GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
-                    schur_tc_kernel<4><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<4>(), stream>>>(map_mx, map_at, ta);
-                }
-                GCU_CHECK(cudaGetLastError());
-                ctr.kernel_launches += 1;
-            }
-            // t < ntp: the windows of pivot tile t; t == ntp: the non-pivot tiles (D scattered into D')
-            ea.t_lo = t; ea.t_hi = t < ntp ? t + 1 : L.n_tiles;
-            ea.cd = (t > 0 && t < ntp) ? d_cd.as<uint32_t>() : nullptr;
-            ea.queue = d_mt.as<uint32_t>() + t;
-            kern<<<elim_grid, elim_threads, smem, stream>>>(ea);
+        const CUtensorMap map_cx = make_tmap_u8(d_cx.p, T, (uint64_t)nl * mp, TC_BK, TC_BM);
+        TriRowsArgs ra{};
+        ra.L = L; ra.seg = d_seg.as<uint32_t>(); ra.ent = d_ent.as<uint2>(); ra.row_begin = rank; ra.row_step = world; ra.n_local = n_local;
+        for (uint32_t t = 0; t < ntp; ++t) {
+            const uint32_t tw = lay_tile_width(L, t);
+            ra.dst = d_cd.as<uint32_t>(); ra.ld = T; ra.width = T; ra.t_lo = t; ra.t_hi = t + 1; ra.col_base = t * T; ra.n_pad = mp;
+            tri_rows_kernel<<<mp, 128, 0, stream>>>(ra);
+            GCU_CHECK(cudaGetLastError());
+            TcArgs ta{};
+            ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = T; ta.n_rows = n_local; ta.n_cols = tw; ta.ld = T;
+            ta.d = d_cd.as<uint32_t>(); ta.m_tiles = mp / TC_BM; ta.n_tiles = T / bn;
+            ta.first_piv = d_first.as<uint32_t>(); ta.row_begin = rank; ta.row_step = world;
+            ta.kchunk = kchunk; ta.k_end = t * T;
+            ta.o1 = d_cx.as<uint8_t>(); ta.o1_plane = (uint64_t)mp * T; ta.o1_ld = T;
+            const CUtensorMap map_at = t ? make_tmap_u8(d_at.as<uint8_t>() + at_off[t], (uint64_t)t * T, (uint64_t)nl * T, TC_BK, bn) : map_vt;
+            launch_limb_gemm<EPI_RMW_LIMBS>(f.small != 0, map_mx, map_at, ta, 1, stream);
+            TcArgs xa{};
+            xa.f = f; xa.mp = mp; xa.np = kt; xa.n_rows = n_local; xa.n_cols = tw; xa.m_tiles = mp / TC_BM; xa.n_tiles = (tw + bn - 1) / bn;
+            xa.first_piv = d_first.as<uint32_t>(); xa.row_begin = rank; xa.row_step = world;
+            xa.kmin_sub = t * T; xa.skip_hi = (t + 1) * T;
+            xa.kchunk = tkc; xa.k_end = (tw + TC_BK - 1) / TC_BK * TC_BK;
+            xa.b_row0 = t * T; xa.neg = 1;
+            xa.o1 = d_mx.as<uint8_t>(); xa.o1_plane = mx_plane; xa.o1_ld = kp; xa.o1_col0 = t * T;
+            xa.stats = ea.stats; xa.cnt_row_ptr = d_row_ptr.as<uint64_t>();
+            launch_limb_gemm<EPI_LIMBS>(f.small != 0, map_cx, map_vt, xa, 1, stream);
+            ctr.kernel_launches += 3;
+        }
+        // 3. D scattered into D' (the product below adds M B)
+        if (L.n_nonpiv) {
+            ra.dst = dloc; ra.ld = L.ld_dprime; ra.width = L.ld_dprime; ra.t_lo = ntp; ra.t_hi = L.n_tiles; ra.col_base = L.n_top; ra.n_pad = n_local;
+            tri_rows_kernel<<<n_local, 128, 0, stream>>>(ra);
             GCU_CHECK(cudaGetLastError());
             ctr.kernel_launches += 1;
         }
@@ -663,45 +717,29 @@ void gamba_cuda_engine::eliminate() {
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 1;
     }
+    if (!panel) GCU_CHECK(cudaEventRecord(ev[8], stream));
     GCU_CHECK(cudaEventRecord(ev[7], stream));
     if (schur) {
-        SchurArgs sa{};
-        sa.f = f; sa.mx = d_mx.as<uint8_t>(); sa.bt = d_bt.as<uint8_t>(); sa.mx_plane = mx_plane; sa.bt_plane = bt_plane;
-        sa.kp = kp; sa.n_rows = n_local; sa.n_cols = L.n_nonpiv; sa.ld = L.ld_dprime;
-        sa.d = dloc; sa.row_nz = nzloc; sa.m_tiles = m_tiles; sa.n_tiles = n_tiles;
-        sa.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); sa.k_first = ea.mc_first;
-        sa.row_begin = rank; sa.row_step = world;
-        const uint32_t kc_max = f.small ? schur_kchunk<2>() : schur_kchunk<4>();
-        sa.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, kc_max) : kc_max;
-        if (opt_schur_tc) {
-            // tcgen05 + TMA version (kernels_schur_tc.cuh): the limb planes as 2-D byte tensors [NL * rows][kp]
-            TcArgs ta{};
-            ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = np; ta.n_rows = n_local; ta.n_cols = L.n_nonpiv; ta.ld = L.ld_dprime;
-            ta.d = dloc; ta.row_nz = nzloc; ta.m_tiles = mp / TC_BM; ta.n_tiles = np / (f.small ? TcCfg<2>::BN : TcCfg<4>::BN);
-            ta.first_piv = sa.first_piv; ta.k_first = sa.k_first; ta.row_begin = rank; ta.row_step = world;
-            const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
-            ta.kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
-            ta.k_end = kp;
-            CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
-            CUtensorMap map_bt = make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, f.small ? TcCfg<2>::BN : TcCfg<4>::BN);
-            if (f.small) {
-                GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
-                schur_tc_kernel<2><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<2>(), stream>>>(map_mx, map_bt, ta);
-            } else {
-                GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
-                schur_tc_kernel<4><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<4>(), stream>>>(map_mx, map_bt, ta);
-            }
-        } else if (f.small) {
-            GCU_CHECK(cudaFuncSetAttribute(schur_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem<2>()));
-            schur_mma_kernel<2><<<m_tiles * n_tiles, schur_threads<2>(), schur_smem<2>(), stream>>>(sa);
-        } else {
-            GCU_CHECK(cudaFuncSetAttribute(schur_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem<4>()));
-            schur_mma_kernel<4><<<m_tiles * n_tiles, schur_threads<4>(), schur_smem<4>(), stream>>>(sa);
-        }
-        GCU_CHECK(cudaGetLastError());
+        // D' = D + M B (kernels_schur_tc.cuh): the limb planes as 2-D byte tensors [NL * rows][kp]
+        TcArgs ta{};
+        ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = np; ta.n_rows = n_local; ta.n_cols = L.n_nonpiv; ta.ld = L.ld_dprime;
+        ta.d = dloc; ta.row_nz = nzloc; ta.m_tiles = mp / TC_BM; ta.n_tiles = np / bn;
+        ta.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); ta.k_first = ea.mc_first; ta.row_begin = rank; ta.row_step = world;
+        ta.kchunk = kchunk; ta.k_end = k_used;
+        const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
+        const CUtensorMap map_bt = make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, bn);
+        launch_limb_gemm<EPI_RMW>(f.small != 0, map_mx, map_bt, ta, 1, stream);
         ctr.kernel_launches += 1;
         ctr.schur_macs = (uint64_t)n_local * L.n_top * L.n_nonpiv;
-    } else ctr.schur_macs = 0;
+        // every dense product of the stage, in mod-p multiply-adds (x nl^2 = int8 multiply-adds on the tensor cores)
+        ctr.dense_macs = ctr.schur_macs;
+        if (panel) {
+            double m = 0;
+            for (uint32_t t = 0; t < ntp; ++t) m += (double)mp * T * ((double)t * T + T);
+            for (uint32_t s = TRI_BASE; s < T; s *= 2) m += 2.0 * (double)(kt / (2 * s)) * s * s * s;
+            ctr.dense_macs += (uint64_t)m;
+        }
+    } else { ctr.schur_macs = 0; ctr.dense_macs = 0; }
     GCU_CHECK(cudaEventRecord(ev[3], stream));
     eliminated = true;
 }
@@ -759,14 +797,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
         ta.kchunk = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK; ta.k_end = rp;
         const CUtensorMap map_s = make_tmap_u8(d_mc_s.p, rp, (uint64_t)mnl * kp_, TC_BK, TC_BM);
         const CUtensorMap map_dt = make_tmap_u8(d_mc_dt.p, rp, (uint64_t)mnl * np_, TC_BK, mbn);
-        if (f.small) {
-            GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<2>()));
-            schur_tc_kernel<2><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<2>(), stream>>>(map_s, map_dt, ta);
-        } else {
-            GCU_CHECK(cudaFuncSetAttribute(schur_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<4>()));
-            schur_tc_kernel<4><<<ta.m_tiles * ta.n_tiles, TC_THREADS, tc_smem_bytes<4>(), stream>>>(map_s, map_dt, ta);
-        }
-        GCU_CHECK(cudaGetLastError());
+        launch_limb_gemm<EPI_RMW>(f.small != 0, map_s, map_dt, ta, 1, stream);
         ctr.kernel_launches += 3;
         nr = mc_rows; ech_d = d_mc_dc.as<uint32_t>(); ech_nz = d_mc_nz.as<uint32_t>();
     }
@@ -784,7 +815,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
         ea.piv_row = d_piv_row.as<uint32_t>(); ea.piv_col = d_piv_col.as<uint32_t>();
         ea.is_piv_col = d_is_piv.as<uint8_t>(); ea.counts = d_counts.as<uint32_t>();
         ea.out_ptr = d_out_ptr.as<uint64_t>();
-        if (opt_echelon_mma) {
+        {
             // blocked Gauss-Jordan, trailing updates on the tensor cores (kernels_echelon_mma.cuh)
             const uint32_t nl = f.small ? 2u : 4u;
             const uint32_t ncp = (nc + EM_CW - 1) / EM_CW * EM_CW;
@@ -807,13 +838,6 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
             if (occ < 1) throw std::runtime_error("tensor-core echelon kernel does not fit on an SM");
             void* args[] = {&em};
             GCU_CHECK(cudaLaunchCooperativeKernel(kern, dim3(prop.multiProcessorCount), dim3(EM_THREADS), args, EM_SMEM, stream));
-        } else {
-        int occ = 0;
-        GCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, echelon_kernel, ECH_THREADS, 0));
-        if (occ < 1) throw std::runtime_error("echelon kernel does not fit on an SM");
-        const int grid = prop.multiProcessorCount * std::min(occ, 1);
-        void* args[] = {&ea};
-        GCU_CHECK(cudaLaunchCooperativeKernel((void*)echelon_kernel, dim3(grid), dim3(ECH_THREADS), args, 0, stream));
         }
         ctr.kernel_launches += 1;
         h_misc.ensure(64);
@@ -853,11 +877,16 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
     float ms = 0;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[3])); t_elim_dev = ms * 1e-3;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[6], ev[7])); t_sparse_dev = ms * 1e-3;
+    GCU_CHECK(cudaEventElapsedTime(&ms, ev[6], ev[8])); t_inv_dev = (use_schur && use_panel && n_local) ? ms * 1e-3 : 0.0;
+    ctr.seconds_inverse_last = t_inv_dev;
+    ctr.solve_mode = (use_schur && n_local) ? (use_panel ? 2u : use_block ? 1u : 0u) : 0u;
+    ctr.panel_t = ctr.solve_mode == 2 ? PANEL_T : 0u;
     t_schur_dev = t_elim_dev - t_sparse_dev;
     ctr.seconds_sparse_last = t_sparse_dev; ctr.seconds_schur_last = t_schur_dev;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[4], ev[5])); t_ech_dev = ms * 1e-3;
     ctr.pivots_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[0];
     ctr.fma_applied = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[1];
+    if (ctr.solve_mode == 2) ctr.fma_applied = ctr.dense_macs - ctr.schur_macs;      // the solve is dense: what the products did
     ctr.fma_top = reinterpret_cast<unsigned long long*>(h_misc.as<char>() + 16)[2];
     if (n_local && L.n_top && !mc_k) {
         last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top); last_a = cur_a; have_history = true;
@@ -906,7 +935,7 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
         // Monte-Carlo combinations in front of the echelon: K = predicted rank + margin combinations of the rows of D'
         // instead of the rows (most of which reduce to zero); accepted only if K - rank >= 32, else the rows themselves
         uint32_t kk = 0;
-        if (opt_mc_ech && opt_schur_tc && !mc_k && !(flags & GAMBA_CUDA_STEP_FINAL) && last_rank >= 0 && n_gather_rows >= 512 && L.n_nonpiv) {
+        if (opt_mc_ech && !mc_k && !(flags & GAMBA_CUDA_STEP_FINAL) && last_rank >= 0 && n_gather_rows >= 512 && L.n_nonpiv) {
             const uint32_t want = ((uint32_t)(last_rank + 32 + last_rank / 8) + 127u) / 128u * 128u;
             if ((uint64_t)want * 2 <= n_gather_rows) kk = want;
         }
@@ -1049,13 +1078,11 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         if (k == "tile_cols") e->opt_tile_cols = value;
         else if (k == "ctas_per_sm") e->opt_ctas_per_sm = value;
         else if (k == "elim_warps") e->opt_elim_warps = value;
-        else if (k == "echelon_mma") e->opt_echelon_mma = value;
         else if (k == "coeff_cache") { e->opt_coeff_cache = value; e->cache.clear(); e->cache_used = 0; }
         else if (k == "schur") e->opt_schur = value;
         else if (k == "block") e->opt_block = value;
-        else if (k == "schur_tc") e->opt_schur_tc = value;
         else if (k == "panel") e->opt_panel = value;
-        else if (k == "panel_t") { if (value && (value < 128 || value % 128 || value > 8192)) throw std::runtime_error("panel_t must be a multiple of 128 in [128, 8192]"); e->opt_panel_t = value; }
+        else if (k == "panel_t") { if (value && (value < 128 || value > 8192 || (value & (value - 1)))) throw std::runtime_error("panel_t must be 128 * 2^j, at most 8192"); e->opt_panel_t = value; }
         else if (k == "panel_max_top") e->opt_panel_max_top = value;
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;

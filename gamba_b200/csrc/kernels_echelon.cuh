@@ -84,121 +84,6 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t* sh) {
     return v;
 }
 
-constexpr int ECH_GROUP = 128;                       // threads that update one row together
-constexpr int ECH_GROUPS = ECH_THREADS / ECH_GROUP;
-
-__device__ __forceinline__ void group_bar(uint32_t grp) {
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(ECH_GROUP) : "memory");
-}
-
-__global__ void __launch_bounds__(ECH_THREADS, 1) echelon_kernel(EchArgs a) {
-    cg::grid_group grid = cg::this_grid();
-    __shared__ uint64_t sh64[32];
-    __shared__ uint32_t sh32[32];
-    __shared__ uint32_t sh_grp[ECH_GROUPS][4];
-    const uint32_t tid = threadIdx.x, nb = gridDim.x, bid = blockIdx.x;
-    const uint32_t grp = tid / ECH_GROUP, gt = tid % ECH_GROUP, gw = gt >> 5;
-    const uint32_t nr = a.n_rows, nc = a.n_cols, p = a.f.p;
-    uint32_t* lead0 = a.lead;
-    uint32_t* lead1 = a.lead + nr;
-
-    // leads of the rows (block per row), the inverse of every lead value, the list of non-zero rows
-    for (uint32_t r = bid; r < nr; r += nb) {
-        uint32_t l = ECH_INF;
-        if (a.row_nz[r]) {
-            const uint32_t* row = a.d + (uint64_t)r * a.ld;
-            for (uint32_t j0 = 0; j0 < nc && l == ECH_INF; j0 += ECH_THREADS) {
-                const uint32_t j = j0 + tid;
-                l = block_min_u32(j < nc && row[j] ? j : ECH_INF, sh32);
-            }
-            if (tid == 0 && l != ECH_INF) a.inv_lead[r] = fp_inv32(row[l], p);
-        }
-        if (tid == 0) lead0[r] = l;
-    }
-    for (uint32_t j = bid * ECH_THREADS + tid; j < nc; j += nb * ECH_THREADS) a.is_piv_col[j] = 0;
-    grid.sync();
-    if (bid == 0 && tid == 0) {
-        uint32_t n = 0;
-        for (uint32_t r = 0; r < nr; ++r) if (lead0[r] != ECH_INF) a.nz_list[n++] = r;
-        a.counts[0] = n;
-    }
-    grid.sync();
-    const uint32_t nnz_rows = a.counts[0];
-
-    uint32_t step = 0;
-    for (;; ++step) {
-        const uint32_t* lc = (step & 1) ? lead1 : lead0;
-        uint32_t* ln = (step & 1) ? lead0 : lead1;
-        // every CTA derives the same pivot: smallest lead, ties to the first row
-        uint64_t key = ~0ull;
-        for (uint32_t i = tid; i < nnz_rows; i += ECH_THREADS) {
-            const uint32_t l = lc[a.nz_list[i]];
-            if (l != ECH_INF) { const uint64_t k = ((uint64_t)l << 32) | i; key = k < key ? k : key; }
-        }
-        key = block_min_u64(key, sh64);
-        if (key == ~0ull) break;
-        const uint32_t c = (uint32_t)(key >> 32);
-        const uint32_t pr = a.nz_list[(uint32_t)key];
-        const uint32_t* prow = a.d + (uint64_t)pr * a.ld;
-        const uint32_t inv = a.inv_lead[pr];
-        if (bid == 0 && tid == 0) { a.piv_row[step] = pr; a.piv_col[step] = c; a.is_piv_col[c] = 1; }
-        // rows are dealt to groups of 128 threads: 4 rows per CTA in flight
-        for (uint32_t i = bid * ECH_GROUPS + grp; i < nnz_rows; i += nb * ECH_GROUPS) {
-            const uint32_t r = a.nz_list[i];
-            if (r == pr) { if (gt == 0) ln[r] = ECH_INF; continue; }
-            uint32_t* row = a.d + (uint64_t)r * a.ld;
-            const uint32_t fv = row[c];
-            const uint32_t lr = lc[r];
-            if (fv == 0) { if (gt == 0) ln[r] = lr; continue; }
-            const uint32_t mult = p - fp_mul(fv, inv, a.f);
-            uint32_t nl = ECH_INF;
-            for (uint32_t j0 = c + 1; j0 < nc; j0 += 4 * ECH_GROUP) {
-                uint32_t pv[4], v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t j = j0 + u * ECH_GROUP + gt;
-                    pv[u] = j < nc ? prow[j] : 0u;
-                    v[u] = j < nc ? row[j] : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t j = j0 + u * ECH_GROUP + gt;
-                    if (pv[u]) { v[u] = fp_reduce64((uint64_t)v[u] + (uint64_t)mult * pv[u], a.f); row[j] = v[u]; }
-                    if (v[u] && nl == ECH_INF) nl = j;
-                }
-            }
-            if (lr != ECH_INF) {            // a remaining row: its lead was c, find the new one (and its inverse)
-                for (int o = 16; o; o >>= 1) nl = min(nl, __shfl_xor_sync(0xffffffffu, nl, o));
-                if ((gt & 31) == 0) sh_grp[grp][gw] = nl;
-                group_bar(grp);             // also orders the row[] stores before the read below
-                if (gt == 0) {
-                    nl = min(min(sh_grp[grp][0], sh_grp[grp][1]), min(sh_grp[grp][2], sh_grp[grp][3]));
-                    ln[r] = nl;
-                    if (nl != ECH_INF) a.inv_lead[r] = fp_inv32(row[nl], p);
-                }
-                group_bar(grp);
-            } else if (gt == 0) ln[r] = ECH_INF;
-        }
-        grid.sync();
-    }
-    const uint32_t npiv = step;
-    if (bid == 0 && tid == 0) a.counts[1] = npiv;
-
-    // non-zeros per pivot row over the live columns (its own pivot + non-pivot columns)
-    for (uint32_t s = bid; s < npiv; s += nb) {
-        const uint32_t* row = a.d + (uint64_t)a.piv_row[s] * a.ld;
-        const uint32_t c = a.piv_col[s];
-        uint32_t n = 0;
-        for (uint32_t j = c + tid; j < nc; j += ECH_THREADS) n += (j == c || (!a.is_piv_col[j] && row[j])) ? 1u : 0u;
-        n = block_sum_u32(n, sh32);
-        if (tid == 0) a.out_ptr[s + 1] = n;
-    }
-    grid.sync();
-    if (bid == 0 && tid == 0) {
-        uint64_t acc = 0; a.out_ptr[0] = 0;
-        for (uint32_t s = 0; s < npiv; ++s) { acc += a.out_ptr[s + 1]; a.out_ptr[s + 1] = acc; }
-    }
-}
 
 struct EmitArgs {
     Fp f;

@@ -18,7 +18,8 @@ struct PrepArgs {
     uint32_t* seg;        // [n_tiles * n_rows + 1] tile-major: counts, then (after the exclusive scan) segment starts;
                           // (row, tile) ends where the next element starts (layout.cuh)
     uint2* ent;
-    uint32_t* diag;       // [n_windows][32][32]
+    uint32_t* diag;       // [n_windows][32][32] strictly upper part of the diagonal blocks of A (raw: kernels_tri.cuh reads it)
+    uint32_t* dinv;       // [n_windows][32][32] strictly upper part of their inverses (what the elimination kernels read)
     uint32_t* dnz;        // [n_windows]
     uint32_t* first_piv;  // per bottom row: smallest pivot column present (n_top if none)
     uint32_t* first_min;  // min of first_piv over all rows to reduce (preset to 0xffffffff)
@@ -111,13 +112,14 @@ __global__ void prep_nnz_a_kernel(PrepArgs a, unsigned long long* out) {
     if (threadIdx.x == 0) *out = s;
 }
 
-// One warp per window: replace the strictly-upper block N (A_ww = I + N, diagonal implicit) by the
+// One warp per window: from the strictly-upper block N (A_ww = I + N, diagonal implicit) the
 // strictly-upper part M of (I + N)^-1 = I + M, lane = column:  M[i] = -N[i] - sum_{j>i} N[i][j] * M[j].
 __global__ void __launch_bounds__(256) prep_diag_inverse_kernel(PrepArgs a) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * 8 + warp;
     if (w >= a.L.n_windows) return;
-    uint32_t* blk = a.diag + (uint64_t)w * WINDOW * WINDOW;
+    const uint32_t* blk = a.diag + (uint64_t)w * WINDOW * WINDOW;
+    uint32_t* out = a.dinv + (uint64_t)w * WINDOW * WINDOW;
     uint32_t n[WINDOW], inv[WINDOW];
 #pragma unroll
     for (int i = 0; i < WINDOW; ++i) { n[i] = blk[i * WINDOW + lane]; inv[i] = 0; }
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(256) prep_diag_inverse_kernel(PrepArgs a) {
         if (__ballot_sync(0xffffffffu, inv[i] != 0)) mask |= 1u << i;
     }
 #pragma unroll
-    for (int i = 0; i < WINDOW; ++i) blk[i * WINDOW + lane] = inv[i];
+    for (int i = 0; i < WINDOW; ++i) out[i * WINDOW + lane] = inv[i];
     if (lane == 0) a.dnz[w] = mask;
 }
 

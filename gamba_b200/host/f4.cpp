@@ -476,6 +476,19 @@ void F4::convert() {
 
 void F4::dump_step(const char* tag) {
     if (prm_.dump_dir.empty() || (long)M_.nnz() < prm_.dump_min_nnz) return;
+    const bool is_final = std::string(tag) == "final";
+    if (prm_.dump_top > 0 && !is_final) {
+        // --dump-top N: only the N steps with the most non-zeros stay on disk (the big systems' runs have 60+ steps of
+        // hundreds of MB each); a step smaller than all N kept ones is not written at all
+        if ((long)dump_kept_.size() >= prm_.dump_top) {
+            auto mn = std::min_element(dump_kept_.begin(), dump_kept_.end());
+            if (mn->first >= M_.nnz()) return;
+            std::remove((prm_.dump_dir + "/step_" + mn->second + ".bin").c_str());
+            std::remove((prm_.dump_dir + "/rows_" + mn->second + ".bin").c_str());
+            dump_kept_.erase(mn);
+        }
+        dump_kept_.emplace_back(M_.nnz(), tag);
+    }
     char name[64];
     std::snprintf(name, sizeof name, "/step_%s.bin", tag);
     write_step_file(prm_.dump_dir + name, M_);

@@ -30,6 +30,7 @@ struct Params {
     int threads = 0;            // -t: host threads (0 = all hardware threads, at most 16)
     std::string dump_dir;       // write every step matrix (+ result) here
     long dump_min_nnz = 0;
+    long dump_top = 0;          // keep only the N steps with the most non-zeros (0 = all)
     long stop_after = 0;        // debugging: leave the F4 loop after this many steps (0 = run to the end)
 };
 
@@ -87,6 +88,7 @@ private:
     std::vector<uint32_t> nonpiv_col_;   // relative non-pivot index -> column
     StepMatrix M_;
     NewRows R_;
+    std::vector<std::pair<uint64_t, std::string>> dump_kept_;   // --dump-top: (nnz, tag) of the steps on disk
 
     void import_generators();
     void update(uint32_t h);

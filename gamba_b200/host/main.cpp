@@ -29,6 +29,7 @@ static void usage() {
         "  -v,--verbose UINT               Verbosity level (default 2)\n"
         "  --dump-steps DIR                Write every step matrix and its result to DIR\n"
         "  --dump-min-nnz N                ... only steps with at least N non-zeros\n"
+        "  --dump-top N                    ... only the N steps with the most non-zeros\n"
         "  --stop-after N                  (debugging) leave the F4 loop after N steps");
 }
 
@@ -56,6 +57,7 @@ int main(int argc, char** argv) {
             else if (key == "-v" || key == "--verbose") prm.verbose = std::stoi(need(i, "--verbose"));
             else if (key == "--dump-steps") prm.dump_dir = need(i, "--dump-steps");
             else if (key == "--dump-min-nnz") prm.dump_min_nnz = std::stol(need(i, "--dump-min-nnz"));
+            else if (key == "--dump-top") prm.dump_top = std::stol(need(i, "--dump-top"));
             else if (key == "--stop-after") prm.stop_after = std::stol(need(i, "--stop-after"));
             else if (key == "-h" || key == "--help") { usage(); return 0; }
             else { std::fprintf(stderr, "The following argument was not expected: %s\n", a.c_str()); return 109; }

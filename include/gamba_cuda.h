@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define GAMBA_CUDA_ABI_VERSION 3   /* 3: gamba_cuda_counters grew (seconds_sparse_last, seconds_schur_last, schur_macs) */
+#define GAMBA_CUDA_ABI_VERSION 4   /* 4: gamba_cuda_counters grew (dense_macs, seconds_inverse_last, solve_mode, panel_t) */
 
 #define GAMBA_CUDA_REPR_STANDARD   0u
 #define GAMBA_CUDA_REPR_MONTGOMERY 1u
@@ -167,17 +167,25 @@ typedef struct gamba_cuda_counters {
     double seconds_schur_last;         /* ... of the tensor-core product D' = D + M B (limb planes + schur kernel)     */
     uint64_t schur_macs;               /* mod-p multiply-adds of that product: rows x n_top x n_nonpiv (0 = sparse path) */
     uint32_t mc_ech_combinations;      /* random combinations of the rows of D' the last echelon ran on (0 = the rows themselves) */
+    uint32_t solve_mode;               /* how the multipliers M = -C A^-1 of the last step were found: 0 sparse row-per-CTA kernel,
+                                          1 sparse kernel for blocks of rows, 2 blocked triangular solve on the tensor cores       */
+    uint64_t dense_macs;               /* mod-p multiply-adds of ALL tensor-core products of the elimination stage, last step
+                                          (x 4 / x 16 int8 multiply-adds for 2 / 4 limbs)                                         */
+    double seconds_inverse_last;       /* CUDA-event time of the inverse diagonal tiles (inside seconds_sparse_last), last step   */
+    uint32_t panel_t;                  /* pivot tile of the blocked solve (0 = not used)                                          */
     uint32_t reserved0;
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
 
-/* Options: "tile_cols", "ctas_per_sm" (0 = automatic), "echelon_mma" (default 1: blocked echelon with int8
-   tensor-core trailing updates; 0: one rank-1 update per pivot),
+/* Options: "tile_cols", "ctas_per_sm" (0 = automatic),
    "coeff_cache" (default 0; 1: coefficient arrays stay on the device across steps, keyed by host pointer - the
    caller promises they are immutable while the engine lives, as the reference's basis storage is,
    source/matrix.hpp:189-193; setting the option again drops the cache),
    "schur" (default 1: the B half of the elimination, D' = D + M B, runs as a dense limb-split product on the
-   tensor cores whenever its operands fit "schur_max_gb" (default 64) GB of HBM; 0: sparse path for both halves),
+   tensor cores whenever its operands fit "schur_max_gb" (default 96) GB of HBM; 0: sparse path for both halves),
+   "panel" (with "schur": the multipliers M = -C A^-1 by a blocked triangular solve on the tensor cores, kernels_tri.cuh;
+   0 never, 1 (default) when the cost estimate from the previous step says it beats the sparse kernels, 2 always),
+   "panel_t" (pivot tile of that solve: 128 * 2^j, 0 = automatic), "panel_max_top",
    "block" (with "schur": the sparse half of the elimination for R rows per CTA from one pass over the pivot rows,
    kernels_elim_block.cuh; 0 never, 1 (default) for steps with >= 32768 pivot rows once the previous step had
    more than half of its multipliers non-zero, 2 always), "elim_warps", "schur_min_top", "schur_kchunk" (tuning / tests),

@@ -29,6 +29,14 @@ def build(force: bool = False) -> None:
 _lib = None
 
 
+def host_threads() -> int:
+    """Threads for the checker mode: all the cores this process may run on."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def _load():
     global _lib
     if _lib is None:
@@ -36,12 +44,15 @@ def _load():
         _lib = C.CDLL(LIB)
         _lib.gamba_oracle_reduce.argtypes = [C.c_uint32] * 4 + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_void_p,
                                                                                   C.POINTER(_Result)]
+        _lib.gamba_oracle_reduce_mt.argtypes = [C.c_uint32] * 4 + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                                                     C.POINTER(_Result)]
         _lib.gamba_oracle_free.argtypes = [C.POINTER(_Result)]
     return _lib
 
 
-def reduce(step):
-    """Canonical RREF of D' for a gamba_b200.stepfile.Step -> (Rows, fma_top, seconds)."""
+def reduce(step, threads: int = 1):
+    """Canonical RREF of D' for a gamba_b200.stepfile.Step -> (Rows, fma_top, seconds).
+    threads <= 1: the single-thread timing mode; threads > 1: the checker mode (oracle_checker.cpp)."""
     from gamba_b200.stepfile import Rows
     lib = _load()
     pool = np.ascontiguousarray(step.pool, dtype=np.uint32)
@@ -52,8 +63,8 @@ def reduce(step):
     cid = np.ascontiguousarray(step.coeff_id, dtype=np.uint32)
     clen = np.ascontiguousarray(step.coeff_len, dtype=np.uint32)
     res = _Result()
-    rc = lib.gamba_oracle_reduce(step.p, step.n_top, step.n_bot, step.n_cols, row_ptr.ctypes.data, col.ctypes.data,
-                                 cid.ctypes.data, len(clen), ptrs.ctypes.data, clen.ctypes.data, C.byref(res))
+    rc = lib.gamba_oracle_reduce_mt(step.p, step.n_top, step.n_bot, step.n_cols, row_ptr.ctypes.data, col.ctypes.data,
+                                    cid.ctypes.data, len(clen), ptrs.ctypes.data, clen.ctypes.data, max(1, int(threads)), C.byref(res))
     if rc:
         raise RuntimeError("oracle failed")
     n, nnz = res.n_new, res.nnz_new

@@ -18,10 +18,11 @@ struct gamba_oracle_result {
     double seconds;
 };
 
-int gamba_oracle_reduce(uint32_t p, uint32_t n_top, uint32_t n_bot, uint32_t n_cols,
-                        const uint64_t* row_ptr, const uint32_t* col_idx, const uint32_t* coeff_id,
-                        uint32_t n_coeff_arrays, const uint32_t* const* coeff_ptr, const uint32_t* coeff_len,
-                        gamba_oracle_result* res) {
+// threads <= 1: single-thread timing mode; threads > 1: checker mode (oracle_checker.cpp)
+int gamba_oracle_reduce_mt(uint32_t p, uint32_t n_top, uint32_t n_bot, uint32_t n_cols,
+                           const uint64_t* row_ptr, const uint32_t* col_idx, const uint32_t* coeff_id,
+                           uint32_t n_coeff_arrays, const uint32_t* const* coeff_ptr, const uint32_t* coeff_len,
+                           uint32_t threads, gamba_oracle_result* res) {
     try {
         gb::StepMatrix m;
         m.p = p; m.n_top = n_top; m.n_bot = n_bot; m.n_cols = n_cols;
@@ -31,7 +32,7 @@ int gamba_oracle_reduce(uint32_t p, uint32_t n_top, uint32_t n_bot, uint32_t n_c
         m.coeff_id.assign(coeff_id, coeff_id + nr);
         m.cf_ptr.assign(coeff_ptr, coeff_ptr + n_coeff_arrays);
         m.cf_len.assign(coeff_len, coeff_len + n_coeff_arrays);
-        gb::OracleEngine eng; gb::NewRows out;
+        gb::OracleEngine eng(threads); gb::NewRows out;
         eng.reduce_step(m, out);
         res->n_new = out.n_new; res->nnz_new = out.col.size();
         res->row_ptr = (uint64_t*)std::malloc(sizeof(uint64_t) * (out.n_new + 1));
@@ -43,6 +44,13 @@ int gamba_oracle_reduce(uint32_t p, uint32_t n_top, uint32_t n_bot, uint32_t n_c
         res->fma_top = out.fma_top; res->seconds = out.seconds;
         return 0;
     } catch (...) { return 1; }
+}
+
+int gamba_oracle_reduce(uint32_t p, uint32_t n_top, uint32_t n_bot, uint32_t n_cols,
+                        const uint64_t* row_ptr, const uint32_t* col_idx, const uint32_t* coeff_id,
+                        uint32_t n_coeff_arrays, const uint32_t* const* coeff_ptr, const uint32_t* coeff_len,
+                        gamba_oracle_result* res) {
+    return gamba_oracle_reduce_mt(p, n_top, n_bot, n_cols, row_ptr, col_idx, coeff_id, n_coeff_arrays, coeff_ptr, coeff_len, 1, res);
 }
 
 void gamba_oracle_free(gamba_oracle_result* res) {

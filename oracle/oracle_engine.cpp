@@ -21,6 +21,7 @@ static uint32_t inv_mod_u32(uint32_t a, uint32_t p) {
 }
 
 void OracleEngine::reduce_step(const StepMatrix& m, NewRows& out) {
+    if (threads_ > 1) { oracle_reduce_step_mt(m, out, threads_); return; }
     auto t0 = std::chrono::steady_clock::now();
     const uint32_t p = m.p, ntop = m.n_top, nbot = m.n_bot, ncols = m.n_cols, nnp = ncols - ntop;
     const uint64_t P2 = (uint64_t)p * p;

@@ -23,10 +23,19 @@
 
 namespace gb {
 
+// Checker mode (oracle_checker.cpp): same contract, all host threads; a different stage-2 algorithm on purpose.
+void oracle_reduce_step_mt(const StepMatrix& m, NewRows& out, unsigned n_threads);
+
 class OracleEngine final : public Engine {
 public:
-    const char* name() const override { return "oracle-cpu"; }
+    // threads <= 1: the single-thread timing mode (what cpu_baseline measures; the reference is single-threaded,
+    // README.md:9,71); threads > 1: the checker mode
+    explicit OracleEngine(unsigned threads = 1) : threads_(threads) {}
+    const char* name() const override { return threads_ > 1 ? "oracle-cpu-mt" : "oracle-cpu"; }
     void reduce_step(const StepMatrix& m, NewRows& out) override;
+
+private:
+    unsigned threads_;
 };
 
 }  // namespace gb

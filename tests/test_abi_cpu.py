@@ -24,7 +24,7 @@ def test_header_symbols_exported(built):
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_lib.SYMBOLS) == names
-    assert lib.gamba_cuda_abi_version() == 3
+    assert lib.gamba_cuda_abi_version() == 4
 
 
 def test_struct_sizes_match_header(built, tmp_path):
