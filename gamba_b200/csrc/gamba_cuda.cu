@@ -596,25 +596,39 @@ void gamba_cuda_engine::eliminate() {
     }
     GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (schur) {
-        // operands of the products, rebuilt for every reduction of the step (they are part of the algorithm, not of the hand-over)
+        // operands of the products, rebuilt for every reduction of the step (they are part of the algorithm, not of the
+        // hand-over): operand_build_kernel writes every byte of Bt / At / Adt, so only the planes written piecemeal are zeroed
         GCU_CHECK(cudaMemsetAsync(d_mx.p, 0, nl * mx_plane, stream));
         ea.mx = d_mx.as<uint8_t>(); ea.mx_plane = mx_plane; ea.mx_kp = kp; ea.mx_nl = nl;
-        GCU_CHECK(cudaMemsetAsync(d_bt.p, 0, nl * bt_plane, stream));
-        BtArgs ba{};
-        ba.L = L; ba.seg = d_seg.as<uint32_t>(); ba.ent = d_ent.as<uint2>();
-        ba.bt = d_bt.as<uint8_t>(); ba.bt_plane = bt_plane; ba.kp = kp; ba.nl = nl;
-        if (panel) {
-            GCU_CHECK(cudaMemsetAsync(d_at.p, 0, std::max<uint64_t>(at_bytes, 16), stream));
-            GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-            ba.at = d_at.as<uint8_t>(); ba.at_off = d_at_off.as<uint64_t>();
-            GCU_CHECK(cudaMemsetAsync(d_adt.p, 0, nl * tri_plane, stream));
-            GCU_CHECK(cudaMemsetAsync(d_wr.p, 0, nl * tri_plane, stream));
-            GCU_CHECK(cudaMemsetAsync(d_vt.p, 0, nl * tri_plane, stream));
-            ba.adt = d_adt.as<uint8_t>(); ba.adt_plane = tri_plane;
-        }
-        schur_bt_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(ba);
+        OpArgs oa{};
+        oa.L = L; oa.seg = d_seg.as<uint32_t>(); oa.ent = d_ent.as<uint2>();
+        auto opk = f.small ? operand_build_kernel<2> : operand_build_kernel<4>;
+        const size_t op_sm = f.small ? op_smem<2>() : op_smem<4>();
+        const uint32_t och = f.small ? op_ch<2>() : op_ch<4>();
+        GCU_CHECK(cudaFuncSetAttribute(opk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op_sm));
+        const uint32_t chunks = (L.tile_cols + och - 1) / och;
+        oa.mode = OP_B; oa.out = d_bt.as<uint8_t>(); oa.plane = bt_plane; oa.pitch = kp; oa.rows = np;
+        if ((uint64_t)L.n_tiles_nonpiv * L.tile_cols < np)        // padding rows beyond the last tile (tile width not a multiple of 128)
+            for (uint32_t l = 0; l < nl; ++l)
+                GCU_CHECK(cudaMemsetAsync(d_bt.as<uint8_t>() + l * bt_plane + (uint64_t)L.n_tiles_nonpiv * L.tile_cols * kp, 0,
+                                          (uint64_t)(np - L.n_tiles_nonpiv * L.tile_cols) * kp, stream));
+        opk<<<dim3(kp / OP_KB, chunks, L.n_tiles_nonpiv), 256, op_sm, stream>>>(oa);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 1;
+        if (panel) {
+            GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+            if (ntp > 1) {
+                oa.mode = OP_AT; oa.out = d_at.as<uint8_t>(); oa.at_off = d_at_off.as<uint64_t>();
+                opk<<<dim3((ntp - 1) * (T / OP_KB), chunks, ntp), 256, op_sm, stream>>>(oa);
+                GCU_CHECK(cudaGetLastError());
+            }
+            oa.mode = OP_ADT; oa.out = d_adt.as<uint8_t>(); oa.plane = tri_plane; oa.pitch = T; oa.at_off = nullptr;
+            opk<<<dim3(T / OP_KB, chunks, ntp), 256, op_sm, stream>>>(oa);
+            GCU_CHECK(cudaGetLastError());
+            GCU_CHECK(cudaMemsetAsync(d_wr.p, 0, nl * tri_plane, stream));
+            GCU_CHECK(cudaMemsetAsync(d_vt.p, 0, nl * tri_plane, stream));
+            ctr.kernel_launches += 2;
+        }
     }
     GCU_CHECK(cudaEventRecord(ev[6], stream));
     if (panel) {
@@ -622,11 +636,11 @@ void gamba_cuda_engine::eliminate() {
         // 1. inverse diagonal tiles: 128 x 128 blocks on the CUDA cores, then recursive doubling as batched products
         {
             TriBaseArgs tb{};
-            tb.L = L; tb.f = f; tb.seg = d_seg.as<uint32_t>(); tb.ent = d_ent.as<uint2>(); tb.diag = d_diag.as<uint32_t>();
+            tb.L = L; tb.f = f; tb.seg = d_seg.as<uint32_t>(); tb.ent = d_ent.as<uint2>(); tb.dinv = d_dinv.as<uint32_t>();
             tb.wr = d_wr.as<uint8_t>(); tb.vt = d_vt.as<uint8_t>(); tb.plane = tri_plane; tb.kt = kt; tb.nl = nl;
-            const size_t tb_smem = (size_t)(TRI_BASE * (TRI_BASE + 1) + TRI_BASE) * sizeof(uint32_t);
-            GCU_CHECK(cudaFuncSetAttribute(tri_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
-            tri_base_kernel<<<kt / TRI_BASE, TRI_BASE, tb_smem, stream>>>(tb);
+            auto tbk = f.small ? tri_base_kernel<true> : tri_base_kernel<false>;
+            GCU_CHECK(cudaFuncSetAttribute(tbk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRI_BASE_SMEM));
+            tbk<<<kt / TRI_BASE, TRI_BASE_THREADS, TRI_BASE_SMEM, stream>>>(tb);
             GCU_CHECK(cudaGetLastError());
             ctr.kernel_launches += 1;
         }
@@ -638,14 +652,14 @@ void gamba_cuda_engine::eliminate() {
             const CUtensorMap map_gx = make_tmap_u8(d_gx.p, s, (uint64_t)nl * (kt / 2), TC_BK, TC_BM);
             TcArgs ga{};          // G = P' Q
             ga.f = f; ga.mp = kt; ga.np = kt; ga.n_rows = s; ga.n_cols = s; ga.m_tiles = s / TC_BM; ga.n_tiles = s / bn;
-            ga.kchunk = tkc; ga.k_end = s; ga.k_mod = T;
+            ga.kchunk = tkc; ga.k_end = s; ga.k_mod = T; ga.tri = 1;
             ga.a_row0 = 0; ga.a_row_b = 2 * s; ga.a_k0 = 0; ga.a_k_b = 2 * s;
             ga.b_row0 = s; ga.b_row_b = 2 * s; ga.b_k0 = 0; ga.b_k_b = 2 * s;
             ga.o1 = d_gx.as<uint8_t>(); ga.o1_plane = (uint64_t)(kt / 2) * s; ga.o1_ld = s; ga.o1_row_b = s;
             launch_limb_gemm<EPI_LIMBS>(f.small != 0, map_wr, map_adt, ga, nb, stream);
             TcArgs ha{};          // H = -(G R'), written into Wr and (transposed) Vt
             ha.f = f; ha.mp = kt / 2; ha.np = kt; ha.n_rows = s; ha.n_cols = s; ha.m_tiles = s / TC_BM; ha.n_tiles = s / bn;
-            ha.kchunk = tkc; ha.k_end = s; ha.k_mod = T; ha.neg = 1;
+            ha.kchunk = tkc; ha.k_end = s; ha.k_mod = T; ha.neg = 1; ha.tri = 2;
             ha.a_row0 = 0; ha.a_row_b = s; ha.a_k0 = 0; ha.a_k_b = 0;
             ha.b_row0 = s; ha.b_row_b = 2 * s; ha.b_k0 = s; ha.b_k_b = 2 * s;
             ha.o1 = d_wr.as<uint8_t>(); ha.o1_plane = tri_plane; ha.o1_ld = T; ha.o1_row0 = 0; ha.o1_row_b = 2 * s; ha.o1_col0 = s; ha.o1_col_b = 2 * s;
@@ -677,7 +691,7 @@ void gamba_cuda_engine::eliminate() {
             xa.first_piv = d_first.as<uint32_t>(); xa.row_begin = rank; xa.row_step = world;
             xa.kmin_sub = t * T; xa.skip_hi = (t + 1) * T;
             xa.kchunk = tkc; xa.k_end = (tw + TC_BK - 1) / TC_BK * TC_BK;
-            xa.b_row0 = t * T; xa.neg = 1;
+            xa.b_row0 = t * T; xa.neg = 1; xa.tri = 2;
             xa.o1 = d_mx.as<uint8_t>(); xa.o1_plane = mx_plane; xa.o1_ld = kp; xa.o1_col0 = t * T;
             xa.stats = ea.stats; xa.cnt_row_ptr = d_row_ptr.as<uint64_t>();
             launch_limb_gemm<EPI_LIMBS>(f.small != 0, map_cx, map_vt, xa, 1, stream);

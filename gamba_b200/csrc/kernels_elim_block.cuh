@@ -99,7 +99,7 @@ struct BlkStream {
                 q[d] = make_uint4(sink, 0u, sink, 0u);
                 if (pos < e) q[d] = __ldg(reinterpret_cast<const uint4*>(ent + pos));
                 pos += step; cs += step;
-                const uint32_t j0 = cur.x >> 16, j1 = cur.z >> 16;
+                const uint32_t j0 = (cur.x >> 16) & 31u, j1 = (cur.z >> 16) & 31u;
                 const uint32_t a0 = acc_sa + (cur.x & 0xffffu) * (Acc<SMALLP>::WORDS * 4), a1 = acc_sa + (cur.z & 0xffffu) * (Acc<SMALLP>::WORDS * 4);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {                                  // no branches: the R chains interleave

@@ -11,8 +11,8 @@
 // contractions" rule, same limb technique as kernels_echelon_mma.cuh):
 //
 //   Mx[limb][row][k]   u8 limbs of the multipliers, written by the solve (kernels_tri.cuh / elim_kernel) as it finds them
-//   Bt[limb][col][k]   u8 limbs of B, transposed (k contiguous), scattered once per step by
-//                      schur_bt_kernel from the staged entries of the non-pivot tiles
+//   Bt[limb][col][k]   u8 limbs of B, transposed (k contiguous), built once per step by
+//                      operand_build_kernel from the staged entries of the non-pivot tiles
 //   D'[row][col]       u32 residues; holds D when the product starts
 //
 // The product itself is limb_gemm_tc_kernel (kernels_schur_tc.cuh: tcgen05 + TMA); this file holds the kernels that
@@ -27,64 +27,82 @@ namespace gcu {
 constexpr int SC_BK = 64;                  // bytes of k per stage and row
 
 
-struct BtArgs {
+// Operand builder: the entries of the pivot rows, transposed into dense u8 limb planes op[l][column][k] (k contiguous).
+// One CTA per (block of 128 pivot rows, chunk of OP_CH<NL> columns of one column tile): the block is assembled in shared
+// memory from the rows' entries of that tile (tile-major ent[]: short, contiguous segments) and written out as whole
+// 128-byte rows - every byte of the operand is written exactly once, zeros included, so there is no memset and no
+// scattered byte store in HBM (round 1's per-entry scatter: 2.0 ms + 0.3 ms of memsets per cyclic9-15 step, now ~0.5 ms).
+//   mode OP_B    columns = the non-pivot tiles: Bt[l][col][k], the right operand of D' = D + M B
+//   mode OP_AT   blockIdx.z = pivot tile t >= 1, pivot rows of the EARLIER tiles: At_t[l][col in tile t][k < t T]
+//   mode OP_ADT  blockIdx.z = pivot tile t, its OWN pivot rows (entries right of the row's window):
+//                Adt[l][t T + col][k - t T]  (kernels_tri.cuh: the Q blocks of the recursive doubling)
+constexpr int OP_B = 0, OP_AT = 1, OP_ADT = 2;
+constexpr int OP_KB = 128;                 // pivot rows per block = bytes of one output row segment
+constexpr int OP_PITCH = OP_KB + 16;       // shared-memory row pitch (16-byte aligned, spreads the banks)
+template <int NL> __host__ __device__ constexpr int op_ch() { return 512 / NL; }          // columns per chunk
+template <int NL> __host__ __device__ constexpr size_t op_smem() { return (size_t)NL * op_ch<NL>() * OP_PITCH; }
+
+struct OpArgs {
     Layout L;
     const uint32_t* seg;
     const uint2* ent;
-    uint8_t* bt;                // [nl][np][kp]
-    uint64_t bt_plane;
-    uint32_t kp, nl;
-    // panel mode: the part of A right of a pivot row's own tile goes to per-tile operands as well:
-    // at + at_off[t] is [nl][tile_cols][kp_t] with kp_t = t * tile_cols (only pivots of earlier tiles reach tile t)
-    uint8_t* at;                // NULL: B only
-    const uint64_t* at_off;     // [n_tiles_piv] byte offsets
-    // blocked triangular solve (kernels_tri.cuh): the part of A inside a pivot row's own tile, transposed:
-    // adt[l][g][k'] = A[tile start + k'][g] for the columns g right of the row's window, [nl][kt][tile_cols]
-    uint8_t* adt;               // NULL: not needed
-    uint64_t adt_plane;
+    uint8_t* out;
+    uint64_t plane;             // bytes per limb plane (OP_B, OP_ADT)
+    uint32_t pitch;             // bytes per operand row (OP_B: kp, OP_ADT: tile_cols)
+    uint32_t rows;              // OP_B: operand rows (non-pivot columns padded to 128)
+    uint32_t mode;
+    const uint64_t* at_off;     // OP_AT: byte offset of tile t's operand
 };
 
-// One warp per pivot row k: its entries in the non-pivot tiles become column k of Bt. Consecutive
-// warps write adjacent bytes of the same sectors, which L2 merges before they reach HBM.
-__global__ void __launch_bounds__(256) schur_bt_kernel(BtArgs a) {
+template <int NL>
+__global__ void __launch_bounds__(256) operand_build_kernel(OpArgs a) {
+    constexpr int CH = op_ch<NL>();
+    extern __shared__ __align__(16) unsigned char op_sm[];
     const Layout& L = a.L;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t k = blockIdx.x * 8 + warp;
-    if (k >= L.n_top) return;
-    const uint32_t nr = L.n_rows;
-    if (a.adt) {
-        const uint32_t t = k / L.tile_cols, T = L.tile_cols;
-        const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
-        uint8_t* base = a.adt + (uint64_t)t * T * T + (k - t * T);
-        for (uint32_t i = s + lane; i < e; i += 32) {
-            const uint2 en = __ldg(a.ent + i);
-            if (en.y == 0) continue;                       // padding
-            uint8_t* dst = base + (uint64_t)(en.x & 0xffffu) * T;
-            for (uint32_t l = 0; l < a.nl; ++l) dst[l * a.adt_plane] = (uint8_t)(en.y >> (8 * l));
-        }
+    const uint32_t tid = threadIdx.x;
+    const uint32_t T = L.tile_cols, nr = L.n_rows;
+    const uint32_t kb = blockIdx.x, cc = blockIdx.y, z = blockIdx.z;
+    uint32_t tc, k0, orow0, okoff, pitch, rows;
+    uint64_t plane;
+    uint8_t* out = a.out;
+    if (a.mode == OP_B) {
+        tc = L.n_tiles_piv + z; k0 = kb * OP_KB; orow0 = z * T + cc * CH; okoff = k0; pitch = a.pitch; plane = a.plane; rows = a.rows;
+    } else if (a.mode == OP_AT) {
+        if (kb * OP_KB >= z * T) return;                            // only the pivot rows of earlier tiles reach tile z
+        tc = z; k0 = kb * OP_KB; orow0 = cc * CH; okoff = k0; pitch = z * T; plane = (uint64_t)T * pitch; rows = T;
+        out += a.at_off[z];
+    } else {
+        tc = z; k0 = z * T + kb * OP_KB; orow0 = z * T + cc * CH; okoff = kb * OP_KB; pitch = a.pitch; plane = a.plane; rows = 0xffffffffu;
     }
-    if (a.at) {
-        for (uint32_t t = k / L.tile_cols + 1; t < L.n_tiles_piv; ++t) {
-            const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
-            const uint64_t kpt = (uint64_t)t * L.tile_cols, plane = kpt * L.tile_cols;
-            uint8_t* base = a.at + a.at_off[t] + k;
-            for (uint32_t i = s + lane; i < e; i += 32) {
-                const uint2 en = __ldg(a.ent + i);
-                if (en.y == 0) continue;                   // padding
-                uint8_t* dst = base + (uint64_t)(en.x & 0xffffu) * kpt;
-                for (uint32_t l = 0; l < a.nl; ++l) dst[l * plane] = (uint8_t)(en.y >> (8 * l));
+    if (orow0 >= rows) return;
+    const uint32_t c_lo = cc * CH, c_hi = min(c_lo + CH, T), cw = c_hi - c_lo;     // the tile ends at T
+    for (uint32_t i = tid * 16; i < NL * CH * OP_PITCH; i += 256 * 16) *reinterpret_cast<uint4*>(op_sm + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // in OP_ADT a chunk left of the block's rows holds nothing (A is upper triangular): it is written as zeros
+    const bool empty = a.mode == OP_ADT && c_hi <= kb * OP_KB;
+    if (!empty && k0 < L.n_top) {
+        // the entries of the block's 128 pivot rows in this tile are ONE contiguous range (tile-major ent[]); an entry names
+        // its row inside the block in bits 16-22. Two entries (16 bytes) per thread and pass: segments are padded to that.
+        const uint32_t s = a.seg[(uint64_t)tc * nr + k0], e = a.seg[(uint64_t)tc * nr + min(k0 + OP_KB, L.n_top)];
+        for (uint32_t q = s + tid * 2; q < e; q += 512) {
+            const uint4 en2 = __ldg(reinterpret_cast<const uint4*>(a.ent + q));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t x = h ? en2.z : en2.x, v = h ? en2.w : en2.y;
+                const uint32_t c = x & 0xffffu, i = (x >> 16) & 127u;
+                if (v && c >= c_lo && c < c_hi) {
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) op_sm[((size_t)l * CH + (c - c_lo)) * OP_PITCH + i] = (uint8_t)(v >> (8 * l));
+                }
             }
         }
     }
-    for (uint32_t t = L.n_tiles_piv; t < L.n_tiles; ++t) {
-        const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
-        const uint32_t c0 = (t - L.n_tiles_piv) * L.tile_cols;
-        for (uint32_t i = s + lane; i < e; i += 32) {
-            const uint2 en = __ldg(a.ent + i);
-            if (en.y == 0) continue;                       // padding
-            uint8_t* dst = a.bt + (uint64_t)(c0 + (en.x & 0xffffu)) * a.kp + k;
-            for (uint32_t l = 0; l < a.nl; ++l) dst[l * a.bt_plane] = (uint8_t)(en.y >> (8 * l));
-        }
+    __syncthreads();
+    for (uint32_t w = tid; w < (uint32_t)(NL * CH * 8); w += 256) {
+        const uint32_t part = w & 7u, c = (w >> 3) % CH, l = (w >> 3) / CH;
+        if (c >= cw || orow0 + c >= rows) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(op_sm + ((size_t)l * CH + c) * OP_PITCH + part * 16);
+        *reinterpret_cast<uint4*>(out + l * plane + (uint64_t)(orow0 + c) * pitch + okoff + part * 16) = v;
     }
 }
 

@@ -66,6 +66,8 @@ struct TcArgs {
     //               o2[l * o2_plane + (o2_row0 + b * o2_row_b + col) * o2_ld + ((o2_col0 + b * o2_col_b) mod k_mod) + row]
     uint8_t* o1; uint64_t o1_plane; uint32_t o1_ld, o1_row0, o1_row_b, o1_col0, o1_col_b;
     uint8_t* o2; uint64_t o2_plane; uint32_t o2_ld, o2_row0, o2_row_b, o2_col0, o2_col_b;
+    uint32_t tri;               // 1: the A-operand block is upper triangular (rows <= k): k-steps left of the tile's rows are skipped;
+                                // 2: the B-operand block is upper triangular as [k][col] (k <= col): k-steps right of the tile's columns are skipped
     uint32_t neg;               // EPI_LIMBS: store (p - x) mod p
     // EPI_LIMBS: count the non-zero outputs (row < n_rows, col < n_cols): stats[0] += 1, stats[2] += len[col0 + col]
     const uint64_t* cnt_row_ptr; unsigned long long* stats;
@@ -177,8 +179,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
     }
     __syncthreads();
     const bool skip_all = EPI == EPI_LIMBS && a.skip_hi && s_kmin >= a.skip_hi;   // the output stays what the host zeroed
-    const uint32_t ks_end = (a.k_end + TC_BK - 1) / TC_BK;
-    const uint32_t ks_begin = min((s_kmin > a.kmin_sub ? s_kmin - a.kmin_sub : 0u) / TC_BK, ks_end);
+    uint32_t ks_end = (a.k_end + TC_BK - 1) / TC_BK;
+    if (a.tri == 2) ks_end = min(ks_end, (col0 + (uint32_t)BN + TC_BK - 1) / TC_BK);
+    uint32_t ks_begin = (s_kmin > a.kmin_sub ? s_kmin - a.kmin_sub : 0u) / TC_BK;
+    if (a.tri == 1) ks_begin = max(ks_begin, row0 / TC_BK);
+    ks_begin = min(ks_begin, ks_end);
     const uint32_t n_ks = skip_all ? 0u : ks_end - ks_begin;
     const uint32_t n_chunks = n_ks ? (n_ks + a.kchunk - 1) / a.kchunk : 0;
 
@@ -302,10 +307,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
 #pragma unroll
                             for (int l = 0; l < NL; ++l) o2p[l * a.o2_plane + (uint64_t)(c0 + e) * a.o2_ld] = (uint8_t)(o[e] >> (8 * l));
                     }
-                    if (EPI == EPI_LIMBS && a.stats && row_ok) {
+                    if (EPI == EPI_LIMBS && a.stats) {      // lane e counts the non-zeros of column col + e over the warp's rows
+                        uint32_t mine = 0;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (o[e] && col + e < a.n_cols) { cnt_piv += 1; cnt_fma += a.cnt_row_ptr[a.o1_col0 + col + e + 1] - a.cnt_row_ptr[a.o1_col0 + col + e]; }
+                        for (int e = 0; e < 16; ++e) {
+                            const uint32_t m = __ballot_sync(0xffffffffu, o[e] != 0 && row_ok);
+                            if ((int)lane == e) mine = __popc(m);
+                        }
+                        if (mine && col + lane < a.n_cols) {
+                            const uint32_t k = a.o1_col0 + col + lane;
+                            cnt_piv += mine; cnt_fma += (unsigned long long)mine * (a.cnt_row_ptr[k + 1] - a.cnt_row_ptr[k]);
+                        }
                     }
                 }
             }

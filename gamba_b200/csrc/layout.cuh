@@ -9,7 +9,7 @@
 // warp) and a warp sweeps the tiles left to right.
 //
 // Pivot rows (A|B) and rows to reduce (C|D) are therefore stored re-tiled, TILE-MAJOR:
-//   ent[]      (tile-relative column | position of the pivot row in its window << 16, value) pairs; all
+//   ent[]      (tile-relative column | position of the pivot row in its block of 128 rows << 16, value) pairs; all
 //              segments of tile 0 in row order, then tile 1, ...: the pivot rows of one window - or of
 //              any run of windows - restricted to one tile are ONE contiguous range, which the blocked
 //              elimination kernel streams with full lanes whatever the length of the single segments

@@ -115,6 +115,22 @@ def load_rows(path: str) -> Rows:
     return Rows(n_new, row_ptr, col, val)
 
 
+def thin_step(step: Step, every: int) -> Step:
+    """All pivot rows, every `every`-th row to reduce: a smaller valid step on the same A|B (bounded CPU samples of
+    bench.py's baseline legs; the checks on the uncapped kat15 / eco15 steps, whose 8-20 k rows cost the oracle minutes)."""
+    if every <= 1:
+        return step
+    nt = step.n_top
+    keep = np.arange(0, step.n_bot, every) + nt
+    rp = step.row_ptr.astype(np.int64)
+    parts, lens = [step.col[: rp[nt]]], []
+    for r in keep:
+        parts.append(step.col[rp[r]: rp[r + 1]]); lens.append(rp[r + 1] - rp[r])
+    row_ptr = np.concatenate([rp[: nt + 1], rp[nt] + np.cumsum(lens)]).astype(np.uint64)
+    return Step(step.p, nt, len(keep), step.n_cols, row_ptr, np.concatenate(parts),
+                np.concatenate([step.coeff_id[:nt], step.coeff_id[keep]]), step.coeff_len, step.pool)
+
+
 def synthetic_step(n_rows: int, n_cols: int, density: float, p: int, seed: int = 967557673,
                    top_frac: float = 0.92, share: int = 25) -> Step:
     """F4-shaped random step (BASELINE.json configs[4]): n_top pivot rows with

@@ -48,7 +48,27 @@ def step_dirs(built, tmp_path_factory):
             gold_in = os.path.join(GOLD_IN, name + ".txt")
             inp = gold_in if os.path.exists(gold_in) else systems.write_system(name, os.path.join(d, name + ".txt"))
             subprocess.run([oracle.DRIVER, "-i", inp, "-o", os.path.join(d, "out.txt"), "-v", "0", "--dump-steps", d,
-                            *extra], check=True)
+                            *extra], check=True, env=dict(os.environ, GAMBA_ORACLE_THREADS=str(oracle.host_threads())))
+            cache[key] = d
+        return cache[key]
+    return get
+
+
+@pytest.fixture(scope="session")
+def product_step_dirs(built, tmp_path_factory):
+    """Step matrices of the big named systems (BASELINE.json configs[1..3]), dumped by the PRODUCT driver on the GPU
+    (the oracle driver needs minutes to hours for them); the tests check every dumped step against the oracle."""
+    from gamba_b200 import systems
+    cache = {}
+
+    def get(name: str, extra=()):
+        key = (name,) + tuple(extra)
+        if key not in cache:
+            d = str(tmp_path_factory.mktemp("psteps_" + name.replace("-", "_")))
+            inp = systems.write_system(name, os.path.join(d, name + ".txt"))
+            r = subprocess.run([os.path.join(ROOT, "gamba_b200", "bin", "gamba"), "-i", inp, "-o", os.path.join(d, "out.txt"),
+                                "-v", "0", "--dump-steps", d, *extra], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
             cache[key] = d
         return cache[key]
     return get
