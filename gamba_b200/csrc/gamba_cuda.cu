@@ -40,24 +40,48 @@ namespace gcu {
 
 static thread_local std::string g_last_error;
 
-// Device buffers come from the stream-ordered memory pool of the device (release threshold raised to "never"
-// at create): growing a buffer is a pool operation ordered on the engine's stream, not a cudaFree (which
-// synchronises the device) plus a cudaMalloc (milliseconds per GB) - 2 s of a kat15-15 run before.
+// Device buffers come from a stream-ordered memory pool PRIVATE to the engine (release threshold "never": a freed block stays in
+// the pool for the next step): growing a buffer is a pool operation ordered on the engine's stream, not a cudaFree (which
+// synchronises the device) plus a cudaMalloc (milliseconds per GB) - 2 s of a kat15-15 run before. Matrices grow from step to step,
+// so freed blocks of the wrong size pile up in the pool: when an allocation fails the stream is drained, the pool trimmed and the
+// allocation retried. The pool is destroyed with the engine, so nothing stays reserved on the device afterwards and no other
+// user of the device's default pool is affected.
 static thread_local cudaStream_t g_alloc_stream = nullptr;
+static thread_local cudaMemPool_t g_alloc_pool = nullptr;
+
+static void* pool_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t err = cudaMallocFromPoolAsync(&p, bytes, g_alloc_pool, g_alloc_stream);
+    if (err == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        GCU_CHECK(cudaStreamSynchronize(g_alloc_stream));
+        GCU_CHECK(cudaMemPoolTrimTo(g_alloc_pool, 0));
+        err = cudaMallocFromPoolAsync(&p, bytes, g_alloc_pool, g_alloc_stream);
+    }
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        throw std::runtime_error("out of device memory allocating " + std::to_string(bytes >> 20) + " MiB: " + cudaGetErrorString(err));
+    }
+    return p;
+}
 
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) GCU_CHECK(cudaFreeAsync(p, g_alloc_stream));
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 2 + 256;   // matrices grow from step to step: few, generous reallocations
-        GCU_CHECK(cudaMallocAsync(&p, want, g_alloc_stream));
+        release();
+        // few, generous reallocations for the small buffers; the multi-GB operands of the products grow by an eighth
+        const size_t want = bytes + std::min<size_t>(bytes / 2, std::max<size_t>(bytes / 8, (size_t)256 << 20)) + 256;
+        p = pool_alloc(want);
         cap = want;
     }
+    void release() {
+        if (p) GCU_CHECK(cudaFreeAsync(p, g_alloc_stream));
+        p = nullptr; cap = 0;
+    }
     template <class T> T* as() const { return static_cast<T*>(p); }
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
 };
 
 struct HostBuf {  // pinned
@@ -112,6 +136,7 @@ struct gamba_cuda_engine {
     gcu::Fp f{};
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
     cudaEvent_t ev[10]{};
     int max_smem_optin = 0, smem_per_sm = 0;
     int64_t opt_tile_cols = 0;
@@ -134,6 +159,7 @@ struct gamba_cuda_engine {
     int64_t opt_mc_ech = 1;          // Monte-Carlo combinations of the rows of D' in front of the echelon (accepted with a rank margin of 32)
     uint32_t mc_ech_k = 0;           // combinations used by the last echelon (0 = it ran on the rows themselves)
     uint64_t mc_ech_draw = 0;
+    bool mc_fell_back = false;       // the last echelon could not allocate the combinations and ran on the rows
     std::vector<uint64_t> at_off;
     uint64_t at_bytes = 0;
     int64_t opt_block = 1;           // blocked sparse solve (kernels_elim_block.cuh): 0 never, 1 when the multipliers are dense, 2 always
@@ -210,7 +236,11 @@ struct gamba_cuda_engine {
             std::fprintf(stderr, "dbg stage: hdr+layout %.3f alloc %.3f copies+pack %.3f alloc2 %.3f kernels+sync %.3f | reduce: elim-launch %.3f echelon+d2h %.3f\n",
                          dbg_[0], dbg_[1], dbg_[2], dbg_[3], dbg_[4], dbg_[5], dbg_[6]);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
+    }
+    // called by gamba_cuda_destroy after the buffers (members) are gone
+    static void release_device(cudaStream_t st, cudaMemPool_t pl) {
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        if (pl) cudaMemPoolDestroy(pl);
     }
 
     void choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols);
@@ -782,10 +812,12 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
     const uint32_t mnl = f.small ? 2u : 4u, mbn = f.small ? TcCfg<2>::BN : TcCfg<4>::BN;
     const uint32_t rp = (nr + 127u) / 128u * 128u, kp_ = (mc_rows + 127u) / 128u * 128u, np_ = (nc + 127u) / 128u * 128u;
     if (mc_rows) {
-        d_mc_s.ensure((uint64_t)mnl * kp_ * rp);
-        d_mc_dt.ensure((uint64_t)mnl * np_ * rp);
-        d_mc_dc.ensure((uint64_t)kp_ * L.ld_dprime * sizeof(uint32_t));
-        d_mc_nz.ensure((uint64_t)kp_ * sizeof(uint32_t));
+        try {
+            d_mc_s.ensure((uint64_t)mnl * kp_ * rp);
+            d_mc_dt.ensure((uint64_t)mnl * np_ * rp);
+            d_mc_dc.ensure((uint64_t)kp_ * L.ld_dprime * sizeof(uint32_t));
+            d_mc_nz.ensure((uint64_t)kp_ * sizeof(uint32_t));
+        } catch (std::exception const&) { mc_rows = 0; mc_fell_back = true; }     // no room for the combinations: the rows themselves
     }
     GCU_CHECK(cudaMemsetAsync(d_counts.p, 0, 32, stream));
     GCU_CHECK(cudaMemsetAsync(d_counts.as<char>() + 32, 0xff, 32, stream));
@@ -953,7 +985,9 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
             const uint32_t want = ((uint32_t)(last_rank + 32 + last_rank / 8) + 127u) / 128u * 128u;
             if ((uint64_t)want * 2 <= n_gather_rows) kk = want;
         }
+        mc_fell_back = false;
         echelon(out, kk);
+        if (mc_fell_back) kk = 0;
         if (kk && out->n_new + 32 > kk) {      // margin not met
             const double t_first = t_ech_dev;
             kk = 0;
@@ -1011,36 +1045,40 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
             GCU_CHECK(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)cfg->device));
             GCU_CHECK(cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, (int)cfg->device));
             GCU_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-            cudaMemPool_t pool = nullptr;
-            GCU_CHECK(cudaDeviceGetDefaultMemPool(&pool, (int)cfg->device));
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = (int)cfg->device;
+            GCU_CHECK(cudaMemPoolCreate(&e->pool, &props));
             uint64_t keep = ~0ull;                       // freed blocks stay in the pool for the next step
-            GCU_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            // Put some memory into the pool up front (one allocation, released straight back to the pool): the first
-            // steps of a run then grow their buffers without a trip to the driver each time.
-            // GAMBA_POOL_PREWARM_GB (default 6, capped at a quarter of the free memory; 0 = off)
-            {
-                size_t free_b = 0, total_b = 0;
-                GCU_CHECK(cudaMemGetInfo(&free_b, &total_b));
-                const char* pw = std::getenv("GAMBA_POOL_PREWARM_GB");
-                const double want_gb = pw ? std::atof(pw) : 6.0;
-                uint64_t have = 0;
-                GCU_CHECK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &have));
-                const size_t want = (size_t)std::min<double>(want_gb * 1e9, (double)free_b / 4);
-                if (want > have + (64u << 20)) {
+            GCU_CHECK(cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            // GAMBA_POOL_PREWARM_GB=n (default off): one allocation of n GB, released straight back to the pool, so that the
+            // first steps of a run grow their buffers without a trip to the driver each time
+            if (const char* pw = std::getenv("GAMBA_POOL_PREWARM_GB")) {
+                const double want_gb = std::atof(pw);
+                if (want_gb > 0) {
                     void* warm = nullptr;
-                    if (cudaMallocAsync(&warm, want - have, e->stream) == cudaSuccess) GCU_CHECK(cudaFreeAsync(warm, e->stream));
+                    if (cudaMallocFromPoolAsync(&warm, (size_t)(want_gb * 1e9), e->pool, e->stream) == cudaSuccess) GCU_CHECK(cudaFreeAsync(warm, e->stream));
                     else cudaGetLastError();
                     GCU_CHECK(cudaStreamSynchronize(e->stream));
                 }
             }
             for (auto& ev : e->ev) GCU_CHECK(cudaEventCreate(&ev));
             e->ctr.sm_count = (uint32_t)e->prop.multiProcessorCount;
-        } catch (...) { delete e; throw; }
+        } catch (...) { gcu::g_alloc_stream = e->stream; gcu::g_alloc_pool = e->pool; const cudaStream_t st = e->stream; const cudaMemPool_t pl = e->pool; delete e; gamba_cuda_engine::release_device(st, pl); throw; }
         *out = e;
     });
 }
 
-void gamba_cuda_destroy(gamba_cuda_engine* e) { delete e; }
+void gamba_cuda_destroy(gamba_cuda_engine* e) {
+    if (!e) return;
+    cudaSetDevice((int)e->cfg.device);
+    gcu::g_alloc_stream = e->stream; gcu::g_alloc_pool = e->pool;       // the buffers go back to the engine's pool, then the pool goes
+    const cudaStream_t st = e->stream; const cudaMemPool_t pl = e->pool;
+    delete e;
+    gamba_cuda_engine::release_device(st, pl);
+}
 
 void* gamba_cuda_host_alloc(size_t bytes) {
     void* p = nullptr;
@@ -1050,13 +1088,13 @@ void* gamba_cuda_host_alloc(size_t bytes) {
 void gamba_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int gamba_cuda_stage(gamba_cuda_engine* e, const gamba_cuda_step_in* in) {
-    return guarded([&] { GCU_CHECK(cudaSetDevice((int)e->cfg.device)); gcu::g_alloc_stream = e->stream; e->stage(in); });
+    return guarded([&] { GCU_CHECK(cudaSetDevice((int)e->cfg.device)); gcu::g_alloc_stream = e->stream; gcu::g_alloc_pool = e->pool; e->stage(in); });
 }
 
 int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out) {
     return guarded([&] {
         GCU_CHECK(cudaSetDevice((int)e->cfg.device));
-        gcu::g_alloc_stream = e->stream;
+        gcu::g_alloc_stream = e->stream; gcu::g_alloc_pool = e->pool;
         const double t0 = gcu::wall_s();
         e->run_reduce(out);
         out->seconds_total = gcu::wall_s() - t0;
@@ -1066,7 +1104,7 @@ int gamba_cuda_reduce_staged(gamba_cuda_engine* e, gamba_cuda_step_out* out) {
 int gamba_cuda_reduce(gamba_cuda_engine* e, const gamba_cuda_step_in* in, gamba_cuda_step_out* out) {
     return guarded([&] {
         GCU_CHECK(cudaSetDevice((int)e->cfg.device));
-        gcu::g_alloc_stream = e->stream;
+        gcu::g_alloc_stream = e->stream; gcu::g_alloc_pool = e->pool;
         const double t0 = gcu::wall_s();
         e->stage(in);
         e->run_reduce(out);
