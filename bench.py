@@ -1,24 +1,27 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: F4 linear-algebra throughput, nnz reduced per second.
+"""Benchmark of the hot path: F4 linear-algebra throughput, nnz reduced per second (BASELINE.json's metric, quoted on
+cyclic9 and kat15).
 
-Workload (config.workload): the F4 step matrices of cyclic9-15 (BASELINE.json: the metric is quoted
-on cyclic9 / kat15; cyclic9-15 is the largest named system whose whole run fits the default time
-budget) with at least --min-nnz non-zeros. The matrices are produced on the box by the product
-driver (`gamba --dump-steps`, untimed workload generation). One bench "step" = one pass of
-gamba_cuda_reduce over that batch of matrices.
+Workload (config.workload): EVERY F4 step matrix of cyclic9-15 (default options, 46 steps) and EVERY 6TH step matrix of
+kat15-15 (default options, 10 of its 60 steps: the whole run is 1.3e10 nnz and 13 s of kernels per pass, too much for the K + W
+passes the driver asks for; every 6th step is an unbiased sample of the run, from the 5 k-row steps of the first rounds to the
+500 k x 500 k ones of the last), produced on the box by the product driver (`gamba --dump-steps`, untimed workload generation).
+One bench "step" = one pass of the engine over all those matrices in F4 order, one engine per system, so that every choice the
+engine makes from the previous step (kernel choice, predicted rank of the Monte-Carlo echelon) is made as in a real run.
 
-  value   Σ nnz_in / time, steps already staged in HBM (gamba_cuda_stage once, untimed;
-          gamba_cuda_reduce_staged in the timed region: kernels + result D2H)
-  e2e     the same through gamba_cuda_reduce with pinned HOST buffers: H2D + staging kernels +
-          elimination + echelon + D2H all inside the timed region
-  roofline  elimination stage (C|D by A|B = elim_kernel for the multipliers + the tensor-core product
-          D' = D + M B): algorithmic bytes (fma_top*(4+w) + nnz_in*(4+w) + n_bot*n_nonpiv*8)
-          / CUDA-event time of the stage / measured HBM peak; `parts` splits the time and gives the
-          product's int8 multiply-add rate against the measured IMMA peak
-  cpu_baseline  the CPU oracle (a port: the reference's engine is closed source) on a bounded sample
+  value     Σ nnz_in / time with the index arrays of every step already resident in HBM (GAMBA_CUDA_STEP_DEVICE_INDICES;
+            coefficient arrays resident through the engine's coeff_cache): staging kernels + operand builds + elimination +
+            echelon + result D2H are all inside the timed region
+  e2e       the same through gamba_cuda_reduce from pinned HOST buffers: H2D + everything above
+  roofline  dominant kernel = limb_gemm_tc_kernel (every dense mod-p product of the elimination stage, tcgen05 kind::i8):
+            int8 multiply-adds of all its launches / CUDA-event time of the stage without the operand builds / int8 tensor
+            peak MEASURED in the same run (gamba_cuda_measure_int8_peak); the survey's algorithmic-bytes figure (§8(d)) beside it
+  cpu_baseline  the CPU oracle (a port: the reference's engine is closed source), single thread, on a bounded sample
+  parity_check  untimed: every matrix reduced once more by an independent configuration on rank 0 (N > 1: a world_size = 1
+            engine; N = 1: the sparse-kernel path, panel = 0) and compared by checksum
 
-`--impl reference` times the oracle port on bounded samples of the same workload (1 thread: the
-reference is single-threaded, README.md:9,71).
+`--impl reference` runs the oracle's checker mode with all host threads on bounded samples of the SAME matrices (config is
+identical; `cpu_baseline.sample` says what a step was).
 """
 from __future__ import annotations
 
@@ -26,12 +29,14 @@ import argparse
 import glob
 import json
 import os
+import re
 import shutil
 import subprocess
 import sys
 import tempfile
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -40,6 +45,10 @@ import numpy as np  # noqa: E402
 
 METRIC = "F4 lin-alg nnz reduced/s"
 WORK_DIR = os.path.join(tempfile.gettempdir(), "gamba_b200_bench")
+DEFAULT_SYSTEMS = "cyclic9-15:2000:1,kat15-15:2000:6"          # system:max_spairs:every-nth-step
+GAMBA = os.path.join(ROOT, "gamba_b200", "bin", "gamba")
+README_SECONDS = {"cyclic9-15": 17.8, "cyclic9-31": 26.1, "kat15-15": 318.5, "kat15-31": 423.3, "eco15-31": 97.7,
+                  "kat14-15": 59.4, "eco14-15": 16.6}   # closed reference binary, Ryzen 5 3600, 1 thread (README.md:18-23,42-47)
 
 
 def measured_peaks():
@@ -48,15 +57,6 @@ def measured_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:  # noqa: BLE001
         return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def measured_traffic():
-    """DRAM bytes per elimination-kernel launch from the committed ncu capture (profiles/), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01d_elim_traffic.json")) as f:
-            return float(json.load(f)["mean_dram_bytes_per_launch"])
-    except Exception:  # noqa: BLE001
-        return None
 
 
 def cpu_model() -> str:
@@ -115,18 +115,29 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def generate_workload(system: str, min_nnz: int, rank: int, world: int, max_spairs: int = 2000) -> list[str]:
-    """Step matrices of `system` with >= min_nnz non-zeros, produced by the product driver on this box."""
+# ---------------------------------------------------------------------------------------------- workload
+
+def parse_systems(spec: str):
+    out = []
+    for item in spec.split(","):
+        f = item.split(":")
+        out.append((f[0], int(f[1]) if len(f) > 1 and f[1] else 2000, int(f[2]) if len(f) > 2 and f[2] else 1))
+    return out
+
+
+def generate_workload(system: str, max_spairs: int, min_nnz: int, rank: int, world: int, every: int = 1):
+    """Step matrices of `system`, produced by the product driver on this box (rank 0; the others wait). Returns
+    (step files in F4 order, seconds of the driver run that wrote them)."""
     from gamba_b200 import systems
-    d = os.path.join(WORK_DIR, f"{system}_{min_nnz}" + ("" if max_spairs == 2000 else f"_sp{max_spairs}"))
+    d = os.path.join(WORK_DIR, f"{system}_sp{max_spairs}_min{min_nnz}_every{every}")
     done = os.path.join(d, "DONE")
     if rank == 0 and not os.path.exists(done):
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
         inp = systems.write_system(system, os.path.join(d, system + ".txt"))
         t = time.time()
-        r = subprocess.run([os.path.join(ROOT, "gamba_b200", "bin", "gamba"), "-i", inp, "-o", os.path.join(d, "out.txt"),
-                            "-v", "1", "--dump-steps", d, "--dump-min-nnz", str(min_nnz), "--max-spairs", str(max_spairs)],
+        r = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out.txt"), "-v", "1", "--dump-steps", d,
+                            "--dump-min-nnz", str(min_nnz), "--dump-every", str(every), "--max-spairs", str(max_spairs)],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("workload generation failed (no CPU fallback): " + r.stderr[-2000:])
@@ -144,84 +155,148 @@ def generate_workload(system: str, min_nnz: int, rank: int, world: int, max_spai
 
 
 def load_workload(args, rank: int, world: int):
-    """List of step matrices: the named system's F4 steps, or `synthetic:ROWSxCOLS[:density[:bits]]`
-    (BASELINE.json configs[4]: F4-shaped random matrix, every rank generates the same one from the seed)."""
+    """[(system, max_spairs, [Step ...])], description. `synthetic:ROWSxCOLS[:density[:bits]]` gives BASELINE.json
+    configs[4] (one F4-shaped random matrix, every rank generates the same one from the seed)."""
     from gamba_b200 import load_step
     from gamba_b200.stepfile import synthetic_step_large
-    if args.system.startswith("synthetic:"):
-        parts = args.system.split(":")
+    if args.systems.startswith("synthetic:"):
+        parts = args.systems.split(":")
         nr, nc = (int(x) for x in parts[1].lower().split("x"))
         dens = float(parts[2]) if len(parts) > 2 else 0.005
         p = {"15": 32003, "31": 2147483647}[parts[3] if len(parts) > 3 else "31"]
-        return [synthetic_step_large(nr, nc, dens, p)], f"synthetic F4-shaped matrix {nr} x {nc}, density {dens}, p={p}, seed 967557673"
-    files = generate_workload(args.system, args.min_nnz, rank, world, args.max_spairs)
-    return [load_step(f) for f in files], (f"{args.system} F4 step matrices with >= {args.min_nnz} nnz" +
-                                           ("" if args.max_spairs == 2000 else f" (--max-spairs {args.max_spairs})"))
+        return ([("synthetic", 0, [synthetic_step_large(nr, nc, dens, p)])],
+                f"synthetic F4-shaped matrix {nr} x {nc}, density {dens}, p={p}, seed 967557673")
+    groups, desc = [], []
+    for name, sp, every in parse_systems(args.systems):
+        files = generate_workload(name, sp, args.min_nnz, rank, world, every)
+        steps = [load_step(f) for f in files]
+        if args.max_matrices:
+            keep = set(sorted(range(len(steps)), key=lambda i: -steps[i].nnz)[: args.max_matrices])
+            steps = [s for i, s in enumerate(steps) if i in keep]
+        groups.append((name, sp, steps))
+        desc.append(f"{name}" + ("" if sp == 2000 else f" --max-spairs {sp}") + f": {'all ' if not args.min_nnz and not args.max_matrices and every == 1 else ''}"
+                    + (f"every {every}th step, " if every > 1 else "") +
+                    f"{len(steps)} F4 step matrices" + (f" with >= {args.min_nnz} nnz" if args.min_nnz else "") +
+                    f", {sum(s.nnz for s in steps)} nnz, largest {max(s.n_rows for s in steps)} x {max(s.n_cols for s in steps)}")
+    return groups, "; ".join(desc)
+
+
+def config_of(args, wl_desc):
+    """Identical in both arms (the driver compares it)."""
+    return {"workload": wl_desc, "systems": args.systems, "min_nnz": args.min_nnz, "max_matrices": args.max_matrices,
+            "order": "one pass = every matrix once, in F4 order",
+            "l2": "inputs larger than L2: a pass cycles through every matrix (GBs of index arrays and operands) before a matrix is seen again"}
 
 
 def bytes_alg(step, fma_top: int) -> float:
+    """fma_top*(4+w) + nnz_in*(4+w) + n_bot*n_nonpiv*8."""
     w = 2 if step.p < 65536 else 4
     return fma_top * (4 + w) + step.nnz * (4 + w) + step.n_bot * step.n_nonpiv * 8
 
 
-def subsample_rows(step, every: int):
-    """Bounded sample of one step: all pivot rows, every `every`-th row to reduce."""
-    from gamba_b200.stepfile import Step
-    if every <= 1:
-        return step, 1.0
-    nt = step.n_top
-    keep = np.arange(0, step.n_bot, every) + nt
-    rp = step.row_ptr.astype(np.int64)
-    parts = [step.col[: rp[nt]]]
-    lens = []
-    for r in keep:
-        parts.append(step.col[rp[r]: rp[r + 1]]); lens.append(rp[r + 1] - rp[r])
-    row_ptr = np.concatenate([rp[: nt + 1], rp[nt] + np.cumsum(lens)]).astype(np.uint64)
-    s = Step(step.p, nt, len(keep), step.n_cols, row_ptr, np.concatenate(parts),
-             np.concatenate([step.coeff_id[:nt], step.coeff_id[keep]]), step.coeff_len, step.pool)
-    return s, len(keep) / step.n_bot
+def sample_nnz(step, sample) -> float:
+    """nnz_in counted for a thinned step: the A|B part in proportion to the rows kept, plus the rows kept."""
+    top = int(step.row_ptr[step.n_top])
+    return top * (sample.n_bot / max(step.n_bot, 1)) + (sample.nnz - top)
+
+
+def checksum(rows) -> int:
+    c = zlib.crc32(np.ascontiguousarray(rows.row_ptr).view(np.uint8))
+    c = zlib.crc32(np.ascontiguousarray(rows.col).view(np.uint8), c)
+    return zlib.crc32(np.ascontiguousarray(rows.val).view(np.uint8), c)
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+
+def choose_thinning(groups, threads: int, target_s: float):
+    """Rows kept per matrix so that one pass of the oracle over all matrices costs about target_s: calibrated on a
+    1/64 sample of every matrix (fma_top of the sample / seconds), then scaled."""
+    from gamba_b200.stepfile import thin_step
+    from oracle import oracle
+    est = 0.0
+    for _, _, steps in groups:
+        for s in steps:
+            if s.n_bot < 64 or s.nnz < 200000:
+                _, _, sec = oracle.reduce(s, threads=threads)
+                est += sec
+            else:
+                _, _, sec = oracle.reduce(thin_step(s, 64), threads=threads)
+                est += sec * 64
+    return max(1, int(np.ceil(est / target_s)))
 
 
 def run_reference(args, rank: int, world: int):
-    """Reference arm: the CPU oracle (port of the closed engine) on bounded samples of the workload."""
-    if rank != 0:
+    """Reference arm: the CPU oracle (checker mode, all host threads) on bounded samples of the same matrices."""
+    if rank != 0:          # under torchrun rank 0 alone runs the CPU arm; the other ranks exit without work
         return
-    from gamba_b200 import load_step
+    groups, wl_desc = load_workload(args, 0, 1)
+    from gamba_b200.stepfile import thin_step
     from oracle import oracle
     oracle.build()
-    steps, wl_desc = load_workload(args, 0, 1)
-    # smallest matrix of the batch, thinned so that one bench step is a few seconds of CPU work
-    s = min(steps, key=lambda x: x.nnz * x.n_bot)
-    est_fma = 0.5 * s.n_bot * (s.nnz / s.n_rows) * s.n_top * 0.25   # rough: quarter of the pivots hit per row
-    every = max(1, int(est_fma / 8e8 / args.ref_seconds))
-    sample, frac = subsample_rows(s, every)
-    nnz_sample = int(s.row_ptr[s.n_top]) * frac + (sample.nnz - int(s.row_ptr[s.n_top]))
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        oracle.reduce(sample)
+    threads = oracle.host_threads()
+    every = choose_thinning(groups, threads, args.ref_seconds)
+    samples, nnz_s = [], 0.0
+    for _, _, steps in groups:
+        for s in steps:
+            t = thin_step(s, every) if s.n_bot >= 2 * every else s
+            samples.append(t); nnz_s += sample_nnz(s, t)
+    for _ in range(min(args.warmup, 1)):
+        for t in samples:
+            oracle.reduce(t, threads=threads)
     t0 = time.perf_counter()
-    secs = 0.0
     for _ in range(args.steps):
-        _, _, sec = oracle.reduce(sample)
-        secs += sec
+        for t in samples:
+            oracle.reduce(t, threads=threads)
     wall = time.perf_counter() - t0
-    value = nnz_sample * args.steps / secs
-    desc = (f"{args.system} F4 step {s.n_rows}x{s.n_cols} ({s.nnz} nnz), all pivot rows + every {every}-th of the "
-            f"{s.n_bot} rows to reduce; nnz counted = that fraction of nnz_in")
+    value = nnz_s * args.steps / wall
+    desc = (f"every matrix of the workload with all its pivot rows and every {every}-th of its rows to reduce "
+            f"({len(samples)} matrices per step); nnz counted = nnz(A|B) in that proportion + nnz of the rows kept")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u64 (CPU oracle accumulators) over F_p", "data": "synthetic (generated system, no dataset)",
-        "config": {"workload": wl_desc, "sample": desc},
-        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": 1, "kind": "port", "sample": desc, "cpu": cpu_model(),
-                         "note": "oracle port; the reference's own engine (linalg_v3.hpp, kernel/*) is closed source"},
+        "vs_baseline": None, "dtype": "u64 (CPU oracle accumulators) over F_p", "data": "synthetic (generated systems, no dataset)",
+        "config": config_of(args, wl_desc),
+        "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads, "kind": "port", "sample": desc, "cpu": cpu_model(),
+                         "note": "oracle port in checker mode (all host threads); the reference's own engine (linalg_v3.hpp, "
+                                 "kernel/*) is closed source and single-threaded"},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
+# ---------------------------------------------------------------------------------------------- our arm
+
+def e2e_seconds(groups):
+    """Wall seconds of the product binary end to end per system (README.md rows beside them), rank 0, N = 1."""
+    from gamba_b200 import systems
+    out = {}
+    for name, sp, _ in groups:
+        if name == "synthetic":
+            continue
+        d = tempfile.mkdtemp(prefix="gamba_e2e_")
+        inp = systems.write_system(name, os.path.join(d, name + ".txt"))
+        t = time.perf_counter()
+        r = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out.txt"), "-v", "1", "--max-spairs", str(sp)],
+                           capture_output=True, text=True)
+        wall = time.perf_counter() - t
+        m = re.search(r"linalg \(wall\)\s+([0-9.]+) sec\s+\[device-only ([0-9.]+)\]", r.stdout)
+        extra = {}
+        if name.startswith(("kat15", "eco15")) and sp != 0:      # the GPU-preferred setting: fewer, larger steps, same basis (SURVEY.md §8(d))
+            t = time.perf_counter()
+            r0 = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out0.txt"), "-v", "0", "--max-spairs", "0"], capture_output=True, text=True)
+            same = r0.returncode == 0 and open(os.path.join(d, "out0.txt"), "rb").read() == open(os.path.join(d, "out.txt"), "rb").read()
+            extra = {"seconds_max_spairs_0": time.perf_counter() - t if r0.returncode == 0 else None, "same_basis_as_default_run": same}
+        out[name] = {"seconds": wall if r.returncode == 0 else None, "max_spairs": sp, **extra,
+                     "linalg_wall_s": float(m.group(1)) if m else None, "linalg_device_s": float(m.group(2)) if m else None,
+                     "reference_binary_seconds": README_SECONDS.get(name),
+                     "reference_binary_note": "closed GamBa binary, Ryzen 5 3600, 1 thread, default options (README.md:18-23,42-47)"}
+        shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
-    from gamba_b200 import LinalgEngine, load_step, parallel
+    from gamba_b200 import LinalgEngine, _lib, parallel
     from gamba_b200.stepfile import Step
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
@@ -229,37 +304,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    steps, wl_desc = load_workload(args, rank, world)
-    if args.max_matrices:
-        steps = sorted(steps, key=lambda s: -s.nnz)[: args.max_matrices]
-    total_nnz = sum(s.nnz for s in steps)
-
-    def pinned(s: Step) -> Step:  # host buffers the e2e leg copies from
-        def pin(a):
-            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-            return t.numpy(), t
-        keep = []
-        out = []
-        for a in (s.row_ptr, s.col, s.coeff_id, s.coeff_len, s.pool):
-            n, t = pin(a); out.append(n); keep.append(t)
-        st = Step(s.p, s.n_top, s.n_bot, s.n_cols, *out)
-        st._pins = keep
-        return st
-    steps = [pinned(s) for s in steps]
-
-    engines = []
-    gather = parallel.make_allgather() if world > 1 else None
-    bcast = parallel.make_broadcast() if world > 1 and not args.no_bcast else None
-    for s in steps:
-        e = LinalgEngine(s.p, device=local_rank, rank=rank, world_size=world)
-        if gather:
-            e.set_allgather(gather)
-        if bcast:
-            e.set_broadcast(bcast)
-        for kv in args.opt:
-            k, v = kv.split("=")
-            e.set_option(k, int(v))
-        engines.append(e)
+    groups, wl_desc = load_workload(args, rank, world)
+    total_nnz = sum(s.nnz for _, _, steps in groups for s in steps)
+    n_mat = sum(len(steps) for _, _, steps in groups)
 
     def sync():
         torch.cuda.synchronize()
@@ -267,110 +314,186 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             import torch.distributed as dist
             dist.barrier()
 
+    gather = parallel.make_allgather() if world > 1 else None
+    bcast = parallel.make_broadcast() if world > 1 and not args.no_bcast else None
+
+    def make_engine(p, **kw):
+        e = LinalgEngine(p, device=local_rank, **kw)
+        e.set_option("coeff_cache", 1)          # as the product driver does: basis coefficient arrays stay in HBM
+        for kv in args.opt:
+            k, v = kv.split("=")
+            e.set_option(k, int(v))
+        return e
+
+    def pinned(s: Step) -> Step:                # host buffers the e2e leg copies from
+        keep, out = [], []
+        for a in (s.row_ptr, s.col, s.coeff_id, s.coeff_len, s.pool):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            out.append(t.numpy()); keep.append(t)
+        st = Step(s.p, s.n_top, s.n_bot, s.n_cols, *out)
+        st._pins = keep
+        return st
+
+    engines, residents, hosts = [], [], []
+    for _, _, steps in groups:
+        e = make_engine(steps[0].p, rank=rank, world_size=world)
+        if gather:
+            e.set_allgather(gather)
+        engines.append(e)
+        hs = [pinned(s) for s in steps]
+        hosts.append(hs)
+        residents.append([e.make_resident(s, local_rank) for s in hs])
+
     def launches():
         return sum(e.counters()["kernel_launches"] for e in engines)
 
-    # ---- value: steps resident in HBM --------------------------------------------------------
-    def mine(s):   # with the NCCL broadcast only rank 0 hands the step over
-        return s if (rank == 0 or not bcast) else None
-    for e, s in zip(engines, steps):
-        e.stage(mine(s))
-        for _ in range(3):     # untimed: the engine picks its kernels for a step from what the previous steps measured
-            e.reduce_staged()  # (F4 steps change slowly: one step per mode, then the calibrated choice); here every
-            e.stage(mine(s))   # matrix has its own engine, so it sees itself first
+    # ---- parity check (untimed): an independent configuration on rank 0 must give the same rows ----------------------
+    parity = {"status": "skipped"}
+    if not args.no_parity:
+        sums = []
+        for e, rs in zip(engines, residents):
+            sums.append([checksum(e.reduce_resident(r)) for r in rs])
+        if rank == 0:
+            bad, n_cmp = [], 0
+            for gi, (name, _, steps) in enumerate(groups):
+                chk = make_engine(steps[0].p)                 # world_size = 1
+                if world == 1:
+                    chk.set_option("panel", 0)                # N = 1: the sparse-kernel path instead of the tensor-core solve
+                for si, s in enumerate(hosts[gi]):
+                    if world == 1 and s.nnz > args.parity_max_nnz:
+                        continue
+                    n_cmp += 1
+                    if checksum(chk.reduce(s)) != sums[gi][si]:
+                        bad.append(f"{name}[{si}]")
+                chk.close()
+            parity = {"status": "ok" if not bad else "MISMATCH " + ",".join(bad), "matrices": n_cmp,
+                      "against": ("world_size=1 reduction of the same matrices on rank 0" if world > 1 else
+                                  f"sparse-kernel path (panel=0) on the matrices with <= {args.parity_max_nnz} nnz")}
+        sync()
+
+    # ---- value: index arrays resident in HBM -------------------------------------------------------------------------
+    def run_pass(collect=None):
+        for gi, (e, rs) in enumerate(zip(engines, residents)):
+            for si, r in enumerate(rs):
+                e.reduce_resident(r, copy=False)     # the result stays in the engine-owned host buffers the C ABI hands out
+                if collect is not None:
+                    collect(gi, si, e)
+
     for _ in range(args.warmup):
-        for e in engines:
-            e.reduce_staged()
+        run_pass()
     sync()
-    elim_s = [0.0] * len(steps); ech_s = [0.0] * len(steps); dev_s = 0.0
-    sparse_s = 0.0; schur_s = 0.0; schur_imma = 0.0
-    fma_top = [0] * len(steps)
+    per = {}
+
+    def collect(gi, si, e):
+        c = e.counters()
+        per[(gi, si)] = (e.last["seconds_eliminate"], e.last["seconds_echelon"], e.last["seconds_device"], c["fma_top"],
+                         c["dense_macs"], c["seconds_operands_last"], c["solve_mode"], c["seconds_sparse_last"])
     l0 = launches()
     with ClockSampler(local_rank) as clk:
         sync()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            for i, e in enumerate(engines):
-                e.reduce_staged(copy=False)     # the result stays in the engine-owned host buffers the C ABI hands out
-                elim_s[i] += e.last["seconds_eliminate"]; ech_s[i] += e.last["seconds_echelon"]
-                dev_s += e.last["seconds_eliminate"] + e.last["seconds_echelon"]
-                c_ = e.counters()
-                fma_top[i] = c_["fma_top"]
-                sparse_s += c_["seconds_sparse_last"]; schur_s += c_["seconds_schur_last"]
-                schur_imma += c_["schur_macs"] * (4 if steps[i].p < 65536 else 16)   # limb products per mod-p multiply-add
+        for i in range(args.steps):
+            run_pass(collect if i == args.steps - 1 else None)
         sync()
         t_res = time.perf_counter() - t0
     n_launch = launches() - l0
     clocks = clk.summary()
 
-    # ---- e2e: pinned host buffers in, host buffers out -----------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        for e, s in zip(engines, steps):
-            e.reduce(mine(s))
+    # ---- e2e: pinned host buffers in, host buffers out ---------------------------------------------------------------
+    if bcast:
+        for e in engines:
+            e.set_broadcast(bcast)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def run_pass_host():
+        h2d = d2h = 0
+        for e, hs in zip(engines, hosts):
+            for s in hs:
+                e.reduce(s if (rank == 0 or not bcast) else None, copy=False)
+                h2d += e.last["h2d_bytes"]; d2h += e.last["d2h_bytes"]
+        return h2d, d2h
+    run_pass_host()
     sync()
     t0 = time.perf_counter()
     h2d = d2h = 0
-    for _ in range(args.steps):
-        for e, s in zip(engines, steps):
-            e.reduce(mine(s), copy=False)
-            h2d += e.last["h2d_bytes"]; d2h += e.last["d2h_bytes"]
+    for _ in range(e2e_steps):
+        a, b = run_pass_host()
+        h2d += a; d2h += b
     sync()
     t_e2e = time.perf_counter() - t0
 
+    keys = sorted(per)
+    vals = np.array([per[k] for k in keys], dtype=np.float64)
     if world > 1:
         import torch.distributed as dist
         tt = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_res, t_e2e = float(tt[0]), float(tt[1])
-        ft = torch.tensor(fma_top, device="cuda", dtype=torch.int64)
-        dist.all_reduce(ft, op=dist.ReduceOp.SUM)   # every rank counted its own rows
-        fma_top = [int(x) for x in ft]
-        et = torch.tensor(elim_s, device="cuda", dtype=torch.float64)
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        elim_s = [float(x) for x in et]
+        vt = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        vmax = vt.clone(); dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+        vsum = vt.clone(); dist.all_reduce(vsum, op=dist.ReduceOp.SUM)
+        vals = vmax.cpu().numpy()
+        vals[:, 3] = vsum.cpu().numpy()[:, 3]          # fma_top: every rank counted its own rows
+        vals[:, 4] = vsum.cpu().numpy()[:, 4]          # dense multiply-adds: summed over the ranks
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        # dominant kernel: the C|D-by-A|B elimination; per launch = per matrix, averaged over the batch
-        alg = sum(bytes_alg(s, f) for s, f in zip(steps, fma_top)) / len(steps)
-        dur = sum(elim_s) / (args.steps * len(steps))
-        achieved = alg / dur / 1e9 / world      # per GPU: every rank streams its share of the rows
-        c = engines[0].counters()
+        hbm_peak, hbm_src = measured_peaks()
+        lib = _lib.load()
+        import ctypes as C
+        steps_flat = [groups[gi][2][si] for gi, si in keys]
+        nl2 = np.array([4.0 if s.p < 65536 else 16.0 for s in steps_flat])
+        peak_n = 128 if steps_flat[0].p < 65536 else 64
+        pk = C.c_double(0.0)
+        if lib.gamba_cuda_measure_int8_peak(local_rank, peak_n, C.byref(pk)):
+            raise RuntimeError("gamba_cuda_measure_int8_peak: " + lib.gamba_cuda_last_error().decode())
+        int8_peak = pk.value                                         # TMAC/s
+        elim, ech, dev, fma_top, dense, opnd, mode, sparse = (vals[:, i] for i in range(8))
+        gemm_s = float(np.sum(np.where(mode == 2, elim - opnd, np.maximum(elim - sparse - opnd, 0.0))))   # the products' share of the stage
+        int8_macs = float(np.sum(dense * nl2))
+        achieved_tops = 2.0 * int8_macs / max(gemm_s, 1e-12) / 1e12 / world          # per GPU
+        alg = float(sum(bytes_alg(s, f) for s, f in zip(steps_flat, fma_top)))
         out = {
             "metric": METRIC, "value": total_nnz * args.steps / t_res, "unit": "nnz/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 residues mod p=%d (32-bit delayed-reduction lanes in the sparse solve; u8 limbs -> s32 on the tensor cores in the Schur product and the echelon)" % steps[0].p, "data": "synthetic (generated system, no dataset)",
-            "config": {"workload": f"{wl_desc} ({len(steps)} matrices, "
-                                   f"{total_nnz} nnz per pass, largest {max(s.n_rows for s in steps)} x {max(s.n_cols for s in steps)})",
-                       "parallelism": (f"C|D rows sharded r % {world}, step uploaded by rank 0 and replicated by NCCL broadcast, "
+            "dtype": "u32 residues mod p; u8 limbs -> s32 accumulators on the tensor cores (tcgen05 kind::i8) in every dense product "
+                     "and the echelon; 32-bit delayed-reduction lanes in the sparse kernels",
+            "data": "synthetic (generated systems, no dataset)",
+            "config": config_of(args, wl_desc),
+            "engine": {"parallelism": (f"C|D rows sharded r % {world}; value: every rank holds the step; e2e: rank 0 uploads, NCCL broadcast; "
                                        f"NCCL all-gather of D' rows, echelon replicated") if world > 1 else "1 GPU",
-                       "l2": "inputs larger than L2 (every pass cycles through all matrices; smallest staged step > 126 MB)",
-                       "max_spairs": args.max_spairs, "tile_cols": c["tile_cols"], "acc_bits": c["acc_bits"]},
-            "e2e": {"value": total_nnz * args.steps / t_e2e, "unit": "nnz/s", "h2d_bytes_per_step": h2d // args.steps,
-                    "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
+                       "matrices_per_step": n_mat, "nnz_per_step": total_nnz,
+                       "solve_modes": {"sparse": int(np.sum(mode == 0)), "sparse_blocked": int(np.sum(mode == 1)),
+                                       "tensor_core_blocked_solve": int(np.sum(mode == 2))}},
+            "e2e": {"value": total_nnz * e2e_steps / t_e2e, "unit": "nnz/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                    "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": n_launch,
             "clocks": clocks,
-            "roofline": {"kernel": "elimination stage C|D by A|B: elim_kernel (walk of the pivot windows) + schur_tc_kernel per column "
-                                   "tile (earlier pivots' contribution, tcgen05) for the multipliers M; schur_bt_kernel + schur_tc_kernel "
-                                   "for D' = D + M B",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic() if args.system == "cyclic9-15" else None,
-                         "traffic_source": "ncu dram__bytes_read+write of the stage's kernels per matrix, profiles/r01d_elim_traffic.json",
-                         "peak_source": peak_src,
-                         "parts": {"sparse_solve_ms_per_step": 1e3 * sparse_s / args.steps, "schur_ms_per_step": 1e3 * schur_s / args.steps,
-                                   "schur_tensor": {"achieved": schur_imma / max(schur_s, 1e-12) / 1e12, "peak": 2250.0, "unit": "int8 TMAC/s",
-                                                    "frac": schur_imma / max(schur_s, 1e-12) / 1e12 / 2250.0,
-                                                    "peak_source": "nominal dense int8 of tcgen05 on B200 (4.5 POP/s = 2x the bf16 rate; MEASURED_PEAKS.json "
-                                                                   "has cuBLAS bf16 at 1648 TFLOP/s = 1648 int8-equivalent TMAC/s); the time includes "
-                                                                   "zeroing the multiplier planes"}},
-                         "bytes_alg_per_launch": alg, "avg_launch_ms": dur * 1e3,
-                         "share_of_device_time": sum(elim_s) / max(dev_s, 1e-12),
-                         "fma_top_per_pass": int(sum(fma_top))},
-            "breakdown_ms_per_step": {"eliminate": 1e3 * sum(elim_s) / args.steps, "echelon": 1e3 * sum(ech_s) / args.steps},
+            "parity_check": parity,
+            "roofline": {"kernel": "limb_gemm_tc_kernel: every dense mod-p product of the elimination stage (blocked triangular solve: "
+                                   "earlier-tile products, inverse-tile products, recursive doubling; D' = D + M B), tcgen05 kind::i8 on u8 limb planes",
+                         "bound": "tensor", "achieved": achieved_tops, "peak": 2.0 * int8_peak, "unit": "TOP/s (int8, 2 per multiply-add)",
+                         "frac": achieved_tops / (2.0 * int8_peak),
+                         "peak_source": f"measured in this run: tcgen05.mma kind::i8 128x{peak_n}x32 from shared memory on all SMs "
+                                        f"(gamba_cuda_measure_int8_peak); nominal dense int8 4500 TOP/s",
+                         "traffic": None, "traffic_note": "not measured inside bench.py; ncu captures of the kernel are under profiles/",
+                         "launch_time_basis": "CUDA events on the engine's stream around the stage, minus the operand builds; includes the small "
+                                              "scatter / base-inverse kernels between the products (conservative)",
+                         "int8_macs_per_step": int8_macs, "avg_stage_ms_per_matrix": 1e3 * gemm_s / max(len(keys), 1),
+                         "share_of_device_time": float(np.sum(elim) / max(np.sum(dev), 1e-12)),
+                         "hbm_alg": {"note": "SURVEY.md §8(d) figure: algorithmic bytes of the sparse row-by-row elimination / elimination time / "
+                                             "measured HBM peak; > 1 because the stage is dense products, not streamed pivot rows",
+                                     "achieved": alg / max(float(np.sum(elim)), 1e-12) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": alg / max(float(np.sum(elim)), 1e-12) / 1e9 / world / hbm_peak, "peak_source": hbm_src,
+                                     "fma_top_per_step": float(np.sum(fma_top))}},
+            "breakdown_ms_per_step": {"staging_kernels": 1e3 * float(np.sum(dev - elim - ech)), "operand_builds": 1e3 * float(np.sum(opnd)),
+                                      "eliminate_without_operands": 1e3 * float(np.sum(elim - opnd)), "echelon": 1e3 * float(np.sum(ech)),
+                                      "device_total": 1e3 * float(np.sum(dev))},
         }
+        if world == 1 and not args.no_e2e_seconds:
+            out["e2e_seconds"] = e2e_seconds(groups)
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(steps, fma_top, args)
+            out["cpu_baseline"] = cpu_baseline(groups, args)
         print(json.dumps(out))
     for e in engines:
         e.close()
@@ -379,37 +502,42 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
-def cpu_baseline(steps, fma_top, args):
-    """The oracle port on a bounded sample (~args.ref_seconds of CPU work), rank 0, N=1 only."""
+def cpu_baseline(groups, args):
+    """The oracle port, single thread (the reference is single-threaded, README.md:9,71), on a bounded sample, rank 0, N=1."""
+    from gamba_b200.stepfile import thin_step
     from oracle import oracle
     oracle.build()
-    i = min(range(len(steps)), key=lambda k: fma_top[k])
-    s, f = steps[i], fma_top[i]
-    every = max(1, int(f / 8e8 / args.ref_seconds))
-    sample, frac = subsample_rows(s, every)
-    nnz_sample = int(s.row_ptr[s.n_top]) * frac + (sample.nnz - int(s.row_ptr[s.n_top]))
+    name, _, steps = groups[0]
+    cand = [s for s in steps if s.nnz >= 1_000_000] or steps
+    s = min(cand, key=lambda x: x.nnz * x.n_bot)
+    _, fma, sec = oracle.reduce(thin_step(s, 16) if s.n_bot >= 64 else s)
+    every = max(1, int(np.ceil(sec * 16 / args.cpu_seconds))) if s.n_bot >= 64 else 1
+    sample = thin_step(s, every)
     _, fma, sec = oracle.reduce(sample)
-    return {"value": nnz_sample / sec, "unit": "nnz/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
-            "sample": f"{args.system} F4 step {s.n_rows}x{s.n_cols} ({s.nnz} nnz), all pivot rows + every {every}-th of the "
-                      f"{s.n_bot} rows to reduce ({fma:.3g} multiply-adds, {sec:.1f} s); nnz counted = that fraction of nnz_in",
+    return {"value": sample_nnz(s, sample) / sec, "unit": "nnz/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
+            "sample": f"{name} F4 step {s.n_rows}x{s.n_cols} ({s.nnz} nnz), all pivot rows + every {every}-th of the {s.n_bot} rows to "
+                      f"reduce ({fma:.3g} multiply-adds, {sec:.1f} s); nnz counted = nnz(A|B) in that proportion + nnz of the rows kept",
             "fma_per_s": fma / sec,
-            "note": "oracle port; the reference's own engine is closed source. Published end-to-end (closed binary, "
-                    "Ryzen 5 3600, 1 thread): cyclic9-15 17.8 s (README.md:18)"}
+            "note": "oracle port, timing mode; the reference's own engine is closed source"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--system", default="cyclic9-15")
-    ap.add_argument("--min-nnz", type=int, default=15_000_000)
-    ap.add_argument("--max-matrices", type=int, default=0)
-    ap.add_argument("--max-spairs", type=int, default=2000, help="pair cap of the driver run that produces the matrices (0 = none)")
-    ap.add_argument("--ref-seconds", type=float, default=6.0)
+    ap.add_argument("--systems", default=DEFAULT_SYSTEMS, help="system:max_spairs:every[,...] or synthetic:ROWSxCOLS[:density[:bits]]")
+    ap.add_argument("--min-nnz", type=int, default=0, help="only step matrices with at least this many non-zeros (default: all)")
+    ap.add_argument("--max-matrices", type=int, default=0, help="only the N largest matrices of each system (default: all)")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="passes of the host-buffer leg (at most --steps)")
+    ap.add_argument("--ref-seconds", type=float, default=6.0, help="--impl reference: CPU seconds one sampled pass should cost")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="cpu_baseline: CPU seconds of the sample")
+    ap.add_argument("--parity-max-nnz", type=int, default=60_000_000, help="N=1 parity check: matrices above this are skipped (sparse path: seconds each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-bcast", action="store_true", help="N>1: every rank uploads the step itself (no NCCL broadcast)")
+    ap.add_argument("--no-e2e-seconds", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-bcast", action="store_true", help="N>1 e2e leg: every rank uploads the step itself (no NCCL broadcast)")
     ap.add_argument("--opt", nargs="*", default=[], help="engine options key=value (gamba_cuda_set_option)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

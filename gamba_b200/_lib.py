@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libgamba_cuda.so")
 
 REPR_STANDARD, REPR_MONTGOMERY = 0, 1
 STEP_FINAL = 1
+STEP_DEVICE_INDICES = 2
 
 
 class Config(C.Structure):
@@ -38,7 +39,8 @@ class Counters(C.Structure):
                 ("seconds_stage_last", C.c_double), ("seconds_sparse_last", C.c_double),
                 ("seconds_schur_last", C.c_double), ("schur_macs", C.c_uint64),
                 ("mc_ech_combinations", C.c_uint32), ("solve_mode", C.c_uint32), ("dense_macs", C.c_uint64),
-                ("seconds_inverse_last", C.c_double), ("panel_t", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("seconds_inverse_last", C.c_double), ("panel_t", C.c_uint32), ("reserved0", C.c_uint32),
+                ("seconds_operands_last", C.c_double)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
@@ -47,7 +49,7 @@ BROADCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
 # every symbol include/gamba_cuda.h declares
 SYMBOLS = ["gamba_cuda_abi_version", "gamba_cuda_last_error", "gamba_cuda_create", "gamba_cuda_destroy",
            "gamba_cuda_reduce", "gamba_cuda_stage", "gamba_cuda_reduce_staged", "gamba_cuda_set_allgather", "gamba_cuda_set_broadcast", "gamba_cuda_host_alloc", "gamba_cuda_host_free",
-           "gamba_cuda_get_counters", "gamba_cuda_set_option"]
+           "gamba_cuda_get_counters", "gamba_cuda_set_option", "gamba_cuda_measure_int8_peak"]
 
 _lib = None
 
@@ -72,5 +74,6 @@ def load() -> C.CDLL:
     lib.gamba_cuda_set_broadcast.argtypes = [C.c_void_p, BROADCAST_FN, C.c_void_p]
     lib.gamba_cuda_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
     lib.gamba_cuda_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    lib.gamba_cuda_measure_int8_peak.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     _lib = lib
     return lib

@@ -198,6 +198,7 @@ struct gamba_cuda_engine {
     uint32_t flags = 0;
     uint64_t nnz = 0;
     gcu::DevBuf d_row_ptr, d_col, d_coeff_id, d_coeff_off, d_pool, d_row_src, d_col_map;
+    const uint64_t* s_row_ptr = nullptr;    // row pointers of the staged step on the device (ours, or the caller's with DEVICE_INDICES)
     gcu::DevBuf d_seg, d_ent, d_diag, d_dnz, d_first, d_scan_tmp;
     gcu::HostBuf h_pool, h_off;
     uint64_t h2d_bytes = 0;
@@ -342,9 +343,12 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     const bool have = !use_bcast || cfg.rank == 0;       // this rank uploads the step from its host buffers
     if (have && !in) throw std::runtime_error("no step passed (only ranks > 0 of a broadcasting group may pass NULL)");
     StepHdr hd{};
+    // GAMBA_CUDA_STEP_DEVICE_INDICES: the index arrays of the step already live on this device and are used where they are
+    const bool dev_idx = have && (in->flags & GAMBA_CUDA_STEP_DEVICE_INDICES) != 0;
+    if (dev_idx && use_bcast) throw std::runtime_error("device-resident index arrays cannot be combined with the broadcast callback");
     if (have) {
         if (in->n_cols < in->n_top) throw std::runtime_error("n_cols < n_top");
-        if (in->row_ptr[in->n_top + in->n_bot] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
+        if (!dev_idx && in->row_ptr[in->n_top + in->n_bot] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
         hd.n_top = in->n_top; hd.n_bot = in->n_bot; hd.n_cols = in->n_cols; hd.n_arr = in->n_coeff_arrays;
         hd.nnz = in->nnz; hd.flags = in->flags;
         hd.n_src = in->col_idx_len ? in->col_idx_len : in->nnz;
@@ -365,7 +369,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     }
     const uint32_t n_rows = hd.n_top + hd.n_bot;
     choose_layout(hd.n_top, hd.n_bot, hd.n_cols);
-    flags = hd.flags; nnz = hd.nnz;
+    flags = hd.flags & ~GAMBA_CUDA_STEP_DEVICE_INDICES; nnz = hd.nnz;
     if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
     if (nnz + 1ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
@@ -420,27 +424,31 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         if (cached) { uint64_t t = 0; for (uint32_t i : fresh) { pack_one(i, pool + t); t += in->coeff_len[i]; } }
         else if (have) for (uint32_t i = 0; i < na; ++i) pack_one(i, pool + off[i]);
     };
-    d_row_ptr.ensure((n_rows + 1) * sizeof(uint64_t));
-    d_col.ensure(std::max<uint64_t>(hd.n_src, 1) * sizeof(uint32_t));
-    if (hd.has_row_src) d_row_src.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint64_t));
-    if (hd.col_map_len) d_col_map.ensure((size_t)hd.col_map_len * sizeof(uint32_t));
-    d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
+    if (!dev_idx) {
+        d_row_ptr.ensure((n_rows + 1) * sizeof(uint64_t));
+        d_col.ensure(std::max<uint64_t>(hd.n_src, 1) * sizeof(uint32_t));
+        if (hd.has_row_src) d_row_src.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint64_t));
+        if (hd.col_map_len) d_col_map.ensure((size_t)hd.col_map_len * sizeof(uint32_t));
+        d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
+    }
     d_coeff_off.ensure((na + 1) * sizeof(uint64_t));
     if (!cached) d_pool.ensure(std::max<uint64_t>(tot, 1) * sizeof(uint32_t));
     h2d_bytes = 0;
     dbg_[1] += wall_s() - tq; tq = wall_s();
     if (have) {
-        GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-        GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, hd.n_src * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        if (hd.has_row_src) GCU_CHECK(cudaMemcpyAsync(d_row_src.p, in->row_src, n_rows * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-        if (hd.col_map_len) GCU_CHECK(cudaMemcpyAsync(d_col_map.p, in->col_map, (size_t)hd.col_map_len * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        if (!dev_idx) {
+            GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+            GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, hd.n_src * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            if (hd.has_row_src) GCU_CHECK(cudaMemcpyAsync(d_row_src.p, in->row_src, n_rows * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+            if (hd.col_map_len) GCU_CHECK(cudaMemcpyAsync(d_col_map.p, in->col_map, (size_t)hd.col_map_len * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        }
         // the coefficient pool is packed while the column indices (page-locked at the caller: a plain DMA) are in flight
         pack_pool();
         GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
         if (tot) GCU_CHECK(cudaMemcpyAsync(d_pool.as<uint32_t>() + pool_base, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        h2d_bytes = (n_rows + 1) * 8ull + hd.n_src * 4ull + n_rows * 4ull + (na + 1) * 8ull + tot * 4ull +
-                    (hd.has_row_src ? n_rows * 8ull : 0) + hd.col_map_len * 4ull;
+        h2d_bytes = (na + 1) * 8ull + tot * 4ull;
+        if (!dev_idx) h2d_bytes += (n_rows + 1) * 8ull + hd.n_src * 4ull + n_rows * 4ull + (hd.has_row_src ? n_rows * 8ull : 0) + hd.col_map_len * 4ull;
     }
     if (use_bcast) {   // A|B and C|D replicated over NVLink instead of one H2D copy per rank
         const std::pair<void*, size_t> bufs[] = {{d_row_ptr.p, (n_rows + 1) * sizeof(uint64_t)}, {d_col.p, hd.n_src * sizeof(uint32_t)},
@@ -467,12 +475,14 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
 
     PrepArgs pa{};
     pa.L = L; pa.f = f;
-    pa.row_ptr = d_row_ptr.as<uint64_t>(); pa.col = d_col.as<uint32_t>(); pa.coeff_id = d_coeff_id.as<uint32_t>();
+    pa.row_ptr = dev_idx ? in->row_ptr : d_row_ptr.as<uint64_t>(); pa.col = dev_idx ? in->col_idx : d_col.as<uint32_t>();
+    pa.coeff_id = dev_idx ? in->coeff_id : d_coeff_id.as<uint32_t>();
+    s_row_ptr = pa.row_ptr;
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
     pa.seg = d_seg.as<uint32_t>(); pa.ent = d_ent.as<uint2>();
     pa.diag = d_diag.as<uint32_t>(); pa.dinv = d_dinv.as<uint32_t>(); pa.dnz = d_dnz.as<uint32_t>();
-    pa.row_src = hd.has_row_src ? d_row_src.as<uint64_t>() : nullptr;
-    pa.col_map = hd.col_map_len ? d_col_map.as<uint32_t>() : nullptr;
+    pa.row_src = hd.has_row_src ? (dev_idx ? in->row_src : d_row_src.as<uint64_t>()) : nullptr;
+    pa.col_map = hd.col_map_len ? (dev_idx ? in->col_map : d_col_map.as<uint32_t>()) : nullptr;
     pa.first_piv = d_first.as<uint32_t>(); pa.first_min = d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1);
     GCU_CHECK(cudaMemsetAsync(pa.first_min, 0xff, sizeof(uint32_t), stream));
     if (n_rows) {
@@ -592,7 +602,7 @@ void gamba_cuda_engine::eliminate() {
     ea.list_k = d_list_k.as<uint32_t>(); ea.list_m = d_list_m.as<uint32_t>();
     ea.queue = d_queue_stats.as<uint32_t>();
     ea.stats = reinterpret_cast<unsigned long long*>(d_queue_stats.as<char>() + 16);
-    ea.row_ptr = d_row_ptr.as<uint64_t>();
+    ea.row_ptr = s_row_ptr;
     ea.mc_rows = mc_k ? L.n_bot : 0;
     ea.mc_seed = cfg.seed * 0x9e3779b97f4a7c15ull + mc_draw;
     if (mc_k) { GCU_CHECK(cudaMemcpyAsync(&ea.mc_first, d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); GCU_CHECK(cudaStreamSynchronize(stream)); }
@@ -723,7 +733,7 @@ void gamba_cuda_engine::eliminate() {
             xa.kchunk = tkc; xa.k_end = (tw + TC_BK - 1) / TC_BK * TC_BK;
             xa.b_row0 = t * T; xa.neg = 1; xa.tri = 2;
             xa.o1 = d_mx.as<uint8_t>(); xa.o1_plane = mx_plane; xa.o1_ld = kp; xa.o1_col0 = t * T;
-            xa.stats = ea.stats; xa.cnt_row_ptr = d_row_ptr.as<uint64_t>();
+            xa.stats = ea.stats; xa.cnt_row_ptr = s_row_ptr;
             launch_limb_gemm<EPI_LIMBS>(f.small != 0, map_cx, map_vt, xa, 1, stream);
             ctr.kernel_launches += 3;
         }
@@ -925,6 +935,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[6], ev[7])); t_sparse_dev = ms * 1e-3;
     GCU_CHECK(cudaEventElapsedTime(&ms, ev[6], ev[8])); t_inv_dev = (use_schur && use_panel && n_local) ? ms * 1e-3 : 0.0;
     ctr.seconds_inverse_last = t_inv_dev;
+    GCU_CHECK(cudaEventElapsedTime(&ms, ev[2], ev[6])); ctr.seconds_operands_last = ms * 1e-3;
     ctr.solve_mode = (use_schur && n_local) ? (use_panel ? 2u : use_block ? 1u : 0u) : 0u;
     ctr.panel_t = ctr.solve_mode == 2 ? PANEL_T : 0u;
     t_schur_dev = t_elim_dev - t_sparse_dev;
@@ -1118,6 +1129,35 @@ int gamba_cuda_set_allgather(gamba_cuda_engine* e, gamba_cuda_allgather_fn fn, v
 
 int gamba_cuda_set_broadcast(gamba_cuda_engine* e, gamba_cuda_broadcast_fn fn, void* user) {
     return guarded([&] { e->bcast_fn = fn; e->bcast_user = user; });
+}
+
+int gamba_cuda_measure_int8_peak(uint32_t device, uint32_t n, double* tmacs_per_s) {
+    return guarded([&] {
+        if (!tmacs_per_s || (n != 64 && n != 128 && n != 256)) throw std::runtime_error("n must be 64, 128 or 256");
+        GCU_CHECK(cudaSetDevice((int)device));
+        cudaDeviceProp prop{};
+        GCU_CHECK(cudaGetDeviceProperties(&prop, (int)device));
+        if (prop.major < 10) throw std::runtime_error("this library is built for sm_100a (B200) only");
+        cudaStream_t st; cudaEvent_t e0, e1;
+        GCU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        GCU_CHECK(cudaEventCreate(&e0)); GCU_CHECK(cudaEventCreate(&e1));
+        const uint32_t iters = 20000, grid = (uint32_t)prop.multiProcessorCount;
+        auto kern = n == 64 ? gcu::tc_peak_kernel<64> : n == 128 ? gcu::tc_peak_kernel<128> : gcu::tc_peak_kernel<256>;
+        const size_t smem = gcu::tc_peak_smem(n);
+        GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {          // first repetition = warm-up
+            GCU_CHECK(cudaEventRecord(e0, st));
+            kern<<<grid, 128, smem, st>>>(iters);
+            GCU_CHECK(cudaGetLastError());
+            GCU_CHECK(cudaEventRecord(e1, st));
+            GCU_CHECK(cudaStreamSynchronize(st));
+            float ms = 0; GCU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep) best = std::min(best, ms);
+        }
+        *tmacs_per_s = (double)grid * iters * 4.0 * 128.0 * n * 32.0 / (best * 1e-3) / 1e12;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    });
 }
 
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c) {

@@ -346,4 +346,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// ---- microbenchmark: the int8 tensor rate one SM sustains with its operands already in shared memory -----------------
+// (the denominator of bench.py's tensor roofline: MEASURED_PEAKS.json only has cuBLAS bf16). One CTA per SM, one thread
+// issues `iters` x 4 tcgen05.mma kind::i8 of 128 x N x 32 into one accumulator, back to back, and waits for the last commit.
+__host__ __device__ constexpr size_t tc_peak_smem(uint32_t n) { return (size_t)(TC_BM + n) * TC_BK + 1024 + 64; }
+
+template <int N>
+__global__ void __launch_bounds__(128, 1) tc_peak_kernel(uint32_t iters) {
+    constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    extern __shared__ unsigned char tcp_raw[];
+    __shared__ uint32_t s_tmem;
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(tcp_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u, bar = base + (TC_BM + N) * TC_BK;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(TC_BM + N) * TC_BK / 4; i += 128) reinterpret_cast<uint32_t*>(tcp_raw + (base - raw))[i] = i * 2654435761u;
+    if (threadIdx.x == 0) { tc_mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the generic-proxy fill above is read by the tensor cores
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (threadIdx.x == 0) {
+        for (uint32_t it = 0; it < iters; ++it)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                tc_mma_i8(tmem, tc_smem_desc(base + kk * 32), tc_smem_desc(base + TC_BM * TC_BK + kk * 32), IDESC, (it | kk) ? 1u : 0u);
+        tc_commit(bar);
+        tc_mbar_wait(bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace gcu

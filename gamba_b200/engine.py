@@ -20,7 +20,7 @@ class LinalgEngine:
     def __init__(self, p: int, seed: int = 967557673, device: int = 0, coeff_bytes: int = 4,
                  repr: int = _lib.REPR_STANDARD, rank: int = 0, world_size: int = 1):
         self.lib = _lib.load()
-        self.p, self.coeff_bytes = p, coeff_bytes
+        self.p, self.coeff_bytes, self.device = p, coeff_bytes, device
         cfg = _lib.Config(p, coeff_bytes, repr, device, seed, rank, world_size)
         h = C.c_void_p()
         if self.lib.gamba_cuda_create(C.byref(cfg), C.byref(h)):
@@ -57,6 +57,35 @@ class LinalgEngine:
             self._keep += (row_src, col_map)
             sin.row_src, sin.col_map, sin.col_map_len, sin.col_idx_len = row_src.ctypes.data, col_map.ctypes.data, len(col_map), len(col)
         return sin
+
+    def make_resident(self, s: Step, device: int | None = None):
+        """Copy the index arrays of a step to the engine's device (torch is only the allocator here) and return a handle
+        for reduce_resident(): the GAMBA_CUDA_STEP_DEVICE_INDICES form of the hand-over (inputs resident in HBM; the
+        coefficient arrays stay host arrays, kept on the device by the engine's own `coeff_cache`)."""
+        import torch
+        dev = torch.device("cuda", self.device if device is None else device)
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.coeff_bytes]
+        pool = np.ascontiguousarray(s.pool.astype(dt, copy=False))
+        off = s.coeff_offsets()
+        ptrs = (pool.ctypes.data + off[:-1] * self.coeff_bytes).astype(np.uint64)
+        clen = np.ascontiguousarray(s.coeff_len, dtype=np.uint32)
+
+        def up(a, dtype):     # torch has no uint64/uint32 arithmetic, but it can hold the bytes
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype).view(np.uint8)).to(dev)
+        row_ptr, col, cid = up(s.row_ptr, np.uint64), up(s.col, np.uint32), up(s.coeff_id, np.uint32)
+        keep = [pool, ptrs, clen, row_ptr, col, cid]
+        sin = _lib.StepIn(s.n_top, s.n_bot, s.n_cols, len(clen), s.nnz, row_ptr.data_ptr(), col.data_ptr(), cid.data_ptr(),
+                          ptrs.ctypes.data, clen.ctypes.data, _lib.STEP_DEVICE_INDICES)
+        if s.row_src is not None:
+            row_src, col_map = up(s.row_src, np.uint64), up(s.col_map, np.uint32)
+            keep += [row_src, col_map]
+            sin.row_src, sin.col_map, sin.col_map_len, sin.col_idx_len = row_src.data_ptr(), col_map.data_ptr(), len(s.col_map), len(s.col)
+        return (sin, keep)
+
+    def reduce_resident(self, resident, copy: bool = True) -> Rows:
+        out = _lib.StepOut()
+        self._check(self.lib.gamba_cuda_reduce(self.h, C.byref(resident[0]), C.byref(out)), "gamba_cuda_reduce")
+        return self._rows(out, copy)
 
     def _rows(self, out: _lib.StepOut, copy: bool = True) -> Rows:
         """copy=False: the arrays are views of the engine-owned result buffers (valid until the next call on the

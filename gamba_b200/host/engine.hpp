@@ -93,7 +93,8 @@ struct NewRows {
     std::vector<uint32_t> val;
     double seconds = 0.0;           // engine time for this step (f4.hpp:93)
     double kernel_seconds = 0.0;    // device-only part when known
-    uint64_t fma_top = 0;           // oracle only: SURVEY.md §8(d) invariant
+    uint64_t fma_top = 0;           // SURVEY.md §8(d) invariant
+    std::string note;               // engine's one-line account of the step (round table, -v 2)
 };
 
 struct Engine {

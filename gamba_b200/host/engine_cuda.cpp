@@ -37,7 +37,7 @@ public:
     }
     ~CudaEngine() override {
         if (std::getenv("GAMBA_DEBUG_TIMERS"))
-            std::fprintf(stderr, "dbg engine: call %.3f (stage %.3f) copy-out %.3f\n", t_call_, t_stage_, t_copy_);
+            std::fprintf(stderr, "dbg engine: call %.3f (stage %.3f) copy-out %.3f | device: eliminate %.3f echelon %.3f\n", t_call_, t_stage_, t_copy_, t_elim_, t_ech_);
         gamba_cuda_destroy(e_);
     }
     const char* name() const override { return "cuda-b200"; }
@@ -46,7 +46,7 @@ public:
 
 private:
     gamba_cuda_engine* e_ = nullptr;
-    double t_call_ = 0, t_stage_ = 0, t_copy_ = 0;
+    double t_call_ = 0, t_stage_ = 0, t_copy_ = 0, t_elim_ = 0, t_ech_ = 0;
     std::vector<const void*> ptrs_;
     void run(const StepMatrix& m, NewRows& out, uint32_t flags) {
         gamba_cuda_step_in in{};
@@ -72,7 +72,14 @@ private:
         out.col.assign(o.col_rel, o.col_rel + o.nnz_new);
         const uint32_t* v = static_cast<const uint32_t*>(o.coeff);
         out.val.assign(v, v + o.nnz_new);
-        out.seconds = o.seconds_total; out.kernel_seconds = o.seconds_device;
+        out.seconds = o.seconds_total; out.kernel_seconds = o.seconds_device; out.fma_top = c.fma_top;
+        t_elim_ += o.seconds_eliminate; t_ech_ += o.seconds_echelon;
+        char note[160];
+        static const char* const mode[] = {"sparse", "sparse-blocked", "tc-solve"};
+        std::snprintf(note, sizeof note, "[%s T=%u | stage %.1f elim %.1f (operands %.1f) echelon %.1f ms | mc %u]", mode[c.solve_mode % 3], c.tile_cols,
+                      (o.seconds_device - o.seconds_eliminate - o.seconds_echelon) * 1e3, o.seconds_eliminate * 1e3, c.seconds_operands_last * 1e3,
+                      o.seconds_echelon * 1e3, c.mc_ech_combinations);
+        out.note = note;
         t_copy_ += now_s() - t1;
     }
 };

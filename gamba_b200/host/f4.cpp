@@ -477,6 +477,8 @@ void F4::convert() {
 void F4::dump_step(const char* tag) {
     if (prm_.dump_dir.empty() || (long)M_.nnz() < prm_.dump_min_nnz) return;
     const bool is_final = std::string(tag) == "final";
+    // --dump-every N: an unbiased sample of a long run (bench.py: every 6th of kat15-15's 60 steps)
+    if (prm_.dump_every > 1 && !is_final && (stats.steps % (uint64_t)prm_.dump_every) != 0) return;
     if (prm_.dump_top > 0 && !is_final) {
         // --dump-top N: only the N steps with the most non-zeros stay on disk (the big systems' runs have 60+ steps of
         // hundreds of MB each); a step smaller than all N kept ones is not written at all
@@ -585,9 +587,9 @@ void F4::run() {
         if (!trivial_) update_all(prev);
         if (rounds) {
             double dens = 100.0 * (double)M_.nnz() / ((double)M_.n_rows() * (double)M_.n_cols);
-            std::printf("%4llu %4d %7ld/%-6zu %10u x %-9u %8.2f %9u %10.3f %10.3f\n",
+            std::printf("%4llu %4d %7ld/%-6zu %10u x %-9u %8.2f %9u %10.3f %10.3f   %s\n",
                         (unsigned long long)stats.steps, deg, nsel, queue, M_.n_rows(), M_.n_cols, dens,
-                        R_.n_new, tl, now_s() - ts);
+                        R_.n_new, tl, now_s() - ts, R_.note.c_str());
             std::fflush(stdout);
         }
     }

@@ -31,6 +31,7 @@ struct Params {
     std::string dump_dir;       // write every step matrix (+ result) here
     long dump_min_nnz = 0;
     long dump_top = 0;          // keep only the N steps with the most non-zeros (0 = all)
+    long dump_every = 0;        // dump only every N-th step (0/1 = all)
     long stop_after = 0;        // debugging: leave the F4 loop after this many steps (0 = run to the end)
 };
 

@@ -30,6 +30,7 @@ static void usage() {
         "  --dump-steps DIR                Write every step matrix and its result to DIR\n"
         "  --dump-min-nnz N                ... only steps with at least N non-zeros\n"
         "  --dump-top N                    ... only the N steps with the most non-zeros\n"
+        "  --dump-every N                  ... only every N-th step\n"
         "  --stop-after N                  (debugging) leave the F4 loop after N steps");
 }
 
@@ -58,6 +59,7 @@ int main(int argc, char** argv) {
             else if (key == "--dump-steps") prm.dump_dir = need(i, "--dump-steps");
             else if (key == "--dump-min-nnz") prm.dump_min_nnz = std::stol(need(i, "--dump-min-nnz"));
             else if (key == "--dump-top") prm.dump_top = std::stol(need(i, "--dump-top"));
+            else if (key == "--dump-every") prm.dump_every = std::stol(need(i, "--dump-every"));
             else if (key == "--stop-after") prm.stop_after = std::stol(need(i, "--stop-after"));
             else if (key == "-h" || key == "--help") { usage(); return 0; }
             else { std::fprintf(stderr, "The following argument was not expected: %s\n", a.c_str()); return 109; }

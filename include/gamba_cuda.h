@@ -46,7 +46,8 @@
 extern "C" {
 #endif
 
-#define GAMBA_CUDA_ABI_VERSION 4   /* 4: gamba_cuda_counters grew (dense_macs, seconds_inverse_last, solve_mode, panel_t) */
+#define GAMBA_CUDA_ABI_VERSION 4   /* 4: gamba_cuda_counters grew (dense_macs, seconds_inverse_last, solve_mode, panel_t, seconds_operands_last),
+                                      GAMBA_CUDA_STEP_DEVICE_INDICES, gamba_cuda_measure_int8_peak */
 
 #define GAMBA_CUDA_REPR_STANDARD   0u
 #define GAMBA_CUDA_REPR_MONTGOMERY 1u
@@ -56,6 +57,11 @@ extern "C" {
                                           to reduce have distinct non-pivot leads, so the engine checks
                                           n_new == n_bot; same output form (ascending pivot = the bottom
                                           rows' order reversed, matrix.hpp:733-739)                    */
+
+#define GAMBA_CUDA_STEP_DEVICE_INDICES 2u /* row_ptr, col_idx, coeff_id (and row_src, col_map) point to memory of the engine's
+                                          device and are used where they are until the next step is staged (a caller that
+                                          builds or keeps its step matrices on the GPU; bench.py's resident-input leg).
+                                          coeff_ptr / coeff_len stay host arrays (see "coeff_cache"). Not with a broadcast callback. */
 
 typedef struct gamba_cuda_engine gamba_cuda_engine;
 
@@ -174,8 +180,15 @@ typedef struct gamba_cuda_counters {
     double seconds_inverse_last;       /* CUDA-event time of the inverse diagonal tiles (inside seconds_sparse_last), last step   */
     uint32_t panel_t;                  /* pivot tile of the blocked solve (0 = not used)                                          */
     uint32_t reserved0;
+    double seconds_operands_last;      /* CUDA-event time of building the limb-plane operands of the products (inside
+                                          seconds_schur_last), last step                                                          */
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
+
+/* Microbenchmark: the int8 tensor-core rate of `device` with operands resident in shared memory (tcgen05.mma kind::i8,
+   128 x n x 32 per instruction, n = 64, 128 or 256, one CTA per SM), in 10^12 multiply-adds per second. bench.py uses it as
+   the measured denominator of its tensor roofline. */
+int gamba_cuda_measure_int8_peak(uint32_t device, uint32_t n, double* tmacs_per_s);
 
 /* Options: "tile_cols", "ctas_per_sm" (0 = automatic),
    "coeff_cache" (default 0; 1: coefficient arrays stay on the device across steps, keyed by host pointer - the

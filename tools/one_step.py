@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from gamba_b200 import LinalgEngine, load_step
 system, min_nnz, idx = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-files = bench.generate_workload(system, min_nnz, 0, 1)
+files = bench.generate_workload(system, 2000, min_nnz, 0, 1)
 s = load_step(files[idx])
 eng = LinalgEngine(s.p)
 for kv in sys.argv[4:]:
