@@ -182,7 +182,11 @@ struct gamba_cuda_engine {
         return mpad * (k * k * 0.5 + k * t) * nl * nl / rate + k * t * t / 3.0 * nl * nl / (rate / 3) +
                (nl * k * k * 0.5 + 3.0 * nl * k * t) / 3e12 + (3.0 * k / t + 12) * 4e-6;
     }
-    bool use_schur = false, use_block = false;   // decided per staged step (plan_step)
+    // sparse-blocked kernel: every block of R rows streams all of A: rows x nnz(A) row-entries at ~7e11 / s (kat15-15, K = 500 k)
+    static double model_block(double nloc, double k, double a, bool small) { return nloc * k * a / (small ? 7e11 : 4e11); }
+    double calib[3] = {1, 1, 1};     // measured / modelled time of the last steps in each mode (sparse, sparse-blocked, tc-solve)
+    int64_t opt_panel_max_gb = 32;   // budget for the operands of the tc-solve alone (beyond ~170 k pivot rows the sparse kernels win anyway)
+    bool use_schur = false, use_block = false;   // decided per staged step (choose_layout)
     int64_t opt_schur_max_gb = 96;   // budget for the limb-plane operands of the products
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
     int64_t opt_schur_kchunk = 0;    // k-steps between accumulator folds (0 = the exactness bound; tests lower it)
@@ -284,34 +288,47 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         const uint64_t mt_ = (nloc + sc_bm - 1) / sc_bm, nt_ = (L.n_nonpiv + sc_bn - 1) / sc_bn;
         use_schur = opt_schur && nloc && L.n_nonpiv && n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
                     (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kp <= (double)opt_schur_max_gb * 1e9 && mt_ * nt_ < (1ull << 31);
-        // R rows per CTA pay when most pivot rows hit most rows (katsura/eco: 60-70 % of the multipliers are non-zero):
-        // every entry of A is then streamed once per block of rows. With sparse multipliers (cyclic9: 10-40 %) the
-        // row-per-CTA kernel, which only touches the pivot rows a row needs, is faster (tools/blk_variants.sh).
-        use_block = use_schur && !opt_mc && (opt_block >= 2 || (opt_block == 1 && n_top >= 32768 && last_density >= 0.5));
-        if (use_block) tmax = BLK_TMAX;
-        // Blocked solve on the tensor cores (kernels_tri.cuh): pivot tiles of PANEL_T = 128 * 2^j columns. Operands: At_t
-        // [nl][T][t T] per tile (K^2/2 * nl bytes in total), the inverse diagonal tiles and their scratch (3.25 * nl * K * T)
-        use_panel = false;
+        // Three ways of finding the multipliers M = -C A^-1 (the A half of the elimination), chosen per step from modelled times:
+        //   sparse          row-per-CTA kernel (kernels_elim.cuh): work = the pivot rows a row actually hits;
+        //   sparse-blocked  R rows per CTA (kernels_elim_block.cuh): every entry of A is streamed once per block of rows - pays when
+        //                   most pivot rows hit most rows (katsura / eco: 60-70 % of the multipliers are non-zero);
+        //   tc-solve        blocked solve on the tensor cores (kernels_tri.cuh): n_bot K^2 / 2 dense multiply-adds whatever the
+        //                   matrix holds; operands At_t [nl][T][t T] per tile (K^2/2 * nl bytes) + 3.25 * nl * K * T for the
+        //                   inverse diagonal tiles - wins up to K ~ 170 k on katsura-like steps, by 1.5-3x on cyclic9.
+        // The models use the previous step's multiplier density and entries per row of A (F4 steps change slowly); each is scaled
+        // by a calibration factor = measured / modelled time of the steps that ran in that mode (run_reduce), so a model that is off
+        // on a system corrects itself after one step in that mode; every 12th step the runner-up runs to keep its factor fresh.
+        use_block = false; use_panel = false;
         if (opt_panel_t > 0) PANEL_T = (uint32_t)opt_panel_t;
         else PANEL_T = n_top >= 12288 ? 2048u : n_top >= 3072 ? 1024u : 512u;
-        // Blocked solve or sparse kernels? The products cost n_bot K^2 / 2 dense multiply-adds whatever the matrix holds, the
-        // sparse kernel only touches the pivot rows a row hits: predicted from the previous step (F4 steps change slowly)
-        // with measured rates: row-per-CTA kernel 2.1e11 entries/s (1.3e11 for p >= 2^16), products 1.2e15 int8 multiply-adds/s
-        bool panel_pays = opt_panel >= 2;
-        if (opt_panel == 1 && have_history) {
-            const double est_sparse = hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
-            const double est_panel = model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T);
-            panel_pays = est_panel < est_sparse;
-            if (panel_pays && ++since_explore >= 16) { panel_pays = false; since_explore = 0; }   // refresh hitw
-        }
-        if (use_schur && panel_pays && !opt_mc && opt_block < 2 && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
+        bool panel_fits = false;
+        if (use_schur && !opt_mc && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
             const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T, kt_ = ntp_ * PANEL_T;
             const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2) + 3.25 * nl * (double)kt_ * PANEL_T;
-            const uint64_t kpp = kt_;
-            if (at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kpp + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9) {
-                use_panel = true; use_block = false; tmax = PANEL_T;
+            panel_fits = at_b <= (double)opt_panel_max_gb * 1e9 &&
+                         at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kt_ + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9;
+        }
+        const bool block_ok = use_schur && !opt_mc && opt_block >= 1;
+        int mode = 0;
+        if (opt_panel >= 2 && panel_fits) mode = 2;
+        else if (opt_block >= 2 && block_ok) mode = 1;
+        else if (have_history && use_schur && !opt_mc) {
+            double est[3];
+            est[0] = calib[0] * hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
+            est[1] = block_ok && n_top >= 8192 ? calib[1] * model_block(nloc, n_top, last_a, f.small != 0) : 1e30;
+            est[2] = panel_fits && opt_panel >= 1 ? calib[2] * model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T) : 1e30;
+            mode = est[1] < est[0] ? 1 : 0;
+            if (est[2] < est[mode]) mode = 2;
+            if (++since_explore >= 12) {          // the runner-up, if it is within 2x
+                since_explore = 0;
+                int second = -1;
+                for (int m = 0; m < 3; ++m) if (m != mode && est[m] < 2.0 * est[mode] && (second < 0 || est[m] < est[second])) second = m;
+                if (second >= 0) mode = second;
             }
         }
+        use_block = mode == 1; use_panel = mode == 2;
+        if (use_block) tmax = BLK_TMAX;
+        if (use_panel) tmax = PANEL_T;
     }
     if (opt_tile_cols > 0 && !use_panel) tmax = std::min<uint32_t>(tmax, std::max<uint32_t>(gran, (uint32_t)opt_tile_cols / gran * gran));
     auto up = [&](uint32_t x) { return std::max(gran, (x + gran - 1) / gran * gran); };
@@ -949,6 +966,15 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
         last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top); last_a = cur_a; have_history = true;
         if (use_schur && !use_block && !use_panel && last_a > 0 && ctr.pivots_applied > 1000)      // the sparse kernel ran: its real work
             hitw = std::min(16.0, std::max(0.25, (double)ctr.fma_applied / ((double)ctr.pivots_applied * last_a * 0.5)));
+        if (use_schur && L.n_top >= 4096 && n_local >= 64 && t_sparse_dev > 2e-4) {       // calibrate the model of the mode that ran
+            const uint32_t nl_ = f.small ? 2u : 4u;
+            const double mpad = (double)((n_local + 127u) / 128u * 128u);
+            const int m = use_panel ? 2 : use_block ? 1 : 0;
+            const double model = m == 2 ? model_panel(mpad, L.n_top, nl_, PANEL_T)
+                               : m == 1 ? model_block(n_local, L.n_top, cur_a, f.small != 0)
+                                        : hitw * model_sparse(n_local, last_density, L.n_top, cur_a, f.small != 0);
+            if (model > 0) calib[m] = std::min(5.0, std::max(0.2, 0.5 * calib[m] + 0.5 * t_sparse_dev / model));
+        }
     }
     ctr.steps += 1;
 
@@ -1176,6 +1202,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "panel") e->opt_panel = value;
         else if (k == "panel_t") { if (value && (value < 128 || value > 8192 || (value & (value - 1)))) throw std::runtime_error("panel_t must be 128 * 2^j, at most 8192"); e->opt_panel_t = value; }
         else if (k == "panel_max_top") e->opt_panel_max_top = value;
+        else if (k == "panel_max_gb") e->opt_panel_max_gb = value;
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;
         else if (k == "schur_kchunk") e->opt_schur_kchunk = value;

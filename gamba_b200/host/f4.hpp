@@ -28,6 +28,7 @@ struct Params {
     uint64_t seed = 967557673ull;
     int verbose = 2;
     int threads = 0;            // -t: host threads (0 = all hardware threads, at most 16)
+    int gpus = 1;               // --gpus: GPUs of this box the linear algebra is sharded over (C|D rows r % gpus)
     std::string dump_dir;       // write every step matrix (+ result) here
     long dump_min_nnz = 0;
     long dump_top = 0;          // keep only the N steps with the most non-zeros (0 = all)

@@ -26,6 +26,7 @@ static void usage() {
         "  --all-pairs                     Select all pairs in the queue in each round\n"
         "  --no-reduce                     Do not compute a reduced Groebner basis\n"
         "  -t,--threads UINT               Host threads for the symbolic phases (0 = all, at most 16)\n"
+        "  --gpus UINT                     GPUs of this box to shard the linear algebra over (default 1)\n"
         "  -v,--verbose UINT               Verbosity level (default 2)\n"
         "  --dump-steps DIR                Write every step matrix and its result to DIR\n"
         "  --dump-min-nnz N                ... only steps with at least N non-zeros\n"
@@ -55,6 +56,7 @@ int main(int argc, char** argv) {
             else if (key == "--all-pairs") prm.all_pairs = true;
             else if (key == "--no-reduce") prm.no_reduce = true;
             else if (key == "-t" || key == "--threads") prm.threads = std::stoi(need(i, "--threads"));
+            else if (key == "--gpus") prm.gpus = std::stoi(need(i, "--gpus"));
             else if (key == "-v" || key == "--verbose") prm.verbose = std::stoi(need(i, "--verbose"));
             else if (key == "--dump-steps") prm.dump_dir = need(i, "--dump-steps");
             else if (key == "--dump-min-nnz") prm.dump_min_nnz = std::stol(need(i, "--dump-min-nnz"));
