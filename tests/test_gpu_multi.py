@@ -24,3 +24,19 @@ def test_two_ranks_match_oracle(step_dirs, name, opts):
                        capture_output=True, text=True, timeout=600, env=dict(os.environ, CHECK_MULTI_OPTS=opts))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "differing=0" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["cyclic7-31", "kat10-15", "eco10-31"])
+def test_product_driver_on_two_gpus_matches_golden(built, tmp_path, name):
+    """`gamba --gpus 2`: one process, one engine per GPU, rows of C|D sharded r % 2, the step replicated with ncclBroadcast and
+    D' gathered with ncclAllGather (the C++ wiring of the two ABI callbacks, gamba_b200/host/engine_cuda.cpp)."""
+    import torch
+    from conftest import GOLD_IN, golden_bytes
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = tmp_path / "out.txt"
+    r = subprocess.run([os.path.join(ROOT, "gamba_b200", "bin", "gamba"), "-i", os.path.join(GOLD_IN, name + ".txt"), "-o", str(out),
+                        "-v", "1", "--gpus", "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "engine = cuda-b200-multi" in r.stdout
+    assert out.read_bytes() == golden_bytes(name)
