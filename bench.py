@@ -2,10 +2,12 @@
 """Benchmark of the hot path: F4 linear-algebra throughput, nnz reduced per second (BASELINE.json's metric, quoted on
 cyclic9 and kat15).
 
-Workload (config.workload): EVERY F4 step matrix of cyclic9-15 (default options, 46 steps) and EVERY 6TH step matrix of
-kat15-15 (default options, 10 of its 60 steps: the whole run is 1.3e10 nnz and 13 s of kernels per pass, too much for the K + W
-passes the driver asks for; every 6th step is an unbiased sample of the run, from the 5 k-row steps of the first rounds to the
-500 k x 500 k ones of the last), produced on the box by the product driver (`gamba --dump-steps`, untimed workload generation).
+Workload (config.workload): EVERY F4 step matrix of cyclic9-15 (default options, 46 steps) and EVERY 3RD step matrix of
+kat15-15 run with `--max-spairs 0` (same basis; 15 steps of up to 17 k rows to reduce against 500 k pivot rows instead of 60
+steps of 2000 rows: the setting the GPU wants, SURVEY.md §8(d), and 43 s instead of 72 s end to end). The whole kat15-15 run is
+4.6e9 nnz and 15 s of kernels per pass - too much for the K + W passes the driver asks for - so every 3rd step stands for it: an
+unbiased sample from the small steps of the first degrees to the 517 k x 517 k ones of the last. Both are produced on the box by
+the product driver (`gamba --dump-steps`, untimed workload generation).
 One bench "step" = one pass of the engine over all those matrices in F4 order, one engine per system, so that every choice the
 engine makes from the previous step (kernel choice, predicted rank of the Monte-Carlo echelon) is made as in a real run.
 
@@ -45,7 +47,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "F4 lin-alg nnz reduced/s"
 WORK_DIR = os.path.join(tempfile.gettempdir(), "gamba_b200_bench")
-DEFAULT_SYSTEMS = "cyclic9-15:2000:1,kat15-15:2000:6"          # system:max_spairs:every-nth-step
+DEFAULT_SYSTEMS = "cyclic9-15:2000:1,kat15-15:0:3"          # system:max_spairs:every-nth-step
 GAMBA = os.path.join(ROOT, "gamba_b200", "bin", "gamba")
 README_SECONDS = {"cyclic9-15": 17.8, "cyclic9-31": 26.1, "kat15-15": 318.5, "kat15-31": 423.3, "eco15-31": 97.7,
                   "kat14-15": 59.4, "eco14-15": 16.6}   # closed reference binary, Ryzen 5 3600, 1 thread (README.md:18-23,42-47)
@@ -261,7 +263,7 @@ def run_reference(args, rank: int, world: int):
                                  "kernel/*) is closed source and single-threaded"},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -292,6 +294,11 @@ def e2e_seconds(groups):
                      "reference_binary_note": "closed GamBa binary, Ryzen 5 3600, 1 thread, default options (README.md:18-23,42-47)"}
         shutil.rmtree(d, ignore_errors=True)
     return out
+
+
+def log(msg: str):
+    if os.environ.get("GAMBA_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -347,6 +354,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def launches():
         return sum(e.counters()["kernel_launches"] for e in engines)
 
+    log(f"workload loaded: {n_mat} matrices, {total_nnz} nnz")
     # ---- parity check (untimed): an independent configuration on rank 0 must give the same rows ----------------------
     parity = {"status": "skipped"}
     if not args.no_parity:
@@ -371,6 +379,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                   f"sparse-kernel path (panel=0) on the matrices with <= {args.parity_max_nnz} nnz")}
         sync()
 
+    log(f"parity check: {parity}")
     # ---- value: index arrays resident in HBM -------------------------------------------------------------------------
     def run_pass(collect=None):
         for gi, (e, rs) in enumerate(zip(engines, residents)):
@@ -399,6 +408,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     n_launch = launches() - l0
     clocks = clk.summary()
 
+    log(f"value leg done: {t_res:.2f} s for {args.steps} passes")
     # ---- e2e: pinned host buffers in, host buffers out ---------------------------------------------------------------
     if bcast:
         for e in engines:
@@ -422,6 +432,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     sync()
     t_e2e = time.perf_counter() - t0
 
+    log(f"e2e leg done: {t_e2e:.2f} s for {e2e_steps} passes")
     # the engines (tens of GB of operands) and the resident steps go before anything else wants the GPU (e2e_seconds runs the product binary)
     for e in engines:
         e.close()
@@ -499,7 +510,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             out["e2e_seconds"] = e2e_seconds(groups)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(groups, args)
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

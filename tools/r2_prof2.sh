@@ -1,0 +1,11 @@
+#!/bin/bash
+# ncu --set full of the dominant kernel (limb_gemm_tc_kernel): three late launches of the earlier-tile product (RMW_LIMBS) and the
+# Schur product (RMW) of one reduction of a cyclic9-15 step matrix
+cd "$(dirname "$0")/.."
+IDX=${1:-5}
+CMD="python tools/one_step.py cyclic9-15 15000000 $IDX"
+$CMD > gpurun_out/r2_p2_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/r2_p2_plain.log; exit 1; }
+cat gpurun_out/r2_p2_plain.log
+# the third reduction is the steady state: skip the GEMM launches of the first two (2 x ~50)
+ncu --set full --clock-control none --import-source on -k regex:limb_gemm_tc_kernel -s 118 -c 8 -o gpurun_out/r2_p2_gemm $CMD > gpurun_out/r2_p2_ncu.log 2>&1
+ls -la gpurun_out/r2_p2_gemm.ncu-rep
