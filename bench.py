@@ -437,6 +437,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     for e in engines:
         e.close()
     residents.clear()
+    hosts.clear()                  # page-locked copies of the workload
     torch.cuda.empty_cache()
     keys = sorted(per)
     vals = np.array([per[k] for k in keys], dtype=np.float64)

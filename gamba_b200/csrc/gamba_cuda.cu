@@ -24,6 +24,7 @@
 #include "kernels_elim.cuh"
 #include "kernels_elim_block.cuh"
 #include "kernels_prep.cuh"
+#include "kernels_rowgen.cuh"
 #include "kernels_schur.cuh"
 #include "kernels_schur_tc.cuh"
 #include "kernels_tri.cuh"
@@ -235,6 +236,24 @@ struct gamba_cuda_engine {
     gamba_cuda_counters ctr{};
     double t_elim_dev = 0, t_ech_dev = 0;
 
+    // row generation of symbolic preprocessing (kernels_rowgen.cuh)
+    struct RowGenState {
+        uint32_t stride = 0, sd = 0;
+        gcu::DevBuf pex, phv;              // term store of the basis polynomials (append-only across steps)
+        uint64_t terms = 0;
+        gcu::DevBuf slots, hv, ex;         // the step's monomial table
+        uint32_t n_slots = 0, cap = 0, count = 0;
+        gcu::DevBuf rows;                  // handles of the step's rows, in the order the rows were added
+        uint64_t n_rows_entries = 0;
+        gcu::DevBuf cnt, b_first, b_off, b_q, b_hq, b_lead;
+        gcu::HostBuf stage;
+    } rg;
+    void rg_begin(uint32_t stride);
+    void rg_add_poly(uint32_t n, const uint16_t* ex, const uint32_t* hv, uint64_t* first);
+    void rg_add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex, const uint32_t* q_hash,
+                     uint32_t* lead_out, uint32_t* n_monomials);
+    void rg_fetch(uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hv_out);
+
     double dbg_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     ~gamba_cuda_engine() {
         if (std::getenv("GAMBA_DEBUG_TIMERS"))
@@ -363,6 +382,9 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     // GAMBA_CUDA_STEP_DEVICE_INDICES: the index arrays of the step already live on this device and are used where they are
     const bool dev_idx = have && (in->flags & GAMBA_CUDA_STEP_DEVICE_INDICES) != 0;
     if (dev_idx && use_bcast) throw std::runtime_error("device-resident index arrays cannot be combined with the broadcast callback");
+    // GAMBA_CUDA_STEP_DEVICE_COLIDX: col_idx alone is device memory (the handle array of gamba_cuda_rowgen_add_rows)
+    const bool dev_col = have && !dev_idx && (in->flags & GAMBA_CUDA_STEP_DEVICE_COLIDX) != 0;
+    const bool alias_col = dev_idx || (dev_col && !use_bcast);
     if (have) {
         if (in->n_cols < in->n_top) throw std::runtime_error("n_cols < n_top");
         if (!dev_idx && in->row_ptr[in->n_top + in->n_bot] != in->nnz) throw std::runtime_error("row_ptr[n_rows] != nnz");
@@ -386,7 +408,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     }
     const uint32_t n_rows = hd.n_top + hd.n_bot;
     choose_layout(hd.n_top, hd.n_bot, hd.n_cols);
-    flags = hd.flags & ~GAMBA_CUDA_STEP_DEVICE_INDICES; nnz = hd.nnz;
+    flags = hd.flags & ~(GAMBA_CUDA_STEP_DEVICE_INDICES | GAMBA_CUDA_STEP_DEVICE_COLIDX); nnz = hd.nnz;
     if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
     if (nnz + 1ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
     if ((uint64_t)8 * L.n_tiles * 4 > 160 * 1024) throw std::runtime_error("too many column tiles for the staging kernels");
@@ -443,7 +465,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     };
     if (!dev_idx) {
         d_row_ptr.ensure((n_rows + 1) * sizeof(uint64_t));
-        d_col.ensure(std::max<uint64_t>(hd.n_src, 1) * sizeof(uint32_t));
+        if (!alias_col) d_col.ensure(std::max<uint64_t>(hd.n_src, 1) * sizeof(uint32_t));
         if (hd.has_row_src) d_row_src.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint64_t));
         if (hd.col_map_len) d_col_map.ensure((size_t)hd.col_map_len * sizeof(uint32_t));
         d_coeff_id.ensure(std::max<uint32_t>(n_rows, 1) * sizeof(uint32_t));
@@ -455,7 +477,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
     if (have) {
         if (!dev_idx) {
             GCU_CHECK(cudaMemcpyAsync(d_row_ptr.p, in->row_ptr, (n_rows + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-            GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, hd.n_src * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            if (!alias_col) GCU_CHECK(cudaMemcpyAsync(d_col.p, in->col_idx, hd.n_src * sizeof(uint32_t), dev_col ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
             if (hd.has_row_src) GCU_CHECK(cudaMemcpyAsync(d_row_src.p, in->row_src, n_rows * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
             if (hd.col_map_len) GCU_CHECK(cudaMemcpyAsync(d_col_map.p, in->col_map, (size_t)hd.col_map_len * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
             GCU_CHECK(cudaMemcpyAsync(d_coeff_id.p, in->coeff_id, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
@@ -465,7 +487,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         GCU_CHECK(cudaMemcpyAsync(d_coeff_off.p, off, (na + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
         if (tot) GCU_CHECK(cudaMemcpyAsync(d_pool.as<uint32_t>() + pool_base, pool, tot * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         h2d_bytes = (na + 1) * 8ull + tot * 4ull;
-        if (!dev_idx) h2d_bytes += (n_rows + 1) * 8ull + hd.n_src * 4ull + n_rows * 4ull + (hd.has_row_src ? n_rows * 8ull : 0) + hd.col_map_len * 4ull;
+        if (!dev_idx) h2d_bytes += (n_rows + 1) * 8ull + (dev_col ? 0ull : hd.n_src * 4ull) + n_rows * 4ull + (hd.has_row_src ? n_rows * 8ull : 0) + hd.col_map_len * 4ull;
     }
     if (use_bcast) {   // A|B and C|D replicated over NVLink instead of one H2D copy per rank
         const std::pair<void*, size_t> bufs[] = {{d_row_ptr.p, (n_rows + 1) * sizeof(uint64_t)}, {d_col.p, hd.n_src * sizeof(uint32_t)},
@@ -492,7 +514,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
 
     PrepArgs pa{};
     pa.L = L; pa.f = f;
-    pa.row_ptr = dev_idx ? in->row_ptr : d_row_ptr.as<uint64_t>(); pa.col = dev_idx ? in->col_idx : d_col.as<uint32_t>();
+    pa.row_ptr = dev_idx ? in->row_ptr : d_row_ptr.as<uint64_t>(); pa.col = alias_col ? in->col_idx : d_col.as<uint32_t>();
     pa.coeff_id = dev_idx ? in->coeff_id : d_coeff_id.as<uint32_t>();
     s_row_ptr = pa.row_ptr;
     pa.coeff_off = d_coeff_off.as<uint64_t>(); pa.pool = d_pool.as<uint32_t>();
@@ -1047,6 +1069,139 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
     out->seconds_device = t_prep_dev + acc_elim + acc_ech;
 }
 
+// ---- row generation of symbolic preprocessing on the device (kernels_rowgen.cuh) -------------------------------------
+
+// grow a device buffer keeping its first `used` bytes
+static void grow_keep(gcu::DevBuf& b, size_t used, size_t want, cudaStream_t st) {
+    if (want <= b.cap) return;
+    gcu::DevBuf bigger;
+    bigger.ensure(std::max(want, b.cap * 2));
+    if (used) GCU_CHECK(cudaMemcpyAsync(bigger.p, b.p, used, cudaMemcpyDeviceToDevice, st));
+    std::swap(bigger.p, b.p); std::swap(bigger.cap, b.cap);      // the old block goes back to the pool, ordered on the stream
+}
+
+void gamba_cuda_engine::rg_begin(uint32_t stride) {
+    if (stride == 0 || ((stride + 1u) & ~1u) > (uint32_t)RG_MAX_SD) throw std::runtime_error("rowgen: unsupported exponent-vector stride");
+    if (stride != rg.stride) { rg.stride = stride; rg.sd = (stride + 1u) & ~1u; rg.terms = 0; }
+    rg.count = 0; rg.n_rows_entries = 0;
+    rg.cnt.ensure(16);
+    GCU_CHECK(cudaMemsetAsync(rg.cnt.p, 0, 16, stream));
+    if (rg.n_slots) GCU_CHECK(cudaMemsetAsync(rg.slots.p, 0, (size_t)rg.n_slots * sizeof(uint32_t), stream));
+}
+
+void gamba_cuda_engine::rg_add_poly(uint32_t n, const uint16_t* ex, const uint32_t* hv, uint64_t* first) {
+    if (!rg.sd) throw std::runtime_error("rowgen: begin has not been called");
+    const uint32_t sd = rg.sd, st = rg.stride;
+    grow_keep(rg.pex, rg.terms * sd * sizeof(uint16_t), (rg.terms + n) * sd * sizeof(uint16_t), stream);
+    grow_keep(rg.phv, rg.terms * sizeof(uint32_t), (rg.terms + n) * sizeof(uint32_t), stream);
+    const size_t bytes_ex = (size_t)n * sd * sizeof(uint16_t), bytes_hv = (size_t)n * sizeof(uint32_t);
+    GCU_CHECK(cudaStreamSynchronize(stream));            // the staging buffer may still be the source of the previous upload
+    rg.stage.ensure(bytes_ex + bytes_hv);
+    uint16_t* se = rg.stage.as<uint16_t>();
+    for (uint32_t k = 0; k < n; ++k) {
+        std::memcpy(se + (size_t)k * sd, ex + (size_t)k * st, st * sizeof(uint16_t));
+        if (sd != st) se[(size_t)k * sd + st] = 0;
+    }
+    std::memcpy(rg.stage.as<char>() + bytes_ex, hv, bytes_hv);
+    GCU_CHECK(cudaMemcpyAsync(rg.pex.as<uint16_t>() + rg.terms * sd, se, bytes_ex, cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaMemcpyAsync(rg.phv.as<uint32_t>() + rg.terms, rg.stage.as<char>() + bytes_ex, bytes_hv, cudaMemcpyHostToDevice, stream));
+    *first = rg.terms;
+    rg.terms += n;
+}
+
+void gamba_cuda_engine::rg_add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex,
+                                    const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials) {
+    if (!rg.sd) throw std::runtime_error("rowgen: begin has not been called");
+    const uint32_t sd = rg.sd, st = rg.stride;
+    // Sub-batches: the table must have room for every term of a sub-batch being new (it cannot grow inside the kernel), while
+    // almost all terms are hits - so a sub-batch is capped near the table's size (at least 4 M terms).
+    for (uint32_t r0 = 0; r0 < n_rows;) {
+        const uint64_t cap_terms = std::max<uint64_t>((uint64_t)1 << 22, rg.count);
+        uint32_t r1 = r0; uint64_t total = 0;
+        while (r1 < n_rows && (r1 == r0 || total + n_terms[r1] <= cap_terms)) total += n_terms[r1++];
+        const uint32_t nb = r1 - r0;
+        if ((uint64_t)rg.count + total >= 0xfffffff0ull) throw std::runtime_error("rowgen: too many monomials for 32-bit handles");
+        const uint32_t need = rg.count + (uint32_t)total;
+        if (need > rg.cap) {
+            const uint32_t cap = std::max<uint32_t>(need, rg.cap + rg.cap / 2 + (1u << 16));
+            grow_keep(rg.hv, (size_t)rg.count * sizeof(uint32_t), (size_t)cap * sizeof(uint32_t), stream);
+            grow_keep(rg.ex, (size_t)rg.count * sd * sizeof(uint16_t), (size_t)cap * sd * sizeof(uint16_t), stream);
+            rg.cap = cap;
+        }
+        if ((uint64_t)need * 2 > rg.n_slots) {
+            uint64_t ns = std::max<uint64_t>(rg.n_slots, (uint64_t)1 << 20);
+            while ((uint64_t)need * 2 > ns) ns *= 2;
+            if (ns > 0x80000000ull) throw std::runtime_error("rowgen: monomial table too large");
+            rg.slots.ensure(ns * sizeof(uint32_t));
+            rg.n_slots = (uint32_t)ns;
+            GCU_CHECK(cudaMemsetAsync(rg.slots.p, 0, ns * sizeof(uint32_t), stream));
+            if (rg.count) {
+                rowgen_rehash_kernel<<<(rg.count + 255) / 256, 256, 0, stream>>>(rg.slots.as<uint32_t>(), rg.n_slots - 1, rg.hv.as<uint32_t>(), rg.count);
+                GCU_CHECK(cudaGetLastError());
+                ctr.kernel_launches += 1;
+            }
+        }
+        grow_keep(rg.rows, rg.n_rows_entries * sizeof(uint32_t), (rg.n_rows_entries + total) * sizeof(uint32_t), stream);
+        // batch arrays through one page-locked staging buffer
+        const size_t o_first = 0, o_off = o_first + (size_t)nb * 8, o_q = o_off + (size_t)(nb + 1) * 8, o_hq = o_q + (size_t)nb * sd * 2,
+                     o_end = (o_hq + (size_t)nb * 4 + 15) & ~(size_t)15;
+        GCU_CHECK(cudaStreamSynchronize(stream));
+        rg.stage.ensure(o_end);
+        char* sb = rg.stage.as<char>();
+        std::memcpy(sb + o_first, first_term + r0, (size_t)nb * 8);
+        uint64_t* off = reinterpret_cast<uint64_t*>(sb + o_off);
+        off[0] = rg.n_rows_entries;
+        for (uint32_t i = 0; i < nb; ++i) off[i + 1] = off[i] + n_terms[r0 + i];
+        uint16_t* sq = reinterpret_cast<uint16_t*>(sb + o_q);
+        for (uint32_t i = 0; i < nb; ++i) {
+            std::memcpy(sq + (size_t)i * sd, q_ex + (size_t)(r0 + i) * st, st * sizeof(uint16_t));
+            if (sd != st) sq[(size_t)i * sd + st] = 0;
+        }
+        std::memcpy(sb + o_hq, q_hash + r0, (size_t)nb * 4);
+        rg.b_first.ensure(o_end);
+        GCU_CHECK(cudaMemcpyAsync(rg.b_first.p, sb, o_end, cudaMemcpyHostToDevice, stream));
+        rg.b_lead.ensure((size_t)nb * 4);
+        RowGenArgs a{};
+        a.sd = sd; a.pex = rg.pex.as<uint16_t>(); a.phv = rg.phv.as<uint32_t>(); a.n_rows = nb;
+        a.first_term = reinterpret_cast<const uint64_t*>(rg.b_first.as<char>() + o_first);
+        a.row_off = reinterpret_cast<const uint64_t*>(rg.b_first.as<char>() + o_off);
+        a.q = reinterpret_cast<const uint16_t*>(rg.b_first.as<char>() + o_q);
+        a.hq = reinterpret_cast<const uint32_t*>(rg.b_first.as<char>() + o_hq);
+        a.slots = rg.slots.as<uint32_t>(); a.mask = rg.n_slots - 1; a.hv = rg.hv.as<uint32_t>(); a.ex = rg.ex.as<uint16_t>();
+        a.count = rg.cnt.as<uint32_t>(); a.cap = rg.cap; a.overflow = rg.cnt.as<uint32_t>() + 1;
+        a.row_mon = rg.rows.as<uint32_t>(); a.lead = rg.b_lead.as<uint32_t>();
+        const uint32_t grid = std::min<uint32_t>(nb, (uint32_t)prop.multiProcessorCount * 8);
+        if (sd <= 16) rowgen_kernel<8><<<grid, RG_THREADS, 0, stream>>>(a);
+        else if (sd <= 32) rowgen_kernel<16><<<grid, RG_THREADS, 0, stream>>>(a);
+        else rowgen_kernel<64><<<grid, RG_THREADS, 0, stream>>>(a);
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 1;
+        uint32_t res[2] = {0, 0};
+        GCU_CHECK(cudaMemcpyAsync(res, rg.cnt.p, 8, cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaMemcpyAsync(lead_out + r0, rg.b_lead.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaStreamSynchronize(stream));
+        if (res[1]) throw std::runtime_error("rowgen: monomial table overflow");
+        rg.count = res[0];
+        rg.n_rows_entries += total;
+        r0 = r1;
+    }
+    *n_monomials = rg.count;
+}
+
+void gamba_cuda_engine::rg_fetch(uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hv_out) {
+    if ((uint64_t)first + count > rg.count) throw std::runtime_error("rowgen: monomial range out of bounds");
+    if (!count) return;
+    const uint32_t sd = rg.sd, st = rg.stride;
+    const size_t bytes_ex = (size_t)count * sd * sizeof(uint16_t);
+    GCU_CHECK(cudaStreamSynchronize(stream));
+    rg.stage.ensure(bytes_ex);
+    GCU_CHECK(cudaMemcpyAsync(rg.stage.p, rg.ex.as<uint16_t>() + (size_t)first * sd, bytes_ex, cudaMemcpyDeviceToHost, stream));
+    GCU_CHECK(cudaMemcpyAsync(hv_out, rg.hv.as<uint32_t>() + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GCU_CHECK(cudaStreamSynchronize(stream));
+    const uint16_t* se = rg.stage.as<uint16_t>();
+    for (uint32_t k = 0; k < count; ++k) std::memcpy(ex_out + (size_t)k * st, se + (size_t)k * sd, st * sizeof(uint16_t));
+}
+
 // ------------------------------------------------------------------ C ABI -----
 
 template <class F>
@@ -1090,13 +1245,18 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
             GCU_CHECK(cudaMemPoolCreate(&e->pool, &props));
             uint64_t keep = ~0ull;                       // freed blocks stay in the pool for the next step
             GCU_CHECK(cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            // GAMBA_POOL_PREWARM_GB=n (default off): one allocation of n GB, released straight back to the pool, so that the
-            // first steps of a run grow their buffers without a trip to the driver each time
-            if (const char* pw = std::getenv("GAMBA_POOL_PREWARM_GB")) {
-                const double want_gb = std::atof(pw);
-                if (want_gb > 0) {
+            // Put some memory into the engine's pool up front (one allocation, released straight back to the pool): the first steps
+            // of a run then grow their buffers without a trip to the driver each time (1 s of a 3 s cyclic9-15 run otherwise).
+            // GAMBA_POOL_PREWARM_GB (default 6, capped at a quarter of the free memory; 0 = off). The pool dies with the engine.
+            {
+                size_t free_b = 0, total_b = 0;
+                GCU_CHECK(cudaMemGetInfo(&free_b, &total_b));
+                const char* pw = std::getenv("GAMBA_POOL_PREWARM_GB");
+                const double want_gb = pw ? std::atof(pw) : 6.0;
+                const size_t want = (size_t)std::min<double>(want_gb * 1e9, (double)free_b / 4);
+                if (want > ((size_t)64 << 20)) {
                     void* warm = nullptr;
-                    if (cudaMallocFromPoolAsync(&warm, (size_t)(want_gb * 1e9), e->pool, e->stream) == cudaSuccess) GCU_CHECK(cudaFreeAsync(warm, e->stream));
+                    if (cudaMallocFromPoolAsync(&warm, want, e->pool, e->stream) == cudaSuccess) GCU_CHECK(cudaFreeAsync(warm, e->stream));
                     else cudaGetLastError();
                     GCU_CHECK(cudaStreamSynchronize(e->stream));
                 }
@@ -1155,6 +1315,33 @@ int gamba_cuda_set_allgather(gamba_cuda_engine* e, gamba_cuda_allgather_fn fn, v
 
 int gamba_cuda_set_broadcast(gamba_cuda_engine* e, gamba_cuda_broadcast_fn fn, void* user) {
     return guarded([&] { e->bcast_fn = fn; e->bcast_user = user; });
+}
+
+#define GCU_ENTER(e) GCU_CHECK(cudaSetDevice((int)(e)->cfg.device)); gcu::g_alloc_stream = (e)->stream; gcu::g_alloc_pool = (e)->pool
+
+int gamba_cuda_rowgen_begin(gamba_cuda_engine* e, uint32_t stride) {
+    return guarded([&] { GCU_ENTER(e); e->rg_begin(stride); });
+}
+int gamba_cuda_rowgen_add_poly(gamba_cuda_engine* e, uint32_t n_terms, const uint16_t* ex, const uint32_t* hash, uint64_t* first_term) {
+    return guarded([&] { GCU_ENTER(e); e->rg_add_poly(n_terms, ex, hash, first_term); });
+}
+int gamba_cuda_rowgen_add_rows(gamba_cuda_engine* e, uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms,
+                               const uint16_t* q_ex, const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials) {
+    return guarded([&] { GCU_ENTER(e); e->rg_add_rows(n_rows, first_term, n_terms, q_ex, q_hash, lead_out, n_monomials); });
+}
+int gamba_cuda_rowgen_fetch_monomials(gamba_cuda_engine* e, uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hash_out) {
+    return guarded([&] { GCU_ENTER(e); e->rg_fetch(first, count, ex_out, hash_out); });
+}
+int gamba_cuda_rowgen_rows(gamba_cuda_engine* e, const uint32_t** dev_rows, uint64_t* n_entries) {
+    return guarded([&] { *dev_rows = e->rg.rows.as<uint32_t>(); *n_entries = e->rg.n_rows_entries; });
+}
+int gamba_cuda_rowgen_download_rows(gamba_cuda_engine* e, uint64_t first, uint64_t count, uint32_t* out) {
+    return guarded([&] {
+        GCU_ENTER(e);
+        if (first + count > e->rg.n_rows_entries) throw std::runtime_error("rowgen: row range out of bounds");
+        if (count) GCU_CHECK(cudaMemcpyAsync(out, e->rg.rows.as<uint32_t>() + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        GCU_CHECK(cudaStreamSynchronize(e->stream));
+    });
 }
 
 int gamba_cuda_measure_int8_peak(uint32_t device, uint32_t n, double* tmacs_per_s) {

@@ -76,6 +76,7 @@ struct StepMatrix {
     uint64_t src_len = 0;
     std::vector<uint64_t> row_src;
     std::vector<uint32_t> col_map;
+    bool src_on_device = false;         // src points to device memory (rows generated on the GPU, Engine::rowgen()): not readable here
     uint32_t col_at(uint32_t r, uint64_t j) const { return src ? col_map[src[row_src[r] + j]] : col[row_ptr[r] + j]; }
     uint64_t nnz() const { return row_ptr.empty() ? 0 : row_ptr.back(); }
     uint32_t n_rows() const { return n_top + n_bot; }
@@ -97,8 +98,25 @@ struct NewRows {
     std::string note;               // engine's one-line account of the step (round table, -v 2)
 };
 
+// Row generation of symbolic preprocessing on the engine's device (include/gamba_cuda.h: gamba_cuda_rowgen_*; role of
+// matrix_f4::create_multiplied_poly_matrix_row and the matrix' monomial table, source/matrix.hpp:387-444): the step's monomial
+// table and rows live on the GPU; the driver keeps a mirror of the monomials (exponents, hashes) for its reducer search.
+struct RowGenDevice {
+    virtual ~RowGenDevice() = default;
+    virtual void begin(uint32_t stride) = 0;
+    virtual uint64_t add_poly(uint32_t n_terms, const uint16_t* ex, const uint32_t* hv) = 0;
+    // rows poly[i] * x^q[i]; lead_out[i] = handle of the first term of row i; returns the size of the table afterwards
+    virtual uint32_t add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex,
+                              const uint32_t* q_hash, uint32_t* lead_out) = 0;
+    virtual void fetch(uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hv_out) = 0;
+    virtual const uint32_t* rows_device(uint64_t& n_entries) = 0;
+    virtual void download_rows(uint64_t first, uint64_t count, uint32_t* out) = 0;
+};
+
 struct Engine {
     virtual ~Engine() = default;
+    // non-null: the engine generates the step's rows on its device (the CUDA engine); null: the driver does (CPU oracle)
+    virtual RowGenDevice* rowgen() { return nullptr; }
     virtual const char* name() const = 0;
     // One F4 step (role of linalg_v3::initialize + reduce).
     virtual void reduce_step(const StepMatrix& m, NewRows& out) = 0;

@@ -51,8 +51,35 @@ static int nccl_gather_cb(void* user, const void* send, void* recv, size_t bytes
 }
 
 
-class CudaEngine final : public Engine {
+class CudaEngine final : public Engine, public RowGenDevice {
 public:
+    // ---- RowGenDevice: thin wrappers of gamba_cuda_rowgen_* on the engine of GPU 0 ----
+    RowGenDevice* rowgen() override { return std::getenv("GAMBA_HOST_ROWGEN") ? nullptr : this; }
+    void begin(uint32_t stride) override { if (gamba_cuda_rowgen_begin(e_, stride)) fail("gamba_cuda_rowgen_begin"); }
+    uint64_t add_poly(uint32_t n_terms, const uint16_t* ex, const uint32_t* hv) override {
+        uint64_t first = 0;
+        if (gamba_cuda_rowgen_add_poly(e_, n_terms, ex, hv, &first)) fail("gamba_cuda_rowgen_add_poly");
+        return first;
+    }
+    uint32_t add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex,
+                      const uint32_t* q_hash, uint32_t* lead_out) override {
+        uint32_t n = 0;
+        if (gamba_cuda_rowgen_add_rows(e_, n_rows, first_term, n_terms, q_ex, q_hash, lead_out, &n)) fail("gamba_cuda_rowgen_add_rows");
+        return n;
+    }
+    void fetch(uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hv_out) override {
+        if (gamba_cuda_rowgen_fetch_monomials(e_, first, count, ex_out, hv_out)) fail("gamba_cuda_rowgen_fetch_monomials");
+    }
+    const uint32_t* rows_device(uint64_t& n_entries) override {
+        const uint32_t* p = nullptr;
+        if (gamba_cuda_rowgen_rows(e_, &p, &n_entries)) fail("gamba_cuda_rowgen_rows");
+        return p;
+    }
+    void download_rows(uint64_t first, uint64_t count, uint32_t* out) override {
+        if (gamba_cuda_rowgen_download_rows(e_, first, count, out)) fail("gamba_cuda_rowgen_download_rows");
+    }
+    [[noreturn]] static void fail(const char* what) { throw std::runtime_error(std::string(what) + ": " + gamba_cuda_last_error()); }
+
     CudaEngine(const Params& prm, uint32_t p) : world_(std::max(1, prm.gpus)) {
         gamba_cuda_config cfg{};
         cfg.p = p; cfg.coeff_bytes = 4; cfg.repr = GAMBA_CUDA_REPR_STANDARD;
@@ -159,7 +186,7 @@ private:
             in.col_map = m.col_map.data(); in.col_map_len = (uint32_t)m.col_map.size();
         }
         ptrs_.assign(m.cf_ptr.begin(), m.cf_ptr.end());
-        in.coeff_ptr = ptrs_.data(); in.coeff_len = m.cf_len.data(); in.flags = flags;
+        in.coeff_ptr = ptrs_.data(); in.coeff_len = m.cf_len.data(); in.flags = flags | (m.src_on_device ? GAMBA_CUDA_STEP_DEVICE_COLIDX : 0u);
         gamba_cuda_step_out o{};
         const double t0 = now_s();
         if (world_ > 1) { { std::lock_guard<std::mutex> g(mu_); done_ = 0; ++gen_; } cv_.notify_all(); }

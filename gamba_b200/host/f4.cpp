@@ -22,6 +22,7 @@ F4::F4(const PolySystem& in, const Params& prm, Engine& eng)
     cx_.init((int)in.vars.size(), prm_.num_elim, prm_.seed);
     bt_ = MonoTable(&cx_, 1 << 16);
     st_ = MonoTable(&cx_, 1 << 16);
+    rg_ = eng_.rowgen();
     import_generators();
 }
 
@@ -224,8 +225,9 @@ long F4::select_pairs(int32_t& deg) {
 
 void F4::clear_step() {
     st_.clear();
-    row_mon_.clear(); row_off_.assign(1, 0); row_gen_.clear(); row_top_.clear();
+    row_mon_.clear(); row_off_.assign(1, 0); row_gen_.clear(); row_top_.clear(); row_lead_.clear();
     has_red_.clear();
+    if (rg_) rg_->begin((uint32_t)cx_.stride);
 }
 
 // Append the rows gen[i] * x^q[i] (q: flat exponent vectors of full stride) to the step: every term
@@ -241,7 +243,7 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
     uint64_t terms = 0;
     row_off_.reserve(row_off_.size() + nb);
     for (size_t i = 0; i < nb; ++i) { terms += G_[gens[i]].mon.size(); row_off_.push_back(row_off_[r0] + terms); }
-    row_mon_.resize(row_off_.back());
+    if (!rg_) row_mon_.resize(row_off_.back());
     row_gen_.insert(row_gen_.end(), gens.begin(), gens.end());
     row_top_.insert(row_top_.end(), tops.begin(), tops.end());
     {   // contiguous term data of the generators of this batch (once per generator)
@@ -259,6 +261,29 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
             }
         });
     }
+    row_lead_.resize(r0 + nb);
+    if (rg_) {
+        // Rows on the engine's device: the basis polynomials' terms are uploaded once, the products are looked up / inserted in
+        // the device's monomial table and the handles stay there (the staging kernels read them in place). Back come one lead
+        // handle per row and the monomials the batch introduced - mirrored into st_ (exponents and hashes only: nothing is
+        // looked up on the host any more) for the reducer search, the column sort and the new basis elements.
+        double tA = now_s();
+        std::vector<uint64_t> first(nb);
+        std::vector<uint32_t> nt(nb);
+        for (size_t i = 0; i < nb; ++i) {
+            Poly& f = G_[gens[i]];
+            if (f.dev_first == ~0ull) f.dev_first = rg_->add_poly((uint32_t)f.mon.size(), f.ex.data(), f.hv.data());
+            first[i] = f.dev_first; nt[i] = (uint32_t)f.mon.size();
+        }
+        const uint32_t before = st_.n;
+        const uint32_t after = rg_->add_rows((uint32_t)nb, first.data(), nt.data(), qs.data(), hqs.data(), &row_lead_[r0]);
+        if (after > before) {
+            if (st_.hv.size() < after) { const size_t cap = std::max<size_t>(after, st_.hv.size() + st_.hv.size() / 2 + 1024); st_.hv.resize(cap); st_.ex.resize(cap * st); }
+            rg_->fetch(before, after - before, &st_.ex[(size_t)before * st], &st_.hv[before]);
+            st_.n = after;
+        }
+        dbg_t_[1] += now_s() - tA;
+    } else
     // Sub-batches: the table must have room for every term of a batch being NEW (no growth inside the
     // parallel region), while almost all terms are hits - so a batch is capped near the table's size.
     for (size_t b0 = 0; b0 < nb;) {
@@ -300,9 +325,10 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
         dbg_t_[1] += now_s() - tA;
         b0 = b1;
     }
+    if (!rg_) for (size_t i = 0; i < nb; ++i) row_lead_[r0 + i] = row_mon_[row_off_[r0 + i]];
     if (has_red_.size() < st_.size()) has_red_.resize(st_.size(), 0);
     for (size_t i = 0; i < nb; ++i)
-        if (tops[i]) has_red_[row_mon_[row_off_[r0 + i]]] = 1;
+        if (tops[i]) has_red_[row_lead_[r0 + i]] = 1;
 }
 
 // Rows of the selected pairs (source/matrix.hpp:215-347): per distinct lcm the
@@ -421,7 +447,7 @@ void F4::convert() {
     const size_t nrows = row_gen_.size();
     std::vector<uint32_t> top, bot;
     for (uint32_t r = 0; r < nrows; ++r) (row_top_[r] ? top : bot).push_back(r);
-    auto lead = [&](uint32_t r) { return colof[row_mon_[row_off_[r]]]; };
+    auto lead = [&](uint32_t r) { return colof[row_lead_[r]]; };
     std::sort(top.begin(), top.end(), [&](uint32_t a, uint32_t b) { return lead(a) < lead(b); });
     std::stable_sort(bot.begin(), bot.end(), [&](uint32_t a, uint32_t b) { return lead(a) > lead(b); });
 
@@ -466,7 +492,8 @@ void F4::convert() {
     };
     for (uint32_t r : top) place(r);
     for (uint32_t r : bot) place(r);
-    M_.src = row_mon_.data(); M_.src_len = row_mon_.size();
+    if (rg_) { uint64_t n = 0; M_.src = rg_->rows_device(n); M_.src_len = n; M_.src_on_device = true; }
+    else { M_.src = row_mon_.data(); M_.src_len = row_mon_.size(); M_.src_on_device = false; }
     M_.col_map.swap(h2c);
     stats.t_convert += now_s() - t0;
     stats.max_rows = std::max<uint64_t>(stats.max_rows, nrows);
@@ -493,6 +520,14 @@ void F4::dump_step(const char* tag) {
     }
     char name[64];
     std::snprintf(name, sizeof name, "/step_%s.bin", tag);
+    if (M_.src_on_device) {       // the rows live on the GPU: bring them over for the file
+        row_mon_.resize(M_.src_len);
+        rg_->download_rows(0, M_.src_len, row_mon_.data());
+        const uint32_t* dev = M_.src;
+        M_.src = row_mon_.data(); M_.src_on_device = false;
+        write_step_file(prm_.dump_dir + name, M_);
+        M_.src = dev; M_.src_on_device = true;
+    } else
     write_step_file(prm_.dump_dir + name, M_);
     std::snprintf(name, sizeof name, "/rows_%s.bin", tag);
     write_rows_file(prm_.dump_dir + name, R_);
@@ -529,7 +564,7 @@ void F4::final_reduce() {
         std::vector<uint32_t> hs(nr.size(), 0);
         std::vector<uint8_t> tp(nr.size(), 0);
         add_rows(nr, qs, hs, tp);
-        for (size_t i = 0; i < nr.size(); ++i) has_red_[row_mon_[row_off_[i]]] = 1;  // leads need no reducer
+        for (size_t i = 0; i < nr.size(); ++i) has_red_[row_lead_[i]] = 1;  // leads need no reducer
     }
     symbolic();
     convert();

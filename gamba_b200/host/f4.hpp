@@ -61,6 +61,7 @@ private:
         uint32_t deg = 0;
         uint64_t lm_mask = 0;
         bool redundant = false;
+        uint64_t dev_first = ~0ull;  // where its terms start in the device's term store (row generation on the GPU)
     };
     struct Pair { uint32_t i, j, lcm; int32_t deg; };
 
@@ -85,6 +86,8 @@ private:
     std::vector<uint64_t> row_off_;
     std::vector<uint32_t> row_gen_;
     std::vector<uint8_t> row_top_;
+    std::vector<uint32_t> row_lead_;     // step handle of every row's leading monomial
+    RowGenDevice* rg_ = nullptr;         // rows are generated on the engine's device (CUDA engine) instead of here
     std::vector<uint8_t> has_red_;       // per step-table monomial
     std::vector<uint32_t> order_;        // column -> step handle
     std::vector<uint32_t> nonpiv_col_;   // relative non-pivot index -> column

@@ -47,7 +47,7 @@ extern "C" {
 #endif
 
 #define GAMBA_CUDA_ABI_VERSION 4   /* 4: gamba_cuda_counters grew (dense_macs, seconds_inverse_last, solve_mode, panel_t, seconds_operands_last),
-                                      GAMBA_CUDA_STEP_DEVICE_INDICES, gamba_cuda_measure_int8_peak */
+                                      GAMBA_CUDA_STEP_DEVICE_INDICES / _COLIDX, gamba_cuda_measure_int8_peak, gamba_cuda_rowgen_* */
 
 #define GAMBA_CUDA_REPR_STANDARD   0u
 #define GAMBA_CUDA_REPR_MONTGOMERY 1u
@@ -62,6 +62,9 @@ extern "C" {
                                           device and are used where they are until the next step is staged (a caller that
                                           builds or keeps its step matrices on the GPU; bench.py's resident-input leg).
                                           coeff_ptr / coeff_len stay host arrays (see "coeff_cache"). Not with a broadcast callback. */
+
+#define GAMBA_CUDA_STEP_DEVICE_COLIDX 4u  /* col_idx alone points to device memory: the handle array gamba_cuda_rowgen_add_rows
+                                          filled (gamba_cuda_rowgen_rows); every other array is a host array */
 
 typedef struct gamba_cuda_engine gamba_cuda_engine;
 
@@ -184,6 +187,28 @@ typedef struct gamba_cuda_counters {
                                           seconds_schur_last), last step                                                          */
 } gamba_cuda_counters;
 int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
+
+/* Row generation of symbolic preprocessing on the device (role of matrix_f4::create_multiplied_poly_matrix_row
+   and the matrix' monomial hash table, source/matrix.hpp:387-444; callers insert_spairs :215-347 and symbolic_preprocessing :469-566).
+   The step's monomial table and its rows (as 32-bit monomial handles, numbered in order of first appearance) live on the device;
+   the driver keeps the reducer search (source/matrix.hpp:569-600) and gets back, per batch, the new monomials and one lead handle
+   per row. Exponent vectors are `stride` uint16 wide (whatever layout the driver uses; only equality and addition matter) with
+   additive 32-bit hashes: hash(a * b) = hash(a) + hash(b) (source/monomial.hpp:80-90,126-131).
+     rowgen_begin        new step: empty table, no rows (polynomials uploaded earlier stay)
+     rowgen_add_poly     upload the terms of a basis polynomial once; *first_term identifies it in add_rows
+     rowgen_add_rows     append the rows poly[i] * x^q[i]; lead_out[i] = handle of row i's first term; *n_monomials = size of the
+                         table afterwards (handles [old size, new size) are the monomials this batch introduced)
+     rowgen_fetch_monomials   exponent vectors and hashes of the handles [first, first + count)
+     rowgen_rows         device pointer and length of the handle array: pass it as col_idx with GAMBA_CUDA_STEP_DEVICE_COLIDX,
+                         row_src[r] = where row r starts in it (rows are stored in the order they were added)
+     rowgen_download_rows     copy a range of the handle array to the host (dumps, debugging)                                    */
+int gamba_cuda_rowgen_begin(gamba_cuda_engine* e, uint32_t stride);
+int gamba_cuda_rowgen_add_poly(gamba_cuda_engine* e, uint32_t n_terms, const uint16_t* ex, const uint32_t* hash, uint64_t* first_term);
+int gamba_cuda_rowgen_add_rows(gamba_cuda_engine* e, uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms,
+                               const uint16_t* q_ex, const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials);
+int gamba_cuda_rowgen_fetch_monomials(gamba_cuda_engine* e, uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hash_out);
+int gamba_cuda_rowgen_rows(gamba_cuda_engine* e, const uint32_t** dev_rows, uint64_t* n_entries);
+int gamba_cuda_rowgen_download_rows(gamba_cuda_engine* e, uint64_t first, uint64_t count, uint32_t* out);
 
 /* Microbenchmark: the int8 tensor-core rate of `device` with operands resident in shared memory (tcgen05.mma kind::i8,
    128 x n x 32 per instruction, n = 64, 128 or 256, one CTA per SM), in 10^12 multiply-adds per second. bench.py uses it as

@@ -13,7 +13,7 @@ from conftest import ROOT
 def header_functions():
     text = open(os.path.join(ROOT, "include", "gamba_cuda.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(gamba_cuda_[a-z_]+)\s*\(", text)) - {"gamba_cuda_allgather_fn"})
+    return sorted(set(re.findall(r"\b(gamba_cuda_[a-z0-9_]+)\s*\(", text)) - {"gamba_cuda_allgather_fn"})
 
 
 def test_header_symbols_exported(built):
