@@ -1,6 +1,7 @@
 #include "f4.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
@@ -117,34 +118,40 @@ void F4::update(uint32_t h) {
     // ~99 % of the candidates are discarded, and only the survivors' lcms enter the basis table.
     struct NP { uint32_t i, at; int32_t deg; uint64_t mask, key; bool coprime, dead; };
     std::vector<NP> np;
-    np.reserve(h);
     std::vector<uint16_t>& L = upd_lcm_;
-    L.clear();
-    bool keys_ok = cx_.nelim == 0;
-    for (uint32_t i = 0; i < h; ++i) {
-        if (G_[i].redundant) continue;
-        const uint16_t* ei = bt_.e(G_[i].mon[0]);
-        const size_t at = L.size();
-        L.resize(at + st);
-        uint16_t* el = &L[at];
-        uint32_t d = 0, d1 = 0; bool cop = true;
-        for (int v = 0; v < nv; ++v) {
-            uint16_t a = ei[2 + v], b = eh[2 + v];
-            if (a && b) cop = false;
-            uint16_t m = std::max(a, b);
-            el[2 + v] = m; d += m; if (v < cx_.nelim) d1 += m;
+    // one slot per older generator, filled by all threads, compacted afterwards (slot i keeps its lcm at L[i * st])
+    std::vector<NP> slot(h);
+    L.resize((size_t)h * st);
+    std::atomic<bool> keys_bad{false}, overflow{false};
+    pool_->parallel_for(h, 512, [&](size_t i0, size_t i1) {
+        for (uint32_t i = (uint32_t)i0; i < (uint32_t)i1; ++i) {
+            slot[i].dead = true;
+            if (G_[i].redundant) continue;
+            const uint16_t* ei = bt_.e(G_[i].mon[0]);
+            uint16_t* el = &L[(size_t)i * st];
+            uint32_t d = 0, d1 = 0; bool cop = true;
+            for (int v = 0; v < nv; ++v) {
+                uint16_t a = ei[2 + v], b = eh[2 + v];
+                if (a && b) cop = false;
+                uint16_t m = std::max(a, b);
+                el[2 + v] = m; d += m; if (v < cx_.nelim) d1 += m;
+            }
+            if (d >= (1u << 16)) { overflow = true; continue; }
+            el[0] = (uint16_t)d; el[1] = (uint16_t)d1;
+            // order-preserving 64-bit prefix of the grevlex comparison (degree, then the last 7 variables reversed)
+            uint64_t key = 0;
+            if (cx_.nelim == 0) {
+                if (d >= 256) keys_bad = true;
+                key = (uint64_t)(d & 0xff) << 56;
+                for (int v = nv - 1, sh = 48; v >= 0 && sh >= 0; --v, sh -= 8) key |= (uint64_t)(0xffu - (el[2 + v] & 0xffu)) << sh;
+            }
+            slot[i] = NP{i, i, (int32_t)d, G_[i].lm_mask | mh, key, cop, false};
         }
-        if (d >= (1u << 16)) throw std::overflow_error("degree overflow");
-        el[0] = (uint16_t)d; el[1] = (uint16_t)d1;
-        // order-preserving 64-bit prefix of the grevlex comparison (degree, then the last 7 variables reversed)
-        uint64_t key = 0;
-        if (cx_.nelim == 0) {
-            keys_ok &= d < 256;
-            key = (uint64_t)(d & 0xff) << 56;
-            for (int v = nv - 1, sh = 48; v >= 0 && sh >= 0; --v, sh -= 8) key |= (uint64_t)(0xffu - (el[2 + v] & 0xffu)) << sh;
-        }
-        np.push_back({i, (uint32_t)(at / st), (int32_t)d, G_[i].lm_mask | mh, key, cop, false});
-    }
+    });
+    if (overflow) throw std::overflow_error("degree overflow");
+    const bool keys_ok = cx_.nelim == 0 && !keys_bad;
+    np.reserve(h);
+    for (uint32_t i = 0; i < h; ++i) if (!slot[i].dead) np.push_back(slot[i]);
     auto ex_of = [&](const NP& q) { return &L[(size_t)q.at * st]; };
     auto same = [&](const NP& a, const NP& b) { return std::memcmp(ex_of(a), ex_of(b), st * sizeof(uint16_t)) == 0; };
     upd_t_[1] += now_s() - tu; tu = now_s();

@@ -1,7 +1,8 @@
 """Row generation of symbolic preprocessing on the device (gamba_cuda_rowgen_*; reference:
 matrix_f4::create_multiplied_poly_matrix_row + the matrix' monomial table, source/matrix.hpp:387-444) against a plain
-dictionary on the host: same monomial sets, rows that decode to the same monomials, handles numbered densely in order of
-appearance, table growth (rehash) and several batches per step. The end-to-end check is that the product driver, which
+dictionary on the host: same monomial sets, rows that decode to the same monomials, dense handles (one per distinct
+monomial; their order inside a batch is whatever the device's atomics made it - nothing depends on it), table growth
+(rehash) and several batches per step. The end-to-end check is that the product driver, which
 generates every row this way, reproduces the goldens (tests/test_gpu_e2e.py) and the oracle driver's bases
 (tests/test_gpu_named.py)."""
 import ctypes as C
@@ -89,5 +90,5 @@ def test_rows_match_a_dictionary(built, nv, n_polys, max_terms, n_rows, seed):
     ft = np.array([firsts[0]], dtype=np.uint64); nt = np.array([len(polys[0][1])], dtype=np.uint32)
     q0 = np.ascontiguousarray(vec(np.zeros(nv, dtype=np.uint16))[None, :]); h0 = np.zeros(1, dtype=np.uint32)
     assert lib.gamba_cuda_rowgen_add_rows(h, 1, ptr(ft), ptr(nt), ptr(q0), ptr(h0), ptr(lead), C.byref(nmon)) == 0
-    assert nmon.value == len({tuple(v.tolist()) for v in polys[0][0]}) and lead[0] == 0
+    assert nmon.value == len({tuple(v.tolist()) for v in polys[0][0]}) and lead[0] < nmon.value
     eng.close()
