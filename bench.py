@@ -119,6 +119,15 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- workload
 
+def all_cores():
+    """subprocess preexec: the product driver is multi-threaded on the host; torch / OpenMP may have narrowed this process's
+    CPU affinity, which a child would inherit."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except (AttributeError, OSError):
+        pass
+
+
 def parse_systems(spec: str):
     out = []
     for item in spec.split(","):
@@ -140,7 +149,7 @@ def generate_workload(system: str, max_spairs: int, min_nnz: int, rank: int, wor
         t = time.time()
         r = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out.txt"), "-v", "1", "--dump-steps", d,
                             "--dump-min-nnz", str(min_nnz), "--dump-every", str(every), "--max-spairs", str(max_spairs)],
-                           capture_output=True, text=True)
+                           capture_output=True, text=True, preexec_fn=all_cores)
         if r.returncode != 0:
             raise RuntimeError("workload generation failed (no CPU fallback): " + r.stderr[-2000:])
         with open(os.path.join(d, "driver.log"), "w") as f:
@@ -279,13 +288,14 @@ def e2e_seconds(groups):
         inp = systems.write_system(name, os.path.join(d, name + ".txt"))
         t = time.perf_counter()
         r = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out.txt"), "-v", "1", "--max-spairs", str(sp)],
-                           capture_output=True, text=True)
+                           capture_output=True, text=True, preexec_fn=all_cores)
         wall = time.perf_counter() - t
         m = re.search(r"linalg \(wall\)\s+([0-9.]+) sec\s+\[device-only ([0-9.]+)\]", r.stdout)
         extra = {}
         if name.startswith(("kat15", "eco15")) and sp != 0:      # the GPU-preferred setting: fewer, larger steps, same basis
             t = time.perf_counter()
-            r0 = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out0.txt"), "-v", "0", "--max-spairs", "0"], capture_output=True, text=True)
+            r0 = subprocess.run([GAMBA, "-i", inp, "-o", os.path.join(d, "out0.txt"), "-v", "0", "--max-spairs", "0"], capture_output=True, text=True,
+                                preexec_fn=all_cores)
             same = r0.returncode == 0 and open(os.path.join(d, "out0.txt"), "rb").read() == open(os.path.join(d, "out.txt"), "rb").read()
             extra = {"seconds_max_spairs_0": time.perf_counter() - t if r0.returncode == 0 else None, "same_basis_as_default_run": same}
         out[name] = {"seconds": wall if r.returncode == 0 else None, "max_spairs": sp, **extra,

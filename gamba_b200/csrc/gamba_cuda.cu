@@ -155,6 +155,9 @@ struct gamba_cuda_engine {
     int64_t opt_panel_t = 0;         // 0 = chosen per step from n_top
     int64_t opt_panel_max_top = 1000000;  // operands of K^2 / 2 bytes per limb: a cap besides the memory budget and the cost estimate
     gcu::DevBuf d_at, d_at_off, d_cd, d_cx, d_wr, d_vt, d_adt, d_gx, d_dinv;
+    gcu::DevBuf d_bs_bitmap, d_bs_rank, d_bs_base, d_bs_klist, d_bs_op;      // block-sparse operands (kernels_schur.cuh)
+    int64_t opt_bsparse = 1;         // 1: the products skip the blocks of A / B that hold no entry
+    double last_occ = 1.0;           // occupied fraction of the blocks, previous step that measured it
     double t_inv_dev = 0;            // recursive doubling of the inverse diagonal tiles (part of the elimination time)
     gcu::DevBuf d_mc_s, d_mc_dt, d_mc_dc, d_mc_nz;
     int64_t opt_mc_ech = 1;          // Monte-Carlo combinations of the rows of D' in front of the echelon (accepted with a rank margin of 32)
@@ -178,15 +181,16 @@ struct gamba_cuda_engine {
     // blocked solve: products with the earlier tiles (K^2/2) and with the inverse diagonal tiles (K T) at the measured int8
     // rate, the inverse tiles themselves (K T^2 / 3, small batched products: a third of the rate), zeroing / scattering the
     // operands (bytes at ~3 TB/s), ~3 launches per tile
-    static double model_panel(double mpad, double k, double nl, double t) {
+    // occ = occupied fraction of the 128 x bn blocks of A (block-sparse operands skip the rest)
+    static double model_panel(double mpad, double k, double nl, double t, double occ) {
         const double rate = 1.2e15;
-        return mpad * (k * k * 0.5 + k * t) * nl * nl / rate + k * t * t / 3.0 * nl * nl / (rate / 3) +
-               (nl * k * k * 0.5 + 3.0 * nl * k * t) / 3e12 + (3.0 * k / t + 12) * 4e-6;
+        return mpad * (k * k * 0.5 * occ + k * t) * nl * nl / rate + k * t * t / 3.0 * nl * nl / (rate / 3) +
+               (nl * k * k * 0.5 * occ + 3.0 * nl * k * t) / 3e12 + (3.0 * k / t + 12) * 4e-6;
     }
     // sparse-blocked kernel: every block of R rows streams all of A: rows x nnz(A) row-entries at ~7e11 / s (kat15-15, K = 500 k)
     static double model_block(double nloc, double k, double a, bool small) { return nloc * k * a / (small ? 7e11 : 4e11); }
     double calib[3] = {1, 1, 1};     // measured / modelled time of the last steps in each mode (sparse, sparse-blocked, tc-solve)
-    int64_t opt_panel_max_gb = 32;   // budget for the operands of the tc-solve alone (beyond ~170 k pivot rows the sparse kernels win anyway)
+    int64_t opt_panel_max_gb = 64;   // budget for the operands of the tc-solve alone (estimated with the block occupancy of the previous step)
     bool use_schur = false, use_block = false;   // decided per staged step (choose_layout)
     int64_t opt_schur_max_gb = 96;   // budget for the limb-plane operands of the products
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
@@ -321,9 +325,10 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         if (opt_panel_t > 0) PANEL_T = (uint32_t)opt_panel_t;
         else PANEL_T = n_top >= 12288 ? 2048u : n_top >= 3072 ? 1024u : 512u;
         bool panel_fits = false;
+        const double occ_ = opt_bsparse && n_top >= 8192 ? last_occ : 1.0;
         if (use_schur && !opt_mc && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
             const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T, kt_ = ntp_ * PANEL_T;
-            const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2) + 3.25 * nl * (double)kt_ * PANEL_T;
+            const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2) * occ_ + 3.25 * nl * (double)kt_ * PANEL_T;
             panel_fits = at_b <= (double)opt_panel_max_gb * 1e9 &&
                          at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kt_ + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9;
         }
@@ -335,7 +340,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
             double est[3];
             est[0] = calib[0] * hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
             est[1] = block_ok && n_top >= 8192 ? calib[1] * model_block(nloc, n_top, last_a, f.small != 0) : 1e30;
-            est[2] = panel_fits && opt_panel >= 1 ? calib[2] * model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T) : 1e30;
+            est[2] = panel_fits && opt_panel >= 1 ? calib[2] * model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T, occ_) : 1e30;
             mode = est[1] < est[0] ? 1 : 0;
             if (est[2] < est[mode]) mode = 2;
             if (++since_explore >= 12) {          // the runner-up, if it is within 2x
@@ -601,8 +606,8 @@ void gamba_cuda_engine::eliminate() {
     const uint32_t tkc = f.small ? TcCfg<2>::KCHUNK : TcCfg<4>::KCHUNK;
     const uint32_t kchunk = opt_schur_kchunk > 0 ? (uint32_t)std::min<int64_t>(opt_schur_kchunk, tkc) : tkc;
     const bool schur = use_schur && n_local;
-    const bool block = schur && use_block;
-    const bool panel = schur && use_panel;
+    bool block = schur && use_block;
+    bool panel = schur && use_panel;
     elim_grid = 1;
     if (!panel) {
         GCU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -657,23 +662,62 @@ void gamba_cuda_engine::eliminate() {
     const uint32_t mp = (n_local + 127u) / 128u * 128u, np = (L.n_nonpiv + 127u) / 128u * 128u;   // rows per limb plane
     const uint64_t mx_plane = (uint64_t)mp * kp, bt_plane = (uint64_t)np * kp;
     const uint64_t tri_plane = (uint64_t)kt * T;
-    // buffers first: growing one may go to the driver, which must not sit inside the event-timed region
+    GCU_CHECK(cudaEventRecord(ev[2], stream));
+    // Block-sparse operands (kernels_schur.cuh, BsArgs): which blocks of 128 pivot rows x bn columns of B (and, for the blocked
+    // solve, of A right of a row's own tile) hold an entry at all. The products then skip the empty ones.
+    const bool bs = schur && opt_bsparse && L.tile_cols % bn == 0 && L.n_top >= 8192;
+    const uint32_t per_tile = bs ? L.tile_cols / bn : 0;
+    const uint32_t n_cb_piv = (bs && panel) ? ntp * per_tile : 0, n_cb = n_cb_piv + (bs ? L.n_tiles_nonpiv * per_tile : 0);
+    const uint32_t kb_words = ((L.n_top + 127u) / 128u + 31u) / 32u;
+    uint64_t nb_total = 0, nb_a = 0;
+    BsArgs bsa{};
+    if (bs) {
+        d_bs_bitmap.ensure((uint64_t)n_cb * kb_words * 4); d_bs_rank.ensure((uint64_t)n_cb * kb_words * 4); d_bs_base.ensure((uint64_t)(n_cb + 1) * 4);
+        GCU_CHECK(cudaMemsetAsync(d_bs_bitmap.p, 0, (uint64_t)n_cb * kb_words * 4, stream));
+        GCU_CHECK(cudaMemsetAsync(d_bs_base.p, 0, (uint64_t)(n_cb + 1) * 4, stream));
+        bsa.L = L; bsa.seg = d_seg.as<uint32_t>(); bsa.ent = d_ent.as<uint2>(); bsa.cbw = bn; bsa.kb_words = kb_words;
+        bsa.n_cb_piv = n_cb_piv; bsa.n_cb = n_cb; bsa.bitmap = d_bs_bitmap.as<uint32_t>(); bsa.rank = d_bs_rank.as<uint32_t>();
+        bsa.blk_base = d_bs_base.as<uint32_t>(); bsa.with_a = panel ? 1u : 0u;
+        bs_mark_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(bsa);
+        GCU_CHECK(cudaGetLastError());
+        bs_rank_kernel<<<(n_cb + 7) / 8, 256, 0, stream>>>(bsa);
+        GCU_CHECK(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, bsa.blk_base, bsa.blk_base, (int64_t)(n_cb + 1), stream));
+        d_scan_tmp.ensure(tmp_bytes);
+        GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, bsa.blk_base, bsa.blk_base, (int64_t)(n_cb + 1), stream));
+        uint32_t cnt[2] = {0, 0};
+        GCU_CHECK(cudaMemcpyAsync(&cnt[0], bsa.blk_base + n_cb, 4, cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaMemcpyAsync(&cnt[1], bsa.blk_base + n_cb_piv, 4, cudaMemcpyDeviceToHost, stream));
+        GCU_CHECK(cudaStreamSynchronize(stream));
+        nb_total = cnt[0]; nb_a = cnt[1];
+        ctr.kernel_launches += 3;
+        const double tri_cells = (double)n_cb_piv * ((L.n_top + 127u) / 128u) * 0.5, b_cells = (double)(n_cb - n_cb_piv) * ((L.n_top + 127u) / 128u);
+        last_occ = panel && tri_cells > 0 ? (double)nb_a / tri_cells : (b_cells > 0 ? (double)(nb_total - nb_a) / b_cells : 1.0);
+        last_occ = std::min(1.0, std::max(0.01, last_occ));
+        // blocked solve whose operands do not fit after all: the sparse kernel for blocks of rows on the same layout
+        if (panel && (double)nl * nb_total * bn * 128.0 > (double)opt_schur_max_gb * 1e9) { panel = false; block = true; use_panel = false; use_block = true; }
+    }
+    const uint64_t bs_plane = nb_total * bn * 128ull;
+    // buffers: growing one may go to the driver
     if (schur) {
         d_mx.ensure(nl * mx_plane);
-        d_bt.ensure(nl * bt_plane);
+        if (bs) { d_bs_op.ensure(std::max<uint64_t>(nl * bs_plane, 16)); d_bs_klist.ensure(std::max<uint64_t>(nb_total, 1) * 4); }
+        else d_bt.ensure(nl * bt_plane);
         if (panel) {     // operands of the products with the earlier tiles: tile t takes [nl][T][t * T] bytes
-            at_off.assign(ntp + 1, 0);
-            for (uint32_t t = 1; t <= ntp; ++t) at_off[t] = at_off[t - 1] + (t > 1 ? (uint64_t)nl * T * (uint64_t)(t - 1) * T : 0);
-            at_bytes = at_off[ntp];
-            d_at.ensure(std::max<uint64_t>(at_bytes, 16));
-            d_at_off.ensure(at_off.size() * sizeof(uint64_t));
+            if (!bs) {
+                at_off.assign(ntp + 1, 0);
+                for (uint32_t t = 1; t <= ntp; ++t) at_off[t] = at_off[t - 1] + (t > 1 ? (uint64_t)nl * T * (uint64_t)(t - 1) * T : 0);
+                at_bytes = at_off[ntp];
+                d_at.ensure(std::max<uint64_t>(at_bytes, 16));
+                d_at_off.ensure(at_off.size() * sizeof(uint64_t));
+            }
             d_cd.ensure((uint64_t)mp * T * sizeof(uint32_t));
             d_cx.ensure((uint64_t)nl * mp * T);
             d_wr.ensure(nl * tri_plane); d_vt.ensure(nl * tri_plane); d_adt.ensure(nl * tri_plane);
             d_gx.ensure(std::max<uint64_t>(nl * tri_plane / 4, 16));
         }
     }
-    GCU_CHECK(cudaEventRecord(ev[2], stream));
     if (schur) {
         // operands of the products, rebuilt for every reduction of the step (they are part of the algorithm, not of the
         // hand-over): operand_build_kernel writes every byte of Bt / At / Adt, so only the planes written piecemeal are zeroed
@@ -686,27 +730,47 @@ void gamba_cuda_engine::eliminate() {
         const uint32_t och = f.small ? op_ch<2>() : op_ch<4>();
         GCU_CHECK(cudaFuncSetAttribute(opk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op_sm));
         const uint32_t chunks = (L.tile_cols + och - 1) / och;
-        oa.mode = OP_B; oa.out = d_bt.as<uint8_t>(); oa.plane = bt_plane; oa.pitch = kp; oa.rows = np;
-        if ((uint64_t)L.n_tiles_nonpiv * L.tile_cols < np)        // padding rows beyond the last tile (tile width not a multiple of 128)
-            for (uint32_t l = 0; l < nl; ++l)
-                GCU_CHECK(cudaMemsetAsync(d_bt.as<uint8_t>() + l * bt_plane + (uint64_t)L.n_tiles_nonpiv * L.tile_cols * kp, 0,
-                                          (uint64_t)(np - L.n_tiles_nonpiv * L.tile_cols) * kp, stream));
-        opk<<<dim3(kp / OP_KB, chunks, L.n_tiles_nonpiv), 256, op_sm, stream>>>(oa);
-        GCU_CHECK(cudaGetLastError());
-        ctr.kernel_launches += 1;
-        if (panel) {
-            GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-            if (ntp > 1) {
+        if (bs) {
+            bsa.klist = d_bs_klist.as<uint32_t>();
+            bs_list_kernel<<<(n_cb + 7) / 8, 256, 0, stream>>>(bsa);
+            GCU_CHECK(cudaGetLastError());
+            oa.bitmap = bsa.bitmap; oa.rank = bsa.rank; oa.blk_base = bsa.blk_base; oa.kb_words = kb_words; oa.cbw = bn; oa.n_cb_piv = n_cb_piv;
+            oa.out = d_bs_op.as<uint8_t>(); oa.plane = bs_plane; oa.rows = 0xffffffffu; oa.pitch = 0;
+            oa.mode = OP_B;
+            opk<<<dim3(kp / OP_KB, chunks, L.n_tiles_nonpiv), 256, op_sm, stream>>>(oa);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 2;
+            if (panel && ntp > 1) {
+                oa.mode = OP_AT;
+                opk<<<dim3((ntp - 1) * (T / OP_KB), chunks, ntp), 256, op_sm, stream>>>(oa);
+                GCU_CHECK(cudaGetLastError());
+                ctr.kernel_launches += 1;
+            }
+            oa.bitmap = nullptr;
+        } else {
+            oa.mode = OP_B; oa.out = d_bt.as<uint8_t>(); oa.plane = bt_plane; oa.pitch = kp; oa.rows = np;
+            if ((uint64_t)L.n_tiles_nonpiv * L.tile_cols < np)        // padding rows beyond the last tile (tile width not a multiple of 128)
+                for (uint32_t l = 0; l < nl; ++l)
+                    GCU_CHECK(cudaMemsetAsync(d_bt.as<uint8_t>() + l * bt_plane + (uint64_t)L.n_tiles_nonpiv * L.tile_cols * kp, 0,
+                                              (uint64_t)(np - L.n_tiles_nonpiv * L.tile_cols) * kp, stream));
+            opk<<<dim3(kp / OP_KB, chunks, L.n_tiles_nonpiv), 256, op_sm, stream>>>(oa);
+            GCU_CHECK(cudaGetLastError());
+            ctr.kernel_launches += 1;
+            if (panel && ntp > 1) {
+                GCU_CHECK(cudaMemcpyAsync(d_at_off.p, at_off.data(), at_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
                 oa.mode = OP_AT; oa.out = d_at.as<uint8_t>(); oa.at_off = d_at_off.as<uint64_t>();
                 opk<<<dim3((ntp - 1) * (T / OP_KB), chunks, ntp), 256, op_sm, stream>>>(oa);
                 GCU_CHECK(cudaGetLastError());
+                ctr.kernel_launches += 1;
             }
-            oa.mode = OP_ADT; oa.out = d_adt.as<uint8_t>(); oa.plane = tri_plane; oa.pitch = T; oa.at_off = nullptr;
+        }
+        if (panel) {
+            oa.mode = OP_ADT; oa.out = d_adt.as<uint8_t>(); oa.plane = tri_plane; oa.pitch = T; oa.at_off = nullptr; oa.rows = 0;
             opk<<<dim3(T / OP_KB, chunks, ntp), 256, op_sm, stream>>>(oa);
             GCU_CHECK(cudaGetLastError());
             GCU_CHECK(cudaMemsetAsync(d_wr.p, 0, nl * tri_plane, stream));
             GCU_CHECK(cudaMemsetAsync(d_vt.p, 0, nl * tri_plane, stream));
-            ctr.kernel_launches += 2;
+            ctr.kernel_launches += 1;
         }
     }
     GCU_CHECK(cudaEventRecord(ev[6], stream));
@@ -750,6 +814,7 @@ void gamba_cuda_engine::eliminate() {
         // 2. tile by tile: cd = C_t + M[:, < tT] A[< tT, tile t], then M[:, tile t] = -cd Inv_t
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
         const CUtensorMap map_cx = make_tmap_u8(d_cx.p, T, (uint64_t)nl * mp, TC_BK, TC_BM);
+        const CUtensorMap map_bs = bs && nb_total ? make_tmap_u8(d_bs_op.p, TC_BK, (uint64_t)nl * nb_total * bn, TC_BK, bn) : map_cx;
         TriRowsArgs ra{};
         ra.L = L; ra.seg = d_seg.as<uint32_t>(); ra.ent = d_ent.as<uint2>(); ra.row_begin = rank; ra.row_step = world; ra.n_local = n_local;
         for (uint32_t t = 0; t < ntp; ++t) {
@@ -763,7 +828,8 @@ void gamba_cuda_engine::eliminate() {
             ta.first_piv = d_first.as<uint32_t>(); ta.row_begin = rank; ta.row_step = world;
             ta.kchunk = kchunk; ta.k_end = t * T;
             ta.o1 = d_cx.as<uint8_t>(); ta.o1_plane = (uint64_t)mp * T; ta.o1_ld = T;
-            const CUtensorMap map_at = t ? make_tmap_u8(d_at.as<uint8_t>() + at_off[t], (uint64_t)t * T, (uint64_t)nl * T, TC_BK, bn) : map_vt;
+            if (bs) { ta.np = (uint32_t)(nb_total * bn); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>(); ta.kl_cb0 = t * per_tile; }
+            const CUtensorMap map_at = bs ? map_bs : t ? make_tmap_u8(d_at.as<uint8_t>() + at_off[t], (uint64_t)t * T, (uint64_t)nl * T, TC_BK, bn) : map_vt;
             launch_limb_gemm<EPI_RMW_LIMBS>(f.small != 0, map_mx, map_at, ta, 1, stream);
             TcArgs xa{};
             xa.f = f; xa.mp = mp; xa.np = kt; xa.n_rows = n_local; xa.n_cols = tw; xa.m_tiles = mp / TC_BM; xa.n_tiles = (tw + bn - 1) / bn;
@@ -820,15 +886,17 @@ void gamba_cuda_engine::eliminate() {
         ta.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); ta.k_first = ea.mc_first; ta.row_begin = rank; ta.row_step = world;
         ta.kchunk = kchunk; ta.k_end = k_used;
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
-        const CUtensorMap map_bt = make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, bn);
+        if (bs) { ta.np = (uint32_t)(nb_total * bn); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>(); ta.kl_cb0 = n_cb_piv; }
+        const CUtensorMap map_bt = bs ? (nb_total ? make_tmap_u8(d_bs_op.p, TC_BK, (uint64_t)nl * nb_total * bn, TC_BK, bn) : map_mx)
+                                      : make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, bn);
         launch_limb_gemm<EPI_RMW>(f.small != 0, map_mx, map_bt, ta, 1, stream);
         ctr.kernel_launches += 1;
         ctr.schur_macs = (uint64_t)n_local * L.n_top * L.n_nonpiv;
         // every dense product of the stage, in mod-p multiply-adds (x nl^2 = int8 multiply-adds on the tensor cores)
-        ctr.dense_macs = ctr.schur_macs;
+        ctr.dense_macs = bs ? (uint64_t)((double)(nb_total - nb_a) * 128.0 * bn * mp) : ctr.schur_macs;
         if (panel) {
-            double m = 0;
-            for (uint32_t t = 0; t < ntp; ++t) m += (double)mp * T * ((double)t * T + T);
+            double m = bs ? (double)nb_a * 128.0 * bn * mp + (double)mp * T * (double)kt : 0.0;
+            for (uint32_t t = 0; t < ntp && !bs; ++t) m += (double)mp * T * ((double)t * T + T);
             for (uint32_t s = TRI_BASE; s < T; s *= 2) m += 2.0 * (double)(kt / (2 * s)) * s * s * s;
             ctr.dense_macs += (uint64_t)m;
         }
@@ -992,7 +1060,7 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
             const uint32_t nl_ = f.small ? 2u : 4u;
             const double mpad = (double)((n_local + 127u) / 128u * 128u);
             const int m = use_panel ? 2 : use_block ? 1 : 0;
-            const double model = m == 2 ? model_panel(mpad, L.n_top, nl_, PANEL_T)
+            const double model = m == 2 ? model_panel(mpad, L.n_top, nl_, PANEL_T, opt_bsparse && L.n_top >= 8192 ? last_occ : 1.0)
                                : m == 1 ? model_block(n_local, L.n_top, cur_a, f.small != 0)
                                         : hitw * model_sparse(n_local, last_density, L.n_top, cur_a, f.small != 0);
             if (model > 0) calib[m] = std::min(5.0, std::max(0.2, 0.5 * calib[m] + 0.5 * t_sparse_dev / model));
@@ -1390,6 +1458,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "panel_t") { if (value && (value < 128 || value > 8192 || (value & (value - 1)))) throw std::runtime_error("panel_t must be 128 * 2^j, at most 8192"); e->opt_panel_t = value; }
         else if (k == "panel_max_top") e->opt_panel_max_top = value;
         else if (k == "panel_max_gb") e->opt_panel_max_gb = value;
+        else if (k == "bsparse") e->opt_bsparse = value;
         else if (k == "schur_max_gb") e->opt_schur_max_gb = value;
         else if (k == "schur_min_top") e->opt_schur_min_top = value;
         else if (k == "schur_kchunk") e->opt_schur_kchunk = value;

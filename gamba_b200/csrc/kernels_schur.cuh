@@ -52,7 +52,85 @@ struct OpArgs {
     uint32_t rows;              // OP_B: operand rows (non-pivot columns padded to 128)
     uint32_t mode;
     const uint64_t* at_off;     // OP_AT: byte offset of tile t's operand
+    // block-sparse operands (OP_AT, OP_B): only the blocks of 128 pivot rows x cbw columns that hold an entry are stored,
+    // out[l][block id][column in block][128 k bytes]; bitmap / rank / blk_base: BsArgs below
+    const uint32_t* bitmap;     // NULL: dense operand
+    const uint32_t* rank;
+    const uint32_t* blk_base;
+    uint32_t kb_words, cbw, n_cb_piv;
 };
+
+// ---- block-sparse operands ------------------------------------------------------------------------------------------
+// A and B of a katsura / eco step hold 0.1-0.5 % non-zeros, and at the granularity of the product kernel's operand boxes
+// (128 pivot rows x 128 columns; 64 columns for 4 limbs) only 12-30 % of the blocks hold an entry at all
+// (profiles/r02_block_occupancy.txt: kat15-15, K = 440-517 k: 16-19 %; cyclic9-15: 88 %). The products M * A and M * B then
+// skip the empty blocks: per column block the list of occupied k-blocks, the operand stored block-compressed.
+//   bitmap[cb][kb / 32]  bit kb % 32: block (k-block kb, column block cb) holds an entry; pivot column blocks first
+//                        (cb = column / cbw over the tile-padded pivot range), then the non-pivot ones
+//   rank[cb][w]          occupied blocks of column block cb below bitmap word w
+//   blk_base[cb]         first block id of column block cb (exclusive scan of the counts; blk_base[n_cb] = blocks in total)
+//   klist[id]            k-block of block id: ascending inside a column block
+struct BsArgs {
+    Layout L;
+    const uint32_t* seg;
+    const uint2* ent;
+    uint32_t cbw, kb_words, n_cb_piv, n_cb;
+    uint32_t* bitmap;
+    uint32_t* rank;
+    uint32_t* blk_base;         // [n_cb + 1]: counts before the scan, bases after
+    uint32_t* klist;
+    uint32_t with_a;            // 0: B only (the sparse solves), 1: also A right of a pivot row's own tile (the blocked solve)
+};
+
+// One warp per pivot row: mark the blocks its entries fall into.
+__global__ void __launch_bounds__(256) bs_mark_kernel(BsArgs a) {
+    const Layout& L = a.L;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t k = blockIdx.x * 8 + warp;
+    if (k >= L.n_top) return;
+    const uint32_t nr = L.n_rows, T = L.tile_cols, per_tile = T / a.cbw;
+    const uint32_t kb = k / 128u, word = kb >> 5, bit = 1u << (kb & 31u);
+    for (uint32_t t = a.with_a ? k / T + 1 : L.n_tiles_piv; t < L.n_tiles; ++t) {
+        const uint32_t s = a.seg[(uint64_t)t * nr + k], e = a.seg[(uint64_t)t * nr + k + 1];
+        const uint32_t cb0 = t < L.n_tiles_piv ? t * per_tile : a.n_cb_piv + (t - L.n_tiles_piv) * per_tile;
+        for (uint32_t i = s + lane; i < e; i += 32) {
+            const uint2 en = __ldg(a.ent + i);
+            if (en.y == 0) continue;                       // padding
+            uint32_t* w = a.bitmap + (uint64_t)(cb0 + (en.x & 0xffffu) / a.cbw) * a.kb_words + word;
+            if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
+        }
+    }
+}
+
+// One warp per column block: blocks below every bitmap word, count of the column block.
+__global__ void __launch_bounds__(256) bs_rank_kernel(BsArgs a) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cb = blockIdx.x * 8 + warp;
+    if (cb >= a.n_cb) return;
+    uint32_t run = 0;
+    for (uint32_t w0 = 0; w0 < a.kb_words; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        const uint32_t c = w < a.kb_words ? __popc(a.bitmap[(uint64_t)cb * a.kb_words + w]) : 0u;
+        uint32_t inc = c;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += v; }
+        if (w < a.kb_words) a.rank[(uint64_t)cb * a.kb_words + w] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) a.blk_base[cb] = run;
+}
+
+// One warp per column block (after the exclusive scan of blk_base): the k-blocks of its occupied blocks, ascending.
+__global__ void __launch_bounds__(256) bs_list_kernel(BsArgs a) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cb = blockIdx.x * 8 + warp;
+    if (cb >= a.n_cb) return;
+    const uint32_t base = a.blk_base[cb];
+    for (uint32_t w = lane; w < a.kb_words; w += 32) {
+        uint32_t bits = a.bitmap[(uint64_t)cb * a.kb_words + w], pos = base + a.rank[(uint64_t)cb * a.kb_words + w];
+        while (bits) { a.klist[pos++] = w * 32 + (__ffs(bits) - 1); bits &= bits - 1; }
+    }
+}
+
 
 template <int NL>
 __global__ void __launch_bounds__(256) operand_build_kernel(OpArgs a) {
@@ -70,12 +148,30 @@ __global__ void __launch_bounds__(256) operand_build_kernel(OpArgs a) {
     } else if (a.mode == OP_AT) {
         if (kb * OP_KB >= z * T) return;                            // only the pivot rows of earlier tiles reach tile z
         tc = z; k0 = kb * OP_KB; orow0 = cc * CH; okoff = k0; pitch = z * T; plane = (uint64_t)T * pitch; rows = T;
-        out += a.at_off[z];
+        if (!a.bitmap) out += a.at_off[z];
     } else {
         tc = z; k0 = z * T + kb * OP_KB; orow0 = z * T + cc * CH; okoff = kb * OP_KB; pitch = a.pitch; plane = a.plane; rows = 0xffffffffu;
     }
     if (orow0 >= rows) return;
     const uint32_t c_lo = cc * CH, c_hi = min(c_lo + CH, T), cw = c_hi - c_lo;     // the tile ends at T
+    // block-sparse: the chunk's column blocks (CH / cbw of them); nothing to do if none of them is occupied for this k-block
+    __shared__ uint32_t s_blk[8];
+    if (a.bitmap) {
+        if (tid < 8) {
+            uint32_t id = 0xffffffffu;
+            const uint32_t sub = tid;
+            if (sub * a.cbw < cw) {
+                const uint32_t cb = (a.mode == OP_B ? a.n_cb_piv + z * (T / a.cbw) : z * (T / a.cbw)) + c_lo / a.cbw + sub;
+                const uint32_t w = a.bitmap[(uint64_t)cb * a.kb_words + (kb >> 5)], bit = kb & 31u;
+                if ((w >> bit) & 1u) id = a.blk_base[cb] + a.rank[(uint64_t)cb * a.kb_words + (kb >> 5)] + __popc(w & ((1u << bit) - 1u));
+            }
+            s_blk[sub] = id;
+        }
+        __syncthreads();
+        bool any = false;
+        for (uint32_t sub = 0; sub * a.cbw < cw; ++sub) any |= s_blk[sub] != 0xffffffffu;
+        if (!any) return;
+    }
     for (uint32_t i = tid * 16; i < NL * CH * OP_PITCH; i += 256 * 16) *reinterpret_cast<uint4*>(op_sm + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
     // in OP_ADT a chunk left of the block's rows holds nothing (A is upper triangular): it is written as zeros
@@ -102,6 +198,10 @@ __global__ void __launch_bounds__(256) operand_build_kernel(OpArgs a) {
         const uint32_t part = w & 7u, c = (w >> 3) % CH, l = (w >> 3) / CH;
         if (c >= cw || orow0 + c >= rows) continue;
         const uint4 v = *reinterpret_cast<const uint4*>(op_sm + ((size_t)l * CH + c) * OP_PITCH + part * 16);
+        if (a.bitmap) {
+            const uint32_t id = s_blk[c / a.cbw];
+            if (id != 0xffffffffu) *reinterpret_cast<uint4*>(a.out + l * a.plane + ((uint64_t)id * a.cbw + c % a.cbw) * OP_KB + part * 16) = v;
+        } else
         *reinterpret_cast<uint4*>(out + l * plane + (uint64_t)(orow0 + c) * pitch + okoff + part * 16) = v;
     }
 }

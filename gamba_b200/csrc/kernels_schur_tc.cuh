@@ -68,6 +68,11 @@ struct TcArgs {
     uint8_t* o2; uint64_t o2_plane; uint32_t o2_ld, o2_row0, o2_row_b, o2_col0, o2_col_b;
     uint32_t tri;               // 1: the A-operand block is upper triangular (rows <= k): k-steps left of the tile's rows are skipped;
                                 // 2: the B-operand block is upper triangular as [k][col] (k <= col): k-steps right of the tile's columns are skipped
+    // block-sparse B-operand (kernels_schur.cuh, BsArgs): the k-steps of output tile column nt are the occupied blocks
+    // klist[kl_base[kl_cb0 + nt] .. kl_base[kl_cb0 + nt + 1]); the operand of block id sits at row id * BN of its limb plane
+    const uint32_t* klist;      // NULL: dense operand, k-steps ks_begin .. ks_end
+    const uint32_t* kl_base;
+    uint32_t kl_cb0;
     uint32_t neg;               // EPI_LIMBS: store (p - x) mod p
     // EPI_LIMBS: count the non-zero outputs (row < n_rows, col < n_cols): stats[0] += 1, stats[2] += len[col0 + col]
     const uint64_t* cnt_row_ptr; unsigned long long* stats;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
     // instruction descriptor (kind::i8): D = s32, A = B = u8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     constexpr uint32_t IDESC = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     extern __shared__ unsigned char tc_smem_raw[];
-    __shared__ uint32_t s_tmem, s_kmin;
+    __shared__ uint32_t s_tmem, s_kmin, s_list[2];
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B atoms are 1024-byte aligned
     const uint32_t bars = base + STAGES * STAGE_BYTES;               // full[STAGES], empty[STAGES], acc_full, acc_empty
@@ -184,7 +189,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
     uint32_t ks_begin = (s_kmin > a.kmin_sub ? s_kmin - a.kmin_sub : 0u) / TC_BK;
     if (a.tri == 1) ks_begin = max(ks_begin, row0 / TC_BK);
     ks_begin = min(ks_begin, ks_end);
-    const uint32_t n_ks = skip_all ? 0u : ks_end - ks_begin;
+    if (a.klist) {            // block-sparse: the list of this column block, from the first k-block any row of the tile reaches
+        if (tid == 0) {
+            uint32_t lo = a.kl_base[a.kl_cb0 + nt];
+            const uint32_t hi = a.kl_base[a.kl_cb0 + nt + 1];
+            uint32_t l = lo, h = hi;
+            while (l < h) { const uint32_t m = (l + h) >> 1; if (a.klist[m] < ks_begin) l = m + 1; else h = m; }
+            lo = l; l = lo; h = hi;
+            while (l < h) { const uint32_t m = (l + h) >> 1; if (a.klist[m] < ks_end) l = m + 1; else h = m; }
+            s_list[0] = lo; s_list[1] = l;
+        }
+        __syncthreads();
+    }
+    const uint32_t l_lo = a.klist ? s_list[0] : 0u;
+    const uint32_t n_ks = skip_all ? 0u : a.klist ? s_list[1] - l_lo : ks_end - ks_begin;
     const uint32_t n_chunks = n_ks ? (n_ks + a.kchunk - 1) / a.kchunk : 0;
 
     if (warp == 0) {
@@ -197,11 +215,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
                 tc_mbar_wait(empty_bar(s), ph ^ 1);
                 tc_mbar_expect_tx(full_bar(s), STAGE_BYTES);
                 const uint32_t dst = base + s * STAGE_BYTES;
-                const int32_t k0 = (int32_t)((ks_begin + i) * TC_BK);
+                const int32_t k0 = (int32_t)((a.klist ? a.klist[l_lo + i] : ks_begin + i) * TC_BK);
 #pragma unroll
                 for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + l * A_LIMB, &map_a, full_bar(s), ka + k0, (int32_t)(l * a.mp) + ra);
+                if (a.klist) {
 #pragma unroll
-                for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_b, full_bar(s), kb + k0, (int32_t)(l * a.np) + rb);
+                    for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_b, full_bar(s), 0, (int32_t)(l * a.np + (l_lo + i) * BN));
+                } else {
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_b, full_bar(s), kb + k0, (int32_t)(l * a.np) + rb);
+                }
             }
         }
     } else if (warp == 1) {

@@ -424,3 +424,29 @@ def test_mc_echelon_combinations_are_bit_exact(step_dirs, p):
     assert used > 0 and rejected > 0
     eng.set_option("mc_ech", 0)
     eng.close()
+
+
+# ---- block-sparse operands: the products skip the 128 x bn blocks of A / B that hold no entry ----------------------------
+
+@pytest.mark.parametrize("p", [32003, 2147483647])
+@pytest.mark.parametrize("mode", ["panel", "block"])
+@pytest.mark.parametrize("dens", [0.004, 0.0002])
+def test_block_sparse_operands_synthetic(built, p, mode, dens):
+    """n_top >= 8192 switches the block-sparse operands on. Density 0.004: every block holds entries (full lists); 0.0002
+    (2 entries per row): a quarter of the blocks is empty. Both with the blocked solve (A and B block-sparse) and with a sparse
+    solve (B only), and the same with bsparse=0."""
+    from gamba_b200 import LinalgEngine
+    from oracle import oracle
+    s = synthetic_step(10000, 11500, dens, p, seed=31, top_frac=0.88, share=20)
+    want, fma_top, _ = oracle.reduce(s, threads=oracle.host_threads())
+    for bsp in (1, 0):
+        eng = LinalgEngine(p)
+        eng.set_option("schur_min_top", 1); eng.set_option("bsparse", bsp)
+        if mode == "panel":
+            eng.set_option("panel", 2); eng.set_option("panel_t", 512)
+        else:
+            eng.set_option("panel", 0); eng.set_option("block", 2)
+        assert eng.reduce(s).same_as(want), (p, mode, bsp, dens)
+        c = eng.counters()
+        assert c["fma_top"] == fma_top and c["solve_mode"] == (2 if mode == "panel" else 1)
+        eng.close()
