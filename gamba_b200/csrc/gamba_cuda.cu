@@ -66,23 +66,107 @@ static void* pool_alloc(size_t bytes) {
     return p;
 }
 
+// Big buffers (>= 32 MB) do not come from the pool: matrices grow from step to step, a pool block cannot be extended, and the
+// freed smaller blocks pile up (reserved memory ~2-3x the live size, then an out-of-memory trim, then everything again from the
+// driver at ~25 ms per GB: stalls of 0.2-1.4 s inside kat15-15 steps). They are virtual-memory ranges instead: a 256 GB
+// address reservation per buffer, physical memory mapped at its end as the buffer grows - contents stay, nothing is copied or
+// freed, and the driver is asked for every byte exactly once. Driver entry points through the runtime (no libcuda link).
+struct VmmApi {
+    CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+};
+static VmmApi& vmm() {
+    static VmmApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn && q == cudaDriverEntryPointSuccess;
+        };
+        api.ok = get("cuMemAddressReserve", (void**)&api.AddressReserve) && get("cuMemAddressFree", (void**)&api.AddressFree) &&
+                 get("cuMemCreate", (void**)&api.Create) && get("cuMemRelease", (void**)&api.Release) && get("cuMemMap", (void**)&api.Map) &&
+                 get("cuMemUnmap", (void**)&api.Unmap) && get("cuMemSetAccess", (void**)&api.SetAccess) &&
+                 get("cuMemGetAllocationGranularity", (void**)&api.GetGranularity);
+        if (!api.ok) cudaGetLastError();
+        if (std::getenv("GAMBA_NO_VMM")) api.ok = false;
+    }
+    return api;
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    // virtual-memory mode
+    CUdeviceptr va = 0;
+    size_t va_size = 0;
+    std::vector<CUmemGenericAllocationHandle> chunks;
+    static constexpr size_t VMM_MIN = (size_t)32 << 20, VMM_RANGE = (size_t)256 << 30;
+
+    // contents are kept when the buffer is in virtual-memory mode (va != 0), lost otherwise
     void ensure(size_t bytes) {
         if (bytes <= cap) return;
+        if ((va || bytes >= VMM_MIN) && vmm().ok && bytes <= VMM_RANGE) { grow_vmm(bytes); return; }
         release();
-        // few, generous reallocations for the small buffers; the multi-GB operands of the products grow by an eighth
-        const size_t want = bytes + std::min<size_t>(bytes / 2, std::max<size_t>(bytes / 8, (size_t)256 << 20)) + 256;
+        const size_t want = bytes + std::min<size_t>(bytes / 2, (size_t)12 << 30) + 256;     // few, generous reallocations
         p = pool_alloc(want);
         cap = want;
     }
+    void grow_vmm(size_t bytes) {
+        VmmApi& v = vmm();
+        int dev = 0;
+        GCU_CHECK(cudaGetDevice(&dev));
+        CUmemAllocationProp prop{};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = dev;
+        size_t gran = 0;
+        if (v.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !gran) gran = (size_t)2 << 20;
+        if (!va) {
+            if (p) { GCU_CHECK(cudaFreeAsync(p, g_alloc_stream)); p = nullptr; cap = 0; }      // was a small pool block: its contents go
+            if (v.AddressReserve(&va, VMM_RANGE, 0, 0, 0) != CUDA_SUCCESS) throw std::runtime_error("cuMemAddressReserve failed");
+            va_size = VMM_RANGE;
+        }
+        size_t want = bytes + std::min<size_t>(bytes / 4, (size_t)4 << 30);      // growing is cheap: little slack
+        want = std::min((want + gran - 1) / gran * gran, va_size);
+        const size_t delta = want - cap;
+        CUmemGenericAllocationHandle h{};
+        CUresult r = v.Create(&h, delta, &prop, 0);
+        if (r == CUDA_ERROR_OUT_OF_MEMORY) {        // give the pool's idle blocks back to the driver and try again
+            GCU_CHECK(cudaStreamSynchronize(g_alloc_stream));
+            GCU_CHECK(cudaMemPoolTrimTo(g_alloc_pool, 0));
+            r = v.Create(&h, delta, &prop, 0);
+        }
+        if (r != CUDA_SUCCESS) throw std::runtime_error("out of device memory growing a buffer to " + std::to_string(want >> 20) + " MiB");
+        if (v.Map(va + cap, delta, 0, h, 0) != CUDA_SUCCESS) { v.Release(h); throw std::runtime_error("cuMemMap failed"); }
+        CUmemAccessDesc acc{};
+        acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (v.SetAccess(va + cap, delta, &acc, 1) != CUDA_SUCCESS) throw std::runtime_error("cuMemSetAccess failed");
+        chunks.push_back(h);
+        cap = want; p = reinterpret_cast<void*>(va);
+    }
     void release() {
-        if (p) GCU_CHECK(cudaFreeAsync(p, g_alloc_stream));
+        if (va) {        // the owner has drained its stream (gamba_cuda_destroy)
+            VmmApi& v = vmm();
+            if (cap) v.Unmap(va, cap);
+            for (auto h : chunks) v.Release(h);
+            v.AddressFree(va, va_size);
+            chunks.clear(); va = 0; va_size = 0;
+        } else if (p) cudaFreeAsync(p, g_alloc_stream);
         p = nullptr; cap = 0;
     }
     template <class T> T* as() const { return static_cast<T*>(p); }
-    ~DevBuf() { if (p) cudaFreeAsync(p, g_alloc_stream); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
 };
 
 struct HostBuf {  // pinned
@@ -155,7 +239,8 @@ struct gamba_cuda_engine {
     int64_t opt_panel_t = 0;         // 0 = chosen per step from n_top
     int64_t opt_panel_max_top = 1000000;  // operands of K^2 / 2 bytes per limb: a cap besides the memory budget and the cost estimate
     gcu::DevBuf d_at, d_at_off, d_cd, d_cx, d_wr, d_vt, d_adt, d_gx, d_dinv;
-    gcu::DevBuf d_bs_bitmap, d_bs_rank, d_bs_base, d_bs_klist, d_bs_op;      // block-sparse operands (kernels_schur.cuh)
+    gcu::DevBuf d_bs_bitmap, d_bs_rank, d_bs_base, d_bs_klist, d_bs_op, d_bs_at;      // block-sparse operands (kernels_schur.cuh)
+    std::vector<uint32_t> bs_tile_base;   // first block id of every pivot tile
     int64_t opt_bsparse = 1;         // 1: the products skip the blocks of A / B that hold no entry
     double last_occ = 1.0;           // occupied fraction of the blocks, previous step that measured it
     double t_inv_dev = 0;            // recursive doubling of the inverse diagonal tiles (part of the elimination time)
@@ -188,7 +273,8 @@ struct gamba_cuda_engine {
                (nl * k * k * 0.5 * occ + 3.0 * nl * k * t) / 3e12 + (3.0 * k / t + 12) * 4e-6;
     }
     // sparse-blocked kernel: every block of R rows streams all of A: rows x nnz(A) row-entries at ~7e11 / s (kat15-15, K = 500 k)
-    static double model_block(double nloc, double k, double a, bool small) { return nloc * k * a / (small ? 7e11 : 4e11); }
+    // (and never faster than one CTA streaming A once: ~6e8 entries/s, whatever the number of rows)
+    static double model_block(double nloc, double k, double a, bool small) { return std::max(nloc * k * a / (small ? 7e11 : 4e11), k * a / 6e8); }
     double calib[3] = {1, 1, 1};     // measured / modelled time of the last steps in each mode (sparse, sparse-blocked, tc-solve)
     int64_t opt_panel_max_gb = 64;   // budget for the operands of the tc-solve alone (estimated with the block occupancy of the previous step)
     bool use_schur = false, use_block = false;   // decided per staged step (choose_layout)
@@ -253,7 +339,7 @@ struct gamba_cuda_engine {
         gcu::HostBuf stage;
     } rg;
     void rg_begin(uint32_t stride);
-    void rg_add_poly(uint32_t n, const uint16_t* ex, const uint32_t* hv, uint64_t* first);
+    void rg_add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex, const uint32_t* const* hv, uint64_t* first);
     void rg_add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex, const uint32_t* q_hash,
                      uint32_t* lead_out, uint32_t* n_monomials);
     void rg_fetch(uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hv_out);
@@ -328,7 +414,9 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         const double occ_ = opt_bsparse && n_top >= 8192 ? last_occ : 1.0;
         if (use_schur && !opt_mc && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
             const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T, kt_ = ntp_ * PANEL_T;
-            const double at_b = (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2) * occ_ + 3.25 * nl * (double)kt_ * PANEL_T;
+            // dense: every At_t at once; block-sparse: one pivot tile's occupied blocks at a time
+            const double at_b = (occ_ < 1.0 || (opt_bsparse && n_top >= 8192) ? (double)nl * PANEL_T * (double)kt_ * occ_ : (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2))
+                                + 3.25 * nl * (double)kt_ * PANEL_T;
             panel_fits = at_b <= (double)opt_panel_max_gb * 1e9 &&
                          at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kt_ + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9;
         }
@@ -343,10 +431,10 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
             est[2] = panel_fits && opt_panel >= 1 ? calib[2] * model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T, occ_) : 1e30;
             mode = est[1] < est[0] ? 1 : 0;
             if (est[2] < est[mode]) mode = 2;
-            if (++since_explore >= 12) {          // the runner-up, if it is within 2x
+            if (++since_explore >= 8) {           // the runner-up, if it is within 1.5x
                 since_explore = 0;
                 int second = -1;
-                for (int m = 0; m < 3; ++m) if (m != mode && est[m] < 2.0 * est[mode] && (second < 0 || est[m] < est[second])) second = m;
+                for (int m = 0; m < 3; ++m) if (m != mode && est[m] < 1.5 * est[mode] && (second < 0 || est[m] < est[second])) second = m;
                 if (second >= 0) mode = second;
             }
         }
@@ -441,12 +529,14 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
             fresh.push_back(i);
         }
         off[na] = cache_used + tot;
+        if ((cache_used + tot) * sizeof(uint32_t) > d_pool.cap && d_pool.va) d_pool.ensure((cache_used + tot) * 2 * sizeof(uint32_t));   // grows in place
         if ((cache_used + tot) * sizeof(uint32_t) > d_pool.cap) {      // grow the arena, keeping what is there
             gcu::DevBuf bigger;
             bigger.ensure((cache_used + tot) * 2 * sizeof(uint32_t));
             if (cache_used) GCU_CHECK(cudaMemcpyAsync(bigger.p, d_pool.p, cache_used * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
             GCU_CHECK(cudaStreamSynchronize(stream));
             std::swap(bigger.p, d_pool.p); std::swap(bigger.cap, d_pool.cap);
+            std::swap(bigger.va, d_pool.va); std::swap(bigger.va_size, d_pool.va_size); std::swap(bigger.chunks, d_pool.chunks);
         }
         cache_used += tot;
     } else if (have) {
@@ -667,9 +757,11 @@ void gamba_cuda_engine::eliminate() {
     // solve, of A right of a row's own tile) hold an entry at all. The products then skip the empty ones.
     const bool bs = schur && opt_bsparse && L.tile_cols % bn == 0 && L.n_top >= 8192;
     const uint32_t per_tile = bs ? L.tile_cols / bn : 0;
-    const uint32_t n_cb_piv = (bs && panel) ? ntp * per_tile : 0, n_cb = n_cb_piv + (bs ? L.n_tiles_nonpiv * per_tile : 0);
+    // the blocks of A are marked in every mode (one pass over A's entries): their occupied fraction is what the next step's
+    // choice of the solve needs
+    const uint32_t n_cb_piv = bs ? ntp * per_tile : 0, n_cb = n_cb_piv + (bs ? L.n_tiles_nonpiv * per_tile : 0);
     const uint32_t kb_words = ((L.n_top + 127u) / 128u + 31u) / 32u;
-    uint64_t nb_total = 0, nb_a = 0;
+    uint64_t nb_total = 0, nb_a = 0, bs_tile_max = 0;
     BsArgs bsa{};
     if (bs) {
         d_bs_bitmap.ensure((uint64_t)n_cb * kb_words * 4); d_bs_rank.ensure((uint64_t)n_cb * kb_words * 4); d_bs_base.ensure((uint64_t)(n_cb + 1) * 4);
@@ -677,7 +769,7 @@ void gamba_cuda_engine::eliminate() {
         GCU_CHECK(cudaMemsetAsync(d_bs_base.p, 0, (uint64_t)(n_cb + 1) * 4, stream));
         bsa.L = L; bsa.seg = d_seg.as<uint32_t>(); bsa.ent = d_ent.as<uint2>(); bsa.cbw = bn; bsa.kb_words = kb_words;
         bsa.n_cb_piv = n_cb_piv; bsa.n_cb = n_cb; bsa.bitmap = d_bs_bitmap.as<uint32_t>(); bsa.rank = d_bs_rank.as<uint32_t>();
-        bsa.blk_base = d_bs_base.as<uint32_t>(); bsa.with_a = panel ? 1u : 0u;
+        bsa.blk_base = d_bs_base.as<uint32_t>(); bsa.with_a = 1u;
         bs_mark_kernel<<<(L.n_top + 7) / 8, 256, 0, stream>>>(bsa);
         GCU_CHECK(cudaGetLastError());
         bs_rank_kernel<<<(n_cb + 7) / 8, 256, 0, stream>>>(bsa);
@@ -687,22 +779,31 @@ void gamba_cuda_engine::eliminate() {
         d_scan_tmp.ensure(tmp_bytes);
         GCU_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_tmp.p, tmp_bytes, bsa.blk_base, bsa.blk_base, (int64_t)(n_cb + 1), stream));
         uint32_t cnt[2] = {0, 0};
+        bs_tile_base.assign(ntp + 1, 0);
         GCU_CHECK(cudaMemcpyAsync(&cnt[0], bsa.blk_base + n_cb, 4, cudaMemcpyDeviceToHost, stream));
         GCU_CHECK(cudaMemcpyAsync(&cnt[1], bsa.blk_base + n_cb_piv, 4, cudaMemcpyDeviceToHost, stream));
+        if (panel)      // first block of every pivot tile: the operand of the earlier-tile product is built one tile at a time
+            GCU_CHECK(cudaMemcpy2DAsync(bs_tile_base.data(), 4, bsa.blk_base, (size_t)per_tile * 4, 4, ntp + 1, cudaMemcpyDeviceToHost, stream));
         GCU_CHECK(cudaStreamSynchronize(stream));
         nb_total = cnt[0]; nb_a = cnt[1];
+        for (uint32_t t = 0; t < ntp && panel; ++t) bs_tile_max = std::max<uint64_t>(bs_tile_max, bs_tile_base[t + 1] - bs_tile_base[t]);
         ctr.kernel_launches += 3;
         const double tri_cells = (double)n_cb_piv * ((L.n_top + 127u) / 128u) * 0.5, b_cells = (double)(n_cb - n_cb_piv) * ((L.n_top + 127u) / 128u);
-        last_occ = panel && tri_cells > 0 ? (double)nb_a / tri_cells : (b_cells > 0 ? (double)(nb_total - nb_a) / b_cells : 1.0);
+        last_occ = tri_cells > 0 ? (double)nb_a / tri_cells : (b_cells > 0 ? (double)(nb_total - nb_a) / b_cells : 1.0);
         last_occ = std::min(1.0, std::max(0.01, last_occ));
         // blocked solve whose operands do not fit after all: the sparse kernel for blocks of rows on the same layout
-        if (panel && (double)nl * nb_total * bn * 128.0 > (double)opt_schur_max_gb * 1e9) { panel = false; block = true; use_panel = false; use_block = true; }
+        if (panel && (double)nl * (nb_total - nb_a + bs_tile_max) * bn * 128.0 > (double)opt_schur_max_gb * 1e9) { panel = false; block = true; use_panel = false; use_block = true; }
     }
-    const uint64_t bs_plane = nb_total * bn * 128ull;
+    const uint64_t bs_plane = (nb_total - nb_a) * bn * 128ull;          // B alone: the blocks of A are built one pivot tile at a time
+    const uint64_t bs_at_plane = std::max<uint64_t>(bs_tile_max, 1) * bn * 128ull;
+    OpArgs oa_at{};
+    void (*opk)(OpArgs) = nullptr;
+    size_t op_sm = 0;
+    uint32_t chunks = 0;
     // buffers: growing one may go to the driver
     if (schur) {
         d_mx.ensure(nl * mx_plane);
-        if (bs) { d_bs_op.ensure(std::max<uint64_t>(nl * bs_plane, 16)); d_bs_klist.ensure(std::max<uint64_t>(nb_total, 1) * 4); }
+        if (bs) { d_bs_op.ensure(std::max<uint64_t>(nl * bs_plane, 16)); d_bs_klist.ensure(std::max<uint64_t>(nb_total, 1) * 4); if (panel) d_bs_at.ensure(nl * bs_at_plane); }
         else d_bt.ensure(nl * bt_plane);
         if (panel) {     // operands of the products with the earlier tiles: tile t takes [nl][T][t * T] bytes
             if (!bs) {
@@ -725,28 +826,24 @@ void gamba_cuda_engine::eliminate() {
         ea.mx = d_mx.as<uint8_t>(); ea.mx_plane = mx_plane; ea.mx_kp = kp; ea.mx_nl = nl;
         OpArgs oa{};
         oa.L = L; oa.seg = d_seg.as<uint32_t>(); oa.ent = d_ent.as<uint2>();
-        auto opk = f.small ? operand_build_kernel<2> : operand_build_kernel<4>;
-        const size_t op_sm = f.small ? op_smem<2>() : op_smem<4>();
+        opk = f.small ? operand_build_kernel<2> : operand_build_kernel<4>;
+        op_sm = f.small ? op_smem<2>() : op_smem<4>();
         const uint32_t och = f.small ? op_ch<2>() : op_ch<4>();
         GCU_CHECK(cudaFuncSetAttribute(opk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op_sm));
-        const uint32_t chunks = (L.tile_cols + och - 1) / och;
+        chunks = (L.tile_cols + och - 1) / och;
         if (bs) {
             bsa.klist = d_bs_klist.as<uint32_t>();
             bs_list_kernel<<<(n_cb + 7) / 8, 256, 0, stream>>>(bsa);
             GCU_CHECK(cudaGetLastError());
             oa.bitmap = bsa.bitmap; oa.rank = bsa.rank; oa.blk_base = bsa.blk_base; oa.kb_words = kb_words; oa.cbw = bn; oa.n_cb_piv = n_cb_piv;
             oa.out = d_bs_op.as<uint8_t>(); oa.plane = bs_plane; oa.rows = 0xffffffffu; oa.pitch = 0;
-            oa.mode = OP_B;
+            oa.mode = OP_B; oa.id0 = (uint32_t)nb_a;
             opk<<<dim3(kp / OP_KB, chunks, L.n_tiles_nonpiv), 256, op_sm, stream>>>(oa);
             GCU_CHECK(cudaGetLastError());
             ctr.kernel_launches += 2;
-            if (panel && ntp > 1) {
-                oa.mode = OP_AT;
-                opk<<<dim3((ntp - 1) * (T / OP_KB), chunks, ntp), 256, op_sm, stream>>>(oa);
-                GCU_CHECK(cudaGetLastError());
-                ctr.kernel_launches += 1;
-            }
-            oa.bitmap = nullptr;
+            oa_at = oa;                 // the blocks of A: per pivot tile, inside the tile loop
+            oa_at.mode = OP_AT; oa_at.out = d_bs_at.as<uint8_t>(); oa_at.plane = bs_at_plane;
+            oa.bitmap = nullptr; oa.id0 = 0;
         } else {
             oa.mode = OP_B; oa.out = d_bt.as<uint8_t>(); oa.plane = bt_plane; oa.pitch = kp; oa.rows = np;
             if ((uint64_t)L.n_tiles_nonpiv * L.tile_cols < np)        // padding rows beyond the last tile (tile width not a multiple of 128)
@@ -814,7 +911,7 @@ void gamba_cuda_engine::eliminate() {
         // 2. tile by tile: cd = C_t + M[:, < tT] A[< tT, tile t], then M[:, tile t] = -cd Inv_t
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
         const CUtensorMap map_cx = make_tmap_u8(d_cx.p, T, (uint64_t)nl * mp, TC_BK, TC_BM);
-        const CUtensorMap map_bs = bs && nb_total ? make_tmap_u8(d_bs_op.p, TC_BK, (uint64_t)nl * nb_total * bn, TC_BK, bn) : map_cx;
+        const CUtensorMap map_bs = bs ? make_tmap_u8(d_bs_at.p, TC_BK, (uint64_t)nl * (bs_at_plane / 128), TC_BK, bn) : map_cx;
         TriRowsArgs ra{};
         ra.L = L; ra.seg = d_seg.as<uint32_t>(); ra.ent = d_ent.as<uint2>(); ra.row_begin = rank; ra.row_step = world; ra.n_local = n_local;
         for (uint32_t t = 0; t < ntp; ++t) {
@@ -828,7 +925,16 @@ void gamba_cuda_engine::eliminate() {
             ta.first_piv = d_first.as<uint32_t>(); ta.row_begin = rank; ta.row_step = world;
             ta.kchunk = kchunk; ta.k_end = t * T;
             ta.o1 = d_cx.as<uint8_t>(); ta.o1_plane = (uint64_t)mp * T; ta.o1_ld = T;
-            if (bs) { ta.np = (uint32_t)(nb_total * bn); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>(); ta.kl_cb0 = t * per_tile; }
+            if (bs) {
+                if (t) {      // the occupied blocks of A[< tT, tile t], block-compressed, into the one-tile buffer
+                    oa_at.z0 = t; oa_at.id0 = bs_tile_base[t];
+                    opk<<<dim3(t * (T / OP_KB), chunks, 1), 256, op_sm, stream>>>(oa_at);
+                    GCU_CHECK(cudaGetLastError());
+                    ctr.kernel_launches += 1;
+                }
+                ta.np = (uint32_t)(bs_at_plane / 128); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>();
+                ta.kl_cb0 = t * per_tile; ta.kl_id0 = bs_tile_base[t];
+            }
             const CUtensorMap map_at = bs ? map_bs : t ? make_tmap_u8(d_at.as<uint8_t>() + at_off[t], (uint64_t)t * T, (uint64_t)nl * T, TC_BK, bn) : map_vt;
             launch_limb_gemm<EPI_RMW_LIMBS>(f.small != 0, map_mx, map_at, ta, 1, stream);
             TcArgs xa{};
@@ -886,8 +992,8 @@ void gamba_cuda_engine::eliminate() {
         ta.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); ta.k_first = ea.mc_first; ta.row_begin = rank; ta.row_step = world;
         ta.kchunk = kchunk; ta.k_end = k_used;
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
-        if (bs) { ta.np = (uint32_t)(nb_total * bn); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>(); ta.kl_cb0 = n_cb_piv; }
-        const CUtensorMap map_bt = bs ? (nb_total ? make_tmap_u8(d_bs_op.p, TC_BK, (uint64_t)nl * nb_total * bn, TC_BK, bn) : map_mx)
+        if (bs) { ta.np = (uint32_t)(bs_plane / 128); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>(); ta.kl_cb0 = n_cb_piv; ta.kl_id0 = (uint32_t)nb_a; }
+        const CUtensorMap map_bt = bs ? (bs_plane ? make_tmap_u8(d_bs_op.p, TC_BK, (uint64_t)nl * (bs_plane / 128), TC_BK, bn) : map_mx)
                                       : make_tmap_u8(d_bt.p, kp, (uint64_t)nl * np, TC_BK, bn);
         launch_limb_gemm<EPI_RMW>(f.small != 0, map_mx, map_bt, ta, 1, stream);
         ctr.kernel_launches += 1;
@@ -1142,10 +1248,12 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
 // grow a device buffer keeping its first `used` bytes
 static void grow_keep(gcu::DevBuf& b, size_t used, size_t want, cudaStream_t st) {
     if (want <= b.cap) return;
+    if (b.va) { b.ensure(want); return; }          // virtual-memory mode: grows in place
     gcu::DevBuf bigger;
     bigger.ensure(std::max(want, b.cap * 2));
     if (used) GCU_CHECK(cudaMemcpyAsync(bigger.p, b.p, used, cudaMemcpyDeviceToDevice, st));
     std::swap(bigger.p, b.p); std::swap(bigger.cap, b.cap);      // the old block goes back to the pool, ordered on the stream
+    std::swap(bigger.va, b.va); std::swap(bigger.va_size, b.va_size); std::swap(bigger.chunks, b.chunks);
 }
 
 void gamba_cuda_engine::rg_begin(uint32_t stride) {
@@ -1157,23 +1265,31 @@ void gamba_cuda_engine::rg_begin(uint32_t stride) {
     if (rg.n_slots) GCU_CHECK(cudaMemsetAsync(rg.slots.p, 0, (size_t)rg.n_slots * sizeof(uint32_t), stream));
 }
 
-void gamba_cuda_engine::rg_add_poly(uint32_t n, const uint16_t* ex, const uint32_t* hv, uint64_t* first) {
+// n_polys polynomials in one upload: poly i has n_terms[i] terms at ex[i] / hv[i]; first[i] = where it starts in the term store
+void gamba_cuda_engine::rg_add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex, const uint32_t* const* hv, uint64_t* first) {
     if (!rg.sd) throw std::runtime_error("rowgen: begin has not been called");
     const uint32_t sd = rg.sd, st = rg.stride;
+    uint64_t n = 0;
+    for (uint32_t i = 0; i < n_polys; ++i) { first[i] = rg.terms + n; n += n_terms[i]; }
+    if (!n) return;
     grow_keep(rg.pex, rg.terms * sd * sizeof(uint16_t), (rg.terms + n) * sd * sizeof(uint16_t), stream);
     grow_keep(rg.phv, rg.terms * sizeof(uint32_t), (rg.terms + n) * sizeof(uint32_t), stream);
     const size_t bytes_ex = (size_t)n * sd * sizeof(uint16_t), bytes_hv = (size_t)n * sizeof(uint32_t);
     GCU_CHECK(cudaStreamSynchronize(stream));            // the staging buffer may still be the source of the previous upload
     rg.stage.ensure(bytes_ex + bytes_hv);
     uint16_t* se = rg.stage.as<uint16_t>();
-    for (uint32_t k = 0; k < n; ++k) {
-        std::memcpy(se + (size_t)k * sd, ex + (size_t)k * st, st * sizeof(uint16_t));
-        if (sd != st) se[(size_t)k * sd + st] = 0;
+    uint32_t* sh = reinterpret_cast<uint32_t*>(rg.stage.as<char>() + bytes_ex);
+    uint64_t o = 0;
+    for (uint32_t i = 0; i < n_polys; ++i) {
+        for (uint32_t k = 0; k < n_terms[i]; ++k) {
+            std::memcpy(se + (o + k) * sd, ex[i] + (size_t)k * st, st * sizeof(uint16_t));
+            if (sd != st) se[(o + k) * sd + st] = 0;
+        }
+        std::memcpy(sh + o, hv[i], (size_t)n_terms[i] * sizeof(uint32_t));
+        o += n_terms[i];
     }
-    std::memcpy(rg.stage.as<char>() + bytes_ex, hv, bytes_hv);
     GCU_CHECK(cudaMemcpyAsync(rg.pex.as<uint16_t>() + rg.terms * sd, se, bytes_ex, cudaMemcpyHostToDevice, stream));
-    GCU_CHECK(cudaMemcpyAsync(rg.phv.as<uint32_t>() + rg.terms, rg.stage.as<char>() + bytes_ex, bytes_hv, cudaMemcpyHostToDevice, stream));
-    *first = rg.terms;
+    GCU_CHECK(cudaMemcpyAsync(rg.phv.as<uint32_t>() + rg.terms, sh, bytes_hv, cudaMemcpyHostToDevice, stream));
     rg.terms += n;
 }
 
@@ -1315,12 +1431,13 @@ int gamba_cuda_create(const gamba_cuda_config* cfg, gamba_cuda_engine** out) {
             GCU_CHECK(cudaMemPoolSetAttribute(e->pool, cudaMemPoolAttrReleaseThreshold, &keep));
             // Put some memory into the engine's pool up front (one allocation, released straight back to the pool): the first steps
             // of a run then grow their buffers without a trip to the driver each time (1 s of a 3 s cyclic9-15 run otherwise).
-            // GAMBA_POOL_PREWARM_GB (default 6, capped at a quarter of the free memory; 0 = off). The pool dies with the engine.
+            // GAMBA_POOL_PREWARM_GB (default 1 - the big buffers are virtual-memory ranges, not pool blocks; capped at a quarter of
+            // the free memory; 0 = off). The pool dies with the engine.
             {
                 size_t free_b = 0, total_b = 0;
                 GCU_CHECK(cudaMemGetInfo(&free_b, &total_b));
                 const char* pw = std::getenv("GAMBA_POOL_PREWARM_GB");
-                const double want_gb = pw ? std::atof(pw) : 6.0;
+                const double want_gb = pw ? std::atof(pw) : 1.0;
                 const size_t want = (size_t)std::min<double>(want_gb * 1e9, (double)free_b / 4);
                 if (want > ((size_t)64 << 20)) {
                     void* warm = nullptr;
@@ -1341,6 +1458,7 @@ void gamba_cuda_destroy(gamba_cuda_engine* e) {
     cudaSetDevice((int)e->cfg.device);
     gcu::g_alloc_stream = e->stream; gcu::g_alloc_pool = e->pool;       // the buffers go back to the engine's pool, then the pool goes
     const cudaStream_t st = e->stream; const cudaMemPool_t pl = e->pool;
+    if (st) cudaStreamSynchronize(st);                                      // mapped ranges are unmapped by the buffers' destructors
     delete e;
     gamba_cuda_engine::release_device(st, pl);
 }
@@ -1391,7 +1509,11 @@ int gamba_cuda_rowgen_begin(gamba_cuda_engine* e, uint32_t stride) {
     return guarded([&] { GCU_ENTER(e); e->rg_begin(stride); });
 }
 int gamba_cuda_rowgen_add_poly(gamba_cuda_engine* e, uint32_t n_terms, const uint16_t* ex, const uint32_t* hash, uint64_t* first_term) {
-    return guarded([&] { GCU_ENTER(e); e->rg_add_poly(n_terms, ex, hash, first_term); });
+    return guarded([&] { GCU_ENTER(e); e->rg_add_polys(1, &n_terms, &ex, &hash, first_term); });
+}
+int gamba_cuda_rowgen_add_polys(gamba_cuda_engine* e, uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex,
+                                const uint32_t* const* hash, uint64_t* first_term) {
+    return guarded([&] { GCU_ENTER(e); e->rg_add_polys(n_polys, n_terms, ex, hash, first_term); });
 }
 int gamba_cuda_rowgen_add_rows(gamba_cuda_engine* e, uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms,
                                const uint16_t* q_ex, const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials) {

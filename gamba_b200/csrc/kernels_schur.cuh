@@ -58,6 +58,8 @@ struct OpArgs {
     const uint32_t* rank;
     const uint32_t* blk_base;
     uint32_t kb_words, cbw, n_cb_piv;
+    uint32_t z0;                // added to blockIdx.z (OP_AT for one pivot tile at a time)
+    uint32_t id0;               // block-sparse: block ids are stored relative to this one (the operand of ONE pivot tile, or of B alone)
 };
 
 // ---- block-sparse operands ------------------------------------------------------------------------------------------
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(256) operand_build_kernel(OpArgs a) {
     const Layout& L = a.L;
     const uint32_t tid = threadIdx.x;
     const uint32_t T = L.tile_cols, nr = L.n_rows;
-    const uint32_t kb = blockIdx.x, cc = blockIdx.y, z = blockIdx.z;
+    const uint32_t kb = blockIdx.x, cc = blockIdx.y, z = blockIdx.z + a.z0;
     uint32_t tc, k0, orow0, okoff, pitch, rows;
     uint64_t plane;
     uint8_t* out = a.out;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(256) operand_build_kernel(OpArgs a) {
             if (sub * a.cbw < cw) {
                 const uint32_t cb = (a.mode == OP_B ? a.n_cb_piv + z * (T / a.cbw) : z * (T / a.cbw)) + c_lo / a.cbw + sub;
                 const uint32_t w = a.bitmap[(uint64_t)cb * a.kb_words + (kb >> 5)], bit = kb & 31u;
-                if ((w >> bit) & 1u) id = a.blk_base[cb] + a.rank[(uint64_t)cb * a.kb_words + (kb >> 5)] + __popc(w & ((1u << bit) - 1u));
+                if ((w >> bit) & 1u) id = a.blk_base[cb] + a.rank[(uint64_t)cb * a.kb_words + (kb >> 5)] + __popc(w & ((1u << bit) - 1u)) - a.id0;
             }
             s_blk[sub] = id;
         }

@@ -73,6 +73,7 @@ struct TcArgs {
     const uint32_t* klist;      // NULL: dense operand, k-steps ks_begin .. ks_end
     const uint32_t* kl_base;
     uint32_t kl_cb0;
+    uint32_t kl_id0;            // block ids in the operand are relative to this one
     uint32_t neg;               // EPI_LIMBS: store (p - x) mod p
     // EPI_LIMBS: count the non-zero outputs (row < n_rows, col < n_cols): stats[0] += 1, stats[2] += len[col0 + col]
     const uint64_t* cnt_row_ptr; unsigned long long* stats;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
                 for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + l * A_LIMB, &map_a, full_bar(s), ka + k0, (int32_t)(l * a.mp) + ra);
                 if (a.klist) {
 #pragma unroll
-                    for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_b, full_bar(s), 0, (int32_t)(l * a.np + (l_lo + i) * BN));
+                    for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_b, full_bar(s), 0, (int32_t)(l * a.np + (l_lo + i - a.kl_id0) * BN));
                 } else {
 #pragma unroll
                     for (int l = 0; l < NL; ++l) tc_tma_load_2d(dst + NL * A_LIMB + l * B_LIMB, &map_b, full_bar(s), kb + k0, (int32_t)(l * a.np) + rb);

@@ -277,11 +277,19 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
         double tA = now_s();
         std::vector<uint64_t> first(nb);
         std::vector<uint32_t> nt(nb);
-        for (size_t i = 0; i < nb; ++i) {
-            Poly& f = G_[gens[i]];
-            if (f.dev_first == ~0ull) f.dev_first = rg_->add_poly((uint32_t)f.mon.size(), f.ex.data(), f.hv.data());
-            first[i] = f.dev_first; nt[i] = (uint32_t)f.mon.size();
+        {   // polynomials not yet in the device's term store: one upload for all of them
+            std::vector<uint32_t> ug, un; std::vector<const uint16_t*> uex; std::vector<const uint32_t*> uhv;
+            for (size_t i = 0; i < nb; ++i) {
+                Poly& f = G_[gens[i]];
+                if (f.dev_first == ~0ull) { f.dev_first = ~0ull - 1; ug.push_back(gens[i]); un.push_back((uint32_t)f.mon.size()); uex.push_back(f.ex.data()); uhv.push_back(f.hv.data()); }
+            }
+            if (!ug.empty()) {
+                std::vector<uint64_t> uf(ug.size());
+                rg_->add_polys((uint32_t)ug.size(), un.data(), uex.data(), uhv.data(), uf.data());
+                for (size_t k = 0; k < ug.size(); ++k) G_[ug[k]].dev_first = uf[k];
+            }
         }
+        for (size_t i = 0; i < nb; ++i) { const Poly& f = G_[gens[i]]; first[i] = f.dev_first; nt[i] = (uint32_t)f.mon.size(); }
         const uint32_t before = st_.n;
         const uint32_t after = rg_->add_rows((uint32_t)nb, first.data(), nt.data(), qs.data(), hqs.data(), &row_lead_[r0]);
         if (after > before) {

@@ -204,6 +204,9 @@ int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
      rowgen_download_rows     copy a range of the handle array to the host (dumps, debugging)                                    */
 int gamba_cuda_rowgen_begin(gamba_cuda_engine* e, uint32_t stride);
 int gamba_cuda_rowgen_add_poly(gamba_cuda_engine* e, uint32_t n_terms, const uint16_t* ex, const uint32_t* hash, uint64_t* first_term);
+/* the same for n_polys polynomials in one upload (one synchronisation instead of one per polynomial) */
+int gamba_cuda_rowgen_add_polys(gamba_cuda_engine* e, uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex,
+                                const uint32_t* const* hash, uint64_t* first_term);
 int gamba_cuda_rowgen_add_rows(gamba_cuda_engine* e, uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms,
                                const uint16_t* q_ex, const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials);
 int gamba_cuda_rowgen_fetch_monomials(gamba_cuda_engine* e, uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hash_out);
