@@ -5,7 +5,7 @@ eco12-15.txt ...). Those files do not exist on the GPU box, and the systems are
 standard families, so they are re-created here from their definitions, with the
 variable names of the reference's files (the reduced Groebner basis — and hence
 the `-o` file — depends only on the ideal, the variable order and p).
-`tests/test_systems.py` checks the generated text against the committed goldens.
+`tests/test_systems_cpu.py` checks the generated text against the committed golden inputs (same polynomials).
 """
 from __future__ import annotations
 
