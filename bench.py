@@ -321,6 +321,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # end-to-end seconds of the product binary first, while this process holds neither the workload nor a CUDA context
+    # (measured after the timed legs the same runs took twice as long: the host phases of the driver are memory-bound)
+    e2e_s = None
+    if world == 1 and rank == 0 and not args.no_e2e_seconds and not args.systems.startswith("synthetic:"):
+        e2e_s = e2e_seconds([(n, sp, None) for n, sp, _ in parse_systems(args.systems)])
     groups, wl_desc = load_workload(args, rank, world)
     total_nnz = sum(s.nnz for _, _, steps in groups for s in steps)
     n_mat = sum(len(steps) for _, _, steps in groups)
@@ -517,8 +522,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                       "eliminate_without_operands": 1e3 * float(np.sum(elim - opnd)), "echelon": 1e3 * float(np.sum(ech)),
                                       "device_total": 1e3 * float(np.sum(dev))},
         }
-        if world == 1 and not args.no_e2e_seconds:
-            out["e2e_seconds"] = e2e_seconds(groups)
+        if e2e_s is not None:
+            out["e2e_seconds"] = e2e_s
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(groups, args)
         print(json.dumps(out), flush=True)
