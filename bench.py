@@ -456,6 +456,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.empty_cache()
     keys = sorted(per)
     vals = np.array([per[k] for k in keys], dtype=np.float64)
+    if rank == 0 and os.environ.get("GAMBA_BENCH_VERBOSE"):
+        for (gi, si), v in zip(keys, vals):
+            st = groups[gi][2][si]
+            if st.nnz >= 20_000_000:
+                log(f"{groups[gi][0]}[{si}] {st.n_rows}x{st.n_cols} n_bot={st.n_bot}: mode {int(v[6])} eliminate {1e3 * v[0]:.1f} ms (operands {1e3 * v[5]:.1f}) echelon {1e3 * v[1]:.1f} ms")
     if world > 1:
         import torch.distributed as dist
         tt = torch.tensor([t_res, t_e2e], device="cuda", dtype=torch.float64)

@@ -51,7 +51,7 @@ BROADCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
 SYMBOLS = ["gamba_cuda_abi_version", "gamba_cuda_last_error", "gamba_cuda_create", "gamba_cuda_destroy",
            "gamba_cuda_reduce", "gamba_cuda_stage", "gamba_cuda_reduce_staged", "gamba_cuda_set_allgather", "gamba_cuda_set_broadcast", "gamba_cuda_host_alloc", "gamba_cuda_host_free",
            "gamba_cuda_get_counters", "gamba_cuda_set_option", "gamba_cuda_measure_int8_peak",
-           "gamba_cuda_rowgen_begin", "gamba_cuda_rowgen_add_poly", "gamba_cuda_rowgen_add_polys", "gamba_cuda_rowgen_add_rows", "gamba_cuda_rowgen_fetch_monomials",
+           "gamba_cuda_rowgen_begin", "gamba_cuda_rowgen_add_monomials", "gamba_cuda_rowgen_add_polys", "gamba_cuda_rowgen_add_rows", "gamba_cuda_rowgen_fetch_monomials",
            "gamba_cuda_rowgen_rows", "gamba_cuda_rowgen_download_rows"]
 
 _lib = None
@@ -79,7 +79,8 @@ def load() -> C.CDLL:
     lib.gamba_cuda_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     lib.gamba_cuda_measure_int8_peak.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     lib.gamba_cuda_rowgen_begin.argtypes = [C.c_void_p, C.c_uint32]
-    lib.gamba_cuda_rowgen_add_poly.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.gamba_cuda_rowgen_add_monomials.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.gamba_cuda_rowgen_add_polys.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gamba_cuda_rowgen_add_rows.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
     lib.gamba_cuda_rowgen_fetch_monomials.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.gamba_cuda_rowgen_rows.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]

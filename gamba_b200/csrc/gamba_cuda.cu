@@ -329,7 +329,9 @@ struct gamba_cuda_engine {
     // row generation of symbolic preprocessing (kernels_rowgen.cuh)
     struct RowGenState {
         uint32_t stride = 0, sd = 0;
-        gcu::DevBuf pex, phv;              // term store of the basis polynomials (append-only across steps)
+        gcu::DevBuf bex, bhv;              // the driver's basis monomials (exponents, hashes), appended as its table grows
+        uint64_t n_basis = 0;
+        gcu::DevBuf pmon;                  // term store of the basis polynomials: basis-monomial handles (append-only across steps)
         uint64_t terms = 0;
         gcu::DevBuf slots, hv, ex;         // the step's monomial table
         uint32_t n_slots = 0, cap = 0, count = 0;
@@ -339,7 +341,8 @@ struct gamba_cuda_engine {
         gcu::HostBuf stage;
     } rg;
     void rg_begin(uint32_t stride);
-    void rg_add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex, const uint32_t* const* hv, uint64_t* first);
+    void rg_add_monomials(uint32_t count, const uint16_t* ex, const uint32_t* hv, uint64_t* first);
+    void rg_add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint32_t* const* mon, uint64_t* first);
     void rg_add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex, const uint32_t* q_hash,
                      uint32_t* lead_out, uint32_t* n_monomials);
     void rg_fetch(uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hv_out);
@@ -1162,14 +1165,15 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
         last_density = (double)ctr.pivots_applied / ((double)n_local * L.n_top); last_a = cur_a; have_history = true;
         if (use_schur && !use_block && !use_panel && last_a > 0 && ctr.pivots_applied > 1000)      // the sparse kernel ran: its real work
             hitw = std::min(16.0, std::max(0.25, (double)ctr.fma_applied / ((double)ctr.pivots_applied * last_a * 0.5)));
-        if (use_schur && L.n_top >= 4096 && n_local >= 64 && t_sparse_dev > 2e-4) {       // calibrate the model of the mode that ran
+        if (use_schur && L.n_top >= 32768 && n_local >= 64 && t_sparse_dev > 5e-3) {      // calibrate the model of the mode that ran (steps big enough
+                                                                                           // for the model's terms, not its fixed costs, to matter)
             const uint32_t nl_ = f.small ? 2u : 4u;
             const double mpad = (double)((n_local + 127u) / 128u * 128u);
             const int m = use_panel ? 2 : use_block ? 1 : 0;
             const double model = m == 2 ? model_panel(mpad, L.n_top, nl_, PANEL_T, opt_bsparse && L.n_top >= 8192 ? last_occ : 1.0)
                                : m == 1 ? model_block(n_local, L.n_top, cur_a, f.small != 0)
                                         : hitw * model_sparse(n_local, last_density, L.n_top, cur_a, f.small != 0);
-            if (model > 0) calib[m] = std::min(5.0, std::max(0.2, 0.5 * calib[m] + 0.5 * t_sparse_dev / model));
+            if (model > 0) calib[m] = std::min(3.0, std::max(0.33, 0.5 * calib[m] + 0.5 * t_sparse_dev / model));
         }
     }
     ctr.steps += 1;
@@ -1258,38 +1262,53 @@ static void grow_keep(gcu::DevBuf& b, size_t used, size_t want, cudaStream_t st)
 
 void gamba_cuda_engine::rg_begin(uint32_t stride) {
     if (stride == 0 || ((stride + 1u) & ~1u) > (uint32_t)RG_MAX_SD) throw std::runtime_error("rowgen: unsupported exponent-vector stride");
-    if (stride != rg.stride) { rg.stride = stride; rg.sd = (stride + 1u) & ~1u; rg.terms = 0; }
+    if (stride != rg.stride) { rg.stride = stride; rg.sd = (stride + 1u) & ~1u; rg.terms = 0; rg.n_basis = 0; }
     rg.count = 0; rg.n_rows_entries = 0;
     rg.cnt.ensure(16);
     GCU_CHECK(cudaMemsetAsync(rg.cnt.p, 0, 16, stream));
     if (rg.n_slots) GCU_CHECK(cudaMemsetAsync(rg.slots.p, 0, (size_t)rg.n_slots * sizeof(uint32_t), stream));
 }
 
-// n_polys polynomials in one upload: poly i has n_terms[i] terms at ex[i] / hv[i]; first[i] = where it starts in the term store
-void gamba_cuda_engine::rg_add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex, const uint32_t* const* hv, uint64_t* first) {
+// append `count` monomials of the driver's basis table (ex: [count][stride], hv: hashes); *first = index of the first one
+void gamba_cuda_engine::rg_add_monomials(uint32_t count, const uint16_t* ex, const uint32_t* hv, uint64_t* first) {
     if (!rg.sd) throw std::runtime_error("rowgen: begin has not been called");
     const uint32_t sd = rg.sd, st = rg.stride;
+    *first = rg.n_basis;
+    if (!count) return;
+    grow_keep(rg.bex, rg.n_basis * sd * sizeof(uint16_t), (rg.n_basis + count) * sd * sizeof(uint16_t), stream);
+    grow_keep(rg.bhv, rg.n_basis * sizeof(uint32_t), (rg.n_basis + count) * sizeof(uint32_t), stream);
+    if (sd == st) {
+        GCU_CHECK(cudaMemcpyAsync(rg.bex.as<uint16_t>() + rg.n_basis * sd, ex, (size_t)count * sd * sizeof(uint16_t), cudaMemcpyHostToDevice, stream));
+    } else {
+        const size_t bytes = (size_t)count * sd * sizeof(uint16_t);
+        GCU_CHECK(cudaStreamSynchronize(stream));            // the staging buffer may still be the source of the previous upload
+        rg.stage.ensure(bytes);
+        uint16_t* se = rg.stage.as<uint16_t>();
+        for (uint32_t k = 0; k < count; ++k) { std::memcpy(se + (size_t)k * sd, ex + (size_t)k * st, st * sizeof(uint16_t)); se[(size_t)k * sd + st] = 0; }
+        GCU_CHECK(cudaMemcpyAsync(rg.bex.as<uint16_t>() + rg.n_basis * sd, se, bytes, cudaMemcpyHostToDevice, stream));
+    }
+    GCU_CHECK(cudaMemcpyAsync(rg.bhv.as<uint32_t>() + rg.n_basis, hv, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaStreamSynchronize(stream));                // the caller's arrays may move (its table grows)
+    rg.n_basis += count;
+}
+
+// n_polys polynomials in one upload: poly i = n_terms[i] basis-monomial handles at mon[i]; first[i] = where it starts in the term store
+void gamba_cuda_engine::rg_add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint32_t* const* mon, uint64_t* first) {
+    if (!rg.sd) throw std::runtime_error("rowgen: begin has not been called");
     uint64_t n = 0;
     for (uint32_t i = 0; i < n_polys; ++i) { first[i] = rg.terms + n; n += n_terms[i]; }
     if (!n) return;
-    grow_keep(rg.pex, rg.terms * sd * sizeof(uint16_t), (rg.terms + n) * sd * sizeof(uint16_t), stream);
-    grow_keep(rg.phv, rg.terms * sizeof(uint32_t), (rg.terms + n) * sizeof(uint32_t), stream);
-    const size_t bytes_ex = (size_t)n * sd * sizeof(uint16_t), bytes_hv = (size_t)n * sizeof(uint32_t);
+    grow_keep(rg.pmon, rg.terms * sizeof(uint32_t), (rg.terms + n) * sizeof(uint32_t), stream);
     GCU_CHECK(cudaStreamSynchronize(stream));            // the staging buffer may still be the source of the previous upload
-    rg.stage.ensure(bytes_ex + bytes_hv);
-    uint16_t* se = rg.stage.as<uint16_t>();
-    uint32_t* sh = reinterpret_cast<uint32_t*>(rg.stage.as<char>() + bytes_ex);
+    rg.stage.ensure(n * sizeof(uint32_t));
+    uint32_t* sm = rg.stage.as<uint32_t>();
     uint64_t o = 0;
     for (uint32_t i = 0; i < n_polys; ++i) {
-        for (uint32_t k = 0; k < n_terms[i]; ++k) {
-            std::memcpy(se + (o + k) * sd, ex[i] + (size_t)k * st, st * sizeof(uint16_t));
-            if (sd != st) se[(o + k) * sd + st] = 0;
-        }
-        std::memcpy(sh + o, hv[i], (size_t)n_terms[i] * sizeof(uint32_t));
+        for (uint32_t k = 0; k < n_terms[i]; ++k) if (mon[i][k] >= rg.n_basis) throw std::runtime_error("rowgen: polynomial names a monomial that was not uploaded");
+        std::memcpy(sm + o, mon[i], (size_t)n_terms[i] * sizeof(uint32_t));
         o += n_terms[i];
     }
-    GCU_CHECK(cudaMemcpyAsync(rg.pex.as<uint16_t>() + rg.terms * sd, se, bytes_ex, cudaMemcpyHostToDevice, stream));
-    GCU_CHECK(cudaMemcpyAsync(rg.phv.as<uint32_t>() + rg.terms, sh, bytes_hv, cudaMemcpyHostToDevice, stream));
+    GCU_CHECK(cudaMemcpyAsync(rg.pmon.as<uint32_t>() + rg.terms, sm, n * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     rg.terms += n;
 }
 
@@ -1346,7 +1365,7 @@ void gamba_cuda_engine::rg_add_rows(uint32_t n_rows, const uint64_t* first_term,
         GCU_CHECK(cudaMemcpyAsync(rg.b_first.p, sb, o_end, cudaMemcpyHostToDevice, stream));
         rg.b_lead.ensure((size_t)nb * 4);
         RowGenArgs a{};
-        a.sd = sd; a.pex = rg.pex.as<uint16_t>(); a.phv = rg.phv.as<uint32_t>(); a.n_rows = nb;
+        a.sd = sd; a.bex = rg.bex.as<uint16_t>(); a.bhv = rg.bhv.as<uint32_t>(); a.pmon = rg.pmon.as<uint32_t>(); a.n_rows = nb;
         a.first_term = reinterpret_cast<const uint64_t*>(rg.b_first.as<char>() + o_first);
         a.row_off = reinterpret_cast<const uint64_t*>(rg.b_first.as<char>() + o_off);
         a.q = reinterpret_cast<const uint16_t*>(rg.b_first.as<char>() + o_q);
@@ -1508,12 +1527,11 @@ int gamba_cuda_set_broadcast(gamba_cuda_engine* e, gamba_cuda_broadcast_fn fn, v
 int gamba_cuda_rowgen_begin(gamba_cuda_engine* e, uint32_t stride) {
     return guarded([&] { GCU_ENTER(e); e->rg_begin(stride); });
 }
-int gamba_cuda_rowgen_add_poly(gamba_cuda_engine* e, uint32_t n_terms, const uint16_t* ex, const uint32_t* hash, uint64_t* first_term) {
-    return guarded([&] { GCU_ENTER(e); e->rg_add_polys(1, &n_terms, &ex, &hash, first_term); });
+int gamba_cuda_rowgen_add_monomials(gamba_cuda_engine* e, uint32_t count, const uint16_t* ex, const uint32_t* hash, uint64_t* first) {
+    return guarded([&] { GCU_ENTER(e); e->rg_add_monomials(count, ex, hash, first); });
 }
-int gamba_cuda_rowgen_add_polys(gamba_cuda_engine* e, uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex,
-                                const uint32_t* const* hash, uint64_t* first_term) {
-    return guarded([&] { GCU_ENTER(e); e->rg_add_polys(n_polys, n_terms, ex, hash, first_term); });
+int gamba_cuda_rowgen_add_polys(gamba_cuda_engine* e, uint32_t n_polys, const uint32_t* n_terms, const uint32_t* const* mon, uint64_t* first_term) {
+    return guarded([&] { GCU_ENTER(e); e->rg_add_polys(n_polys, n_terms, mon, first_term); });
 }
 int gamba_cuda_rowgen_add_rows(gamba_cuda_engine* e, uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms,
                                const uint16_t* q_ex, const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials) {

@@ -11,7 +11,8 @@
 // traffic is left; what goes back to the host per batch is the new monomials (for its reducer search) and one lead
 // handle per row.
 //
-//   term store   pex[term][sd] u16, phv[term] u32: the basis polynomials' terms, uploaded once per polynomial
+//   basis table  bex[monomial][sd] u16, bhv[monomial] u32: the driver's basis monomials, appended as its table grows
+//   term store   pmon[term] u32: the basis polynomials as handles into that table, uploaded once per polynomial (4 B / term)
 //   step table   slots[cap_slots] (handle + 1 | 0 = empty | PENDING), hv[handle], ex[handle][sd]; open addressing,
 //                linear probing, additive hashes (hash(a * b) = hash(a) + hash(b), as source/monomial.hpp:80-90,126-131)
 //   sd           exponent-vector stride rounded up to an even number of u16 (32-bit compares)
@@ -26,8 +27,9 @@ constexpr int RG_MAX_SD = 128;            // u16 per exponent vector the kernels
 
 struct RowGenArgs {
     uint32_t sd;                          // u16 per exponent vector (even)
-    const uint16_t* pex;
-    const uint32_t* phv;
+    const uint16_t* bex;                  // [basis monomial][sd] the driver's basis monomials
+    const uint32_t* bhv;                  // [basis monomial] their hashes
+    const uint32_t* pmon;                 // term store: basis-monomial handle of every term of the uploaded polynomials
     uint32_t n_rows;
     const uint64_t* first_term;           // [n_rows] first term of the row's polynomial in the term store
     const uint64_t* row_off;              // [n_rows + 1] where the row's handles go in row_mon
@@ -58,11 +60,12 @@ __global__ void __launch_bounds__(RG_THREADS) rowgen_kernel(RowGenArgs a) {
         const uint32_t len = (uint32_t)(a.row_off[row + 1] - o0), hq = a.hq[row];
         for (uint32_t k = threadIdx.x; k < len; k += RG_THREADS) {
             uint32_t e[W];
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.pex + (t0 + k) * a.sd);
+            const uint32_t bm = a.pmon[t0 + k];
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(a.bex + (uint64_t)bm * a.sd);
             // two 16-bit exponents per word: no carry between the halves (exponents stay below 2^15, source/io.cpp:208-214)
 #pragma unroll
             for (int j = 0; j < W; ++j) e[j] = (uint32_t)j < w ? src[j] + s_q[j] : 0u;
-            const uint32_t h = a.phv[t0 + k] + hq;
+            const uint32_t h = a.bhv[bm] + hq;
             uint32_t s = h & a.mask, id;
             for (;;) {
                 uint32_t v = *reinterpret_cast<volatile uint32_t*>(a.slots + s);

@@ -161,7 +161,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) limb_gemm_tc_kernel(const __gri
     auto empty_bar = [&](uint32_t s) { return bars + 8 * (STAGES + s); };
     const uint32_t acc_full = bars + 8 * (2 * STAGES), acc_empty = bars + 8 * (2 * STAGES + 1);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t mt = blockIdx.x % a.m_tiles, nt = blockIdx.x / a.m_tiles, bb = blockIdx.y;
+    // Heaviest tiles first: the rows to reduce come sorted by descending first pivot, so the last row blocks contract over the most
+    // k-steps. With more tiles than SMs the light ones then fill in behind the heavy ones (before: every wave waited for its
+    // heaviest tile; ncu: SMs busy 55 % of such a launch).
+    const uint32_t mt = a.m_tiles - 1u - blockIdx.x / a.n_tiles, nt = blockIdx.x % a.n_tiles, bb = blockIdx.y;
     const uint32_t row0 = mt * TC_BM, col0 = nt * BN;
 
     if (tid == 0) {

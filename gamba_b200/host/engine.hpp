@@ -104,8 +104,10 @@ struct NewRows {
 struct RowGenDevice {
     virtual ~RowGenDevice() = default;
     virtual void begin(uint32_t stride) = 0;
-    // upload polynomials (terms as contiguous exponent vectors + hashes) in one go; first[i] names poly i in add_rows
-    virtual void add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex, const uint32_t* const* hv, uint64_t* first) = 0;
+    // append monomials of the driver's basis table; returns the index of the first one
+    virtual uint64_t add_monomials(uint32_t count, const uint16_t* ex, const uint32_t* hv) = 0;
+    // upload polynomials (lists of basis-table handles) in one go; first[i] names poly i in add_rows
+    virtual void add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint32_t* const* mon, uint64_t* first) = 0;
     // rows poly[i] * x^q[i]; lead_out[i] = handle of the first term of row i; returns the size of the table afterwards
     virtual uint32_t add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex,
                               const uint32_t* q_hash, uint32_t* lead_out) = 0;

@@ -56,8 +56,13 @@ public:
     // ---- RowGenDevice: thin wrappers of gamba_cuda_rowgen_* on the engine of GPU 0 ----
     RowGenDevice* rowgen() override { return std::getenv("GAMBA_HOST_ROWGEN") ? nullptr : this; }
     void begin(uint32_t stride) override { if (gamba_cuda_rowgen_begin(e_, stride)) fail("gamba_cuda_rowgen_begin"); }
-    void add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex, const uint32_t* const* hv, uint64_t* first) override {
-        if (gamba_cuda_rowgen_add_polys(e_, n_polys, n_terms, ex, hv, first)) fail("gamba_cuda_rowgen_add_polys");
+    uint64_t add_monomials(uint32_t count, const uint16_t* ex, const uint32_t* hv) override {
+        uint64_t first = 0;
+        if (gamba_cuda_rowgen_add_monomials(e_, count, ex, hv, &first)) fail("gamba_cuda_rowgen_add_monomials");
+        return first;
+    }
+    void add_polys(uint32_t n_polys, const uint32_t* n_terms, const uint32_t* const* mon, uint64_t* first) override {
+        if (gamba_cuda_rowgen_add_polys(e_, n_polys, n_terms, mon, first)) fail("gamba_cuda_rowgen_add_polys");
     }
     uint32_t add_rows(uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms, const uint16_t* q_ex,
                       const uint32_t* q_hash, uint32_t* lead_out) override {

@@ -253,7 +253,7 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
     if (!rg_) row_mon_.resize(row_off_.back());
     row_gen_.insert(row_gen_.end(), gens.begin(), gens.end());
     row_top_.insert(row_top_.end(), tops.begin(), tops.end());
-    {   // contiguous term data of the generators of this batch (once per generator)
+    if (!rg_) {   // contiguous term data of the generators of this batch (once per generator)
         std::vector<uint32_t> need;
         for (uint32_t g : gens) if (G_[g].hv.empty()) { G_[g].hv.resize(1); need.push_back(g); }
         pool_->parallel_for(need.size(), 4, [&](size_t a, size_t b) {
@@ -277,15 +277,21 @@ void F4::add_rows(const std::vector<uint32_t>& gens, const std::vector<uint16_t>
         double tA = now_s();
         std::vector<uint64_t> first(nb);
         std::vector<uint32_t> nt(nb);
-        {   // polynomials not yet in the device's term store: one upload for all of them
-            std::vector<uint32_t> ug, un; std::vector<const uint16_t*> uex; std::vector<const uint32_t*> uhv;
+        {   // the basis table's new monomials, then the polynomials not yet in the device's term store (as handles into that
+            // table: 4 bytes per term): one upload each
+            if (bt_dev_n_ < bt_.n) {
+                const uint64_t first_m = rg_->add_monomials(bt_.n - bt_dev_n_, bt_.e(bt_dev_n_), &bt_.hv[bt_dev_n_]);
+                if (first_m != bt_dev_n_) throw std::logic_error("device basis table out of step");
+                bt_dev_n_ = bt_.n;
+            }
+            std::vector<uint32_t> ug, un; std::vector<const uint32_t*> um;
             for (size_t i = 0; i < nb; ++i) {
                 Poly& f = G_[gens[i]];
-                if (f.dev_first == ~0ull) { f.dev_first = ~0ull - 1; ug.push_back(gens[i]); un.push_back((uint32_t)f.mon.size()); uex.push_back(f.ex.data()); uhv.push_back(f.hv.data()); }
+                if (f.dev_first == ~0ull) { f.dev_first = ~0ull - 1; ug.push_back(gens[i]); un.push_back((uint32_t)f.mon.size()); um.push_back(f.mon.data()); }
             }
             if (!ug.empty()) {
                 std::vector<uint64_t> uf(ug.size());
-                rg_->add_polys((uint32_t)ug.size(), un.data(), uex.data(), uhv.data(), uf.data());
+                rg_->add_polys((uint32_t)ug.size(), un.data(), um.data(), uf.data());
                 for (size_t k = 0; k < ug.size(); ++k) G_[ug[k]].dev_first = uf[k];
             }
         }
@@ -552,13 +558,18 @@ void F4::dump_step(const char* tag) {
 // source/basis.hpp:697-769): relative non-pivot index -> column -> monomial.
 void F4::insert_new_rows() {
     double t0 = now_s();
+    // the new rows only hold non-pivot columns (a few thousand distinct monomials for up to 10^8 terms): every column's
+    // monomial enters the basis table once, the terms index that map
+    constexpr uint32_t UNSET = 0xffffffffu;
+    std::vector<uint32_t> col2bt(nonpiv_col_.size(), UNSET);
     for (uint32_t r = 0; r < R_.n_new; ++r) {
         Poly f;
         uint64_t a = R_.row_ptr[r], b = R_.row_ptr[r + 1];
         f.mon.resize(b - a); f.cf.assign(R_.val.begin() + a, R_.val.begin() + b);
         for (uint64_t k = a; k < b; ++k) {
-            uint32_t h = order_[nonpiv_col_[R_.col[k]]];
-            f.mon[k - a] = bt_.insert(st_.e(h), st_.hv[h]);
+            const uint32_t c = R_.col[k], h = order_[nonpiv_col_[c]];
+            if (col2bt[c] == UNSET) col2bt[c] = bt_.insert(st_.e(h), st_.hv[h]);
+            f.mon[k - a] = col2bt[c];
             f.deg = std::max<uint32_t>(f.deg, st_.e(h)[0]);
         }
         if (f.cf[0] != 1) throw std::logic_error("engine returned a non-monic row");
@@ -589,13 +600,15 @@ void F4::final_reduce() {
     dump_step("final");
     if (R_.n_new != M_.n_bot) throw std::logic_error("final reduction lost a basis element");
     std::vector<Poly> out;
+    std::vector<uint32_t> col2bt(nonpiv_col_.size(), 0xffffffffu);
     for (uint32_t r = 0; r < R_.n_new; ++r) {
         Poly f;
         uint64_t a = R_.row_ptr[r], b = R_.row_ptr[r + 1];
         f.mon.resize(b - a); f.cf.assign(R_.val.begin() + a, R_.val.begin() + b);
         for (uint64_t k = a; k < b; ++k) {
-            uint32_t h = order_[nonpiv_col_[R_.col[k]]];
-            f.mon[k - a] = bt_.insert(st_.e(h), st_.hv[h]);
+            const uint32_t c = R_.col[k], h = order_[nonpiv_col_[c]];
+            if (col2bt[c] == 0xffffffffu) col2bt[c] = bt_.insert(st_.e(h), st_.hv[h]);
+            f.mon[k - a] = col2bt[c];
         }
         f.lm_mask = cx_.divmask(bt_.e(f.mon[0]));
         out.push_back(std::move(f));

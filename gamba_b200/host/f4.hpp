@@ -88,6 +88,7 @@ private:
     std::vector<uint8_t> row_top_;
     std::vector<uint32_t> row_lead_;     // step handle of every row's leading monomial
     RowGenDevice* rg_ = nullptr;         // rows are generated on the engine's device (CUDA engine) instead of here
+    uint32_t bt_dev_n_ = 0;              // basis-table monomials already uploaded to it
     std::vector<uint8_t> has_red_;       // per step-table monomial
     std::vector<uint32_t> order_;        // column -> step handle
     std::vector<uint32_t> nonpiv_col_;   // relative non-pivot index -> column

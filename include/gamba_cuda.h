@@ -194,19 +194,20 @@ int gamba_cuda_get_counters(gamba_cuda_engine* e, gamba_cuda_counters* c);
    the driver keeps the reducer search (source/matrix.hpp:569-600) and gets back, per batch, the new monomials and one lead handle
    per row. Exponent vectors are `stride` uint16 wide (whatever layout the driver uses; only equality and addition matter) with
    additive 32-bit hashes: hash(a * b) = hash(a) + hash(b) (source/monomial.hpp:80-90,126-131).
-     rowgen_begin        new step: empty table, no rows (polynomials uploaded earlier stay)
-     rowgen_add_poly     upload the terms of a basis polynomial once; *first_term identifies it in add_rows
-     rowgen_add_rows     append the rows poly[i] * x^q[i]; lead_out[i] = handle of row i's first term; *n_monomials = size of the
-                         table afterwards (handles [old size, new size) are the monomials this batch introduced)
-     rowgen_fetch_monomials   exponent vectors and hashes of the handles [first, first + count)
-     rowgen_rows         device pointer and length of the handle array: pass it as col_idx with GAMBA_CUDA_STEP_DEVICE_COLIDX,
-                         row_src[r] = where row r starts in it (rows are stored in the order they were added)
-     rowgen_download_rows     copy a range of the handle array to the host (dumps, debugging)                                    */
+     rowgen_begin          new step: empty table, no rows (basis monomials and polynomials uploaded earlier stay)
+     rowgen_add_monomials  append monomials of the driver's basis table (the one its polynomials are stored in: handles, as
+                           source/basis.hpp keeps them); *first = index the first of them got
+     rowgen_add_polys      upload basis polynomials once, as lists of indices into those monomials; first_term[i] identifies
+                           polynomial i in add_rows
+     rowgen_add_rows       append the rows poly[i] * x^q[i]; lead_out[i] = handle of row i's first term; *n_monomials = size of the
+                           step's table afterwards (handles [old size, new size) are the monomials this batch introduced)
+     rowgen_fetch_monomials   exponent vectors and hashes of the step-table handles [first, first + count)
+     rowgen_rows           device pointer and length of the handle array: pass it as col_idx with GAMBA_CUDA_STEP_DEVICE_COLIDX,
+                           row_src[r] = where row r starts in it (rows are stored in the order they were added)
+     rowgen_download_rows  copy a range of the handle array to the host (dumps, debugging)                                    */
 int gamba_cuda_rowgen_begin(gamba_cuda_engine* e, uint32_t stride);
-int gamba_cuda_rowgen_add_poly(gamba_cuda_engine* e, uint32_t n_terms, const uint16_t* ex, const uint32_t* hash, uint64_t* first_term);
-/* the same for n_polys polynomials in one upload (one synchronisation instead of one per polynomial) */
-int gamba_cuda_rowgen_add_polys(gamba_cuda_engine* e, uint32_t n_polys, const uint32_t* n_terms, const uint16_t* const* ex,
-                                const uint32_t* const* hash, uint64_t* first_term);
+int gamba_cuda_rowgen_add_monomials(gamba_cuda_engine* e, uint32_t count, const uint16_t* ex, const uint32_t* hash, uint64_t* first);
+int gamba_cuda_rowgen_add_polys(gamba_cuda_engine* e, uint32_t n_polys, const uint32_t* n_terms, const uint32_t* const* mon, uint64_t* first_term);
 int gamba_cuda_rowgen_add_rows(gamba_cuda_engine* e, uint32_t n_rows, const uint64_t* first_term, const uint32_t* n_terms,
                                const uint16_t* q_ex, const uint32_t* q_hash, uint32_t* lead_out, uint32_t* n_monomials);
 int gamba_cuda_rowgen_fetch_monomials(gamba_cuda_engine* e, uint32_t first, uint32_t count, uint16_t* ex_out, uint32_t* hash_out);

@@ -33,15 +33,27 @@ def test_rows_match_a_dictionary(built, nv, n_polys, max_terms, n_rows, seed):
         return np.uint32((w * e.astype(np.uint64)).sum() & 0xffffffff)
 
     assert lib.gamba_cuda_rowgen_begin(h, stride) == 0
-    polys, firsts = [], []
+    # the driver's basis table: monomials uploaded in two instalments, polynomials as handles into it
+    polys, firsts, basis_ex, basis_hv = [], [], [], []
     for _ in range(n_polys):
         n = int(rng.integers(1, max_terms + 1))
         es = rng.integers(0, 4, size=(n, nv)).astype(np.uint16)
         ex = np.ascontiguousarray(np.stack([vec(e) for e in es]))
         hv = np.array([hsh(e) for e in es], dtype=np.uint32)
-        first = C.c_uint64()
-        assert lib.gamba_cuda_rowgen_add_poly(h, n, ptr(ex), ptr(hv), C.byref(first)) == 0
-        polys.append((ex, hv)); firsts.append(first.value)
+        mon = np.arange(len(basis_hv), len(basis_hv) + n, dtype=np.uint32)
+        basis_ex.extend(ex); basis_hv.extend(hv)
+        polys.append((ex, hv, mon))
+    bex = np.ascontiguousarray(np.stack(basis_ex)); bhv = np.array(basis_hv, dtype=np.uint32)
+    half = len(bhv) // 2
+    first = C.c_uint64()
+    assert lib.gamba_cuda_rowgen_add_monomials(h, half, ptr(bex[:half]), ptr(bhv[:half]), C.byref(first)) == 0 and first.value == 0
+    assert lib.gamba_cuda_rowgen_add_monomials(h, len(bhv) - half, ptr(np.ascontiguousarray(bex[half:])), ptr(np.ascontiguousarray(bhv[half:])), C.byref(first)) == 0
+    assert first.value == half
+    nts = np.array([len(p_[1]) for p_ in polys], dtype=np.uint32)
+    mptr = (C.c_void_p * n_polys)(*[p_[2].ctypes.data for p_ in polys])
+    fts = np.zeros(n_polys, dtype=np.uint64)
+    assert lib.gamba_cuda_rowgen_add_polys(h, n_polys, ptr(nts), mptr, ptr(fts)) == 0
+    firsts = [int(x) for x in fts]
     table, rows_host, n_seen = {}, [], 0
     handles_dev = []
     for batch in range(3):                                    # several batches per step, the table grows in between
