@@ -23,6 +23,7 @@
 #include "kernels_echelon_mma.cuh"
 #include "kernels_elim.cuh"
 #include "kernels_elim_block.cuh"
+#include "kernels_mc.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_rowgen.cuh"
 #include "kernels_schur.cuh"
@@ -281,11 +282,19 @@ struct gamba_cuda_engine {
     int64_t opt_schur_max_gb = 96;   // budget for the limb-plane operands of the products
     int64_t opt_schur_min_top = 1024; // fewer pivot rows: not worth the dense operands
     int64_t opt_schur_kchunk = 0;    // k-steps between accumulator folds (0 = the exactness bound; tests lower it)
-    int64_t opt_mc = 0;              // Monte-Carlo combinations instead of the rows themselves
+    // Monte-Carlo combinations of the rows to reduce (kernels_mc.cuh): 0 never; 1 on steps with at least mc_min_top pivot rows when the
+    // rank predicted from the previous step needs at most half as many combinations as there are rows; 2 on every step a blocked
+    // solve can run on (64 combinations to start with when no rank is known)
+    int64_t opt_mc = 1;
     int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
+    int64_t opt_mc_min_top = 8192;   // mc = 1: steps with fewer pivot rows eliminate the rows themselves (launch-bound: nothing to gain)
     int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
-    uint32_t mc_k = 0;               // combinations used by the current reduction (0 = exact)
+    uint32_t mc_plan = 0;            // combinations the staged step starts with (choose_layout; 0 = the rows themselves)
+    uint32_t mc_k = 0;               // combinations the current elimination works on (0 = exact)
+    uint32_t mc_base = 0;            // rows of D' that already hold reduced combinations of earlier draws of this step
+    uint32_t mc_cap_rows = 0;        // rows D' must have room for (a later draw must not move the earlier ones)
     uint64_t mc_draw = 0;            // counter making every draw of multipliers different
+    gcu::DevBuf d_mc_sel, d_mc_c;    // multipliers S [combinations][n_bot], dense C half of the combinations [combinations][n_tiles_piv * T]
 
     // staged step
     bool staged = false;
@@ -360,7 +369,7 @@ struct gamba_cuda_engine {
         if (pl) cudaMemPoolDestroy(pl);
     }
 
-    void choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols);
+    void choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols, uint32_t step_flags, uint64_t step_nnz);
     void stage(const gamba_cuda_step_in* in);
     void eliminate();
     void exchange();
@@ -370,7 +379,7 @@ struct gamba_cuda_engine {
 
 using namespace gcu;
 
-void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols) {
+void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n_cols, uint32_t step_flags, uint64_t step_nnz) {
     L = Layout{};
     L.n_top = n_top; L.n_bot = n_bot; L.n_cols = n_cols; L.n_nonpiv = n_cols - n_top; L.n_rows = n_top + n_bot;
     L.ld_dprime = (L.n_nonpiv + 3u) & ~3u;
@@ -393,13 +402,10 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     // (unless Monte-Carlo combinations are on) the A half runs R rows per CTA over narrower tiles
     {
         const uint32_t world = std::max(1u, cfg.world_size);
-        const uint32_t nloc = (n_bot + world - 1) / world;
         const uint32_t nl = f.small ? 2u : 4u;
         const uint32_t sc_bm = 128, sc_bn = 128;     // the limb planes are padded to 128 rows (tile of either product kernel)
         const uint64_t kp = (n_top + SC_BK - 1) / SC_BK * SC_BK;
-        const uint64_t mt_ = (nloc + sc_bm - 1) / sc_bm, nt_ = (L.n_nonpiv + sc_bn - 1) / sc_bn;
-        use_schur = opt_schur && nloc && L.n_nonpiv && n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
-                    (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kp <= (double)opt_schur_max_gb * 1e9 && mt_ * nt_ < (1ull << 31);
+        const uint64_t nt_ = (L.n_nonpiv + sc_bn - 1) / sc_bn;
         // Three ways of finding the multipliers M = -C A^-1 (the A half of the elimination), chosen per step from modelled times:
         //   sparse          row-per-CTA kernel (kernels_elim.cuh): work = the pivot rows a row actually hits;
         //   sparse-blocked  R rows per CTA (kernels_elim_block.cuh): every entry of A is streamed once per block of rows - pays when
@@ -410,37 +416,63 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // The models use the previous step's multiplier density and entries per row of A (F4 steps change slowly); each is scaled
         // by a calibration factor = measured / modelled time of the steps that ran in that mode (run_reduce), so a model that is off
         // on a system corrects itself after one step in that mode; every 12th step the runner-up runs to keep its factor fresh.
-        use_block = false; use_panel = false;
+        // With Monte-Carlo combinations (kernels_mc.cuh) the rows are dense: only the two blocked solves apply.
         if (opt_panel_t > 0) PANEL_T = (uint32_t)opt_panel_t;
         else PANEL_T = n_top >= 12288 ? 2048u : n_top >= 3072 ? 1024u : 512u;
-        bool panel_fits = false;
         const double occ_ = opt_bsparse && n_top >= 8192 ? last_occ : 1.0;
-        if (use_schur && !opt_mc && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top) {
-            const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T, kt_ = ntp_ * PANEL_T;
-            // dense: every At_t at once; block-sparse: one pivot tile's occupied blocks at a time
-            const double at_b = (occ_ < 1.0 || (opt_bsparse && n_top >= 8192) ? (double)nl * PANEL_T * (double)kt_ * occ_ : (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2))
-                                + 3.25 * nl * (double)kt_ * PANEL_T;
-            panel_fits = at_b <= (double)opt_panel_max_gb * 1e9 &&
-                         at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kt_ + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9;
-        }
-        const bool block_ok = use_schur && !opt_mc && opt_block >= 1;
-        int mode = 0;
-        if (opt_panel >= 2 && panel_fits) mode = 2;
-        else if (opt_block >= 2 && block_ok) mode = 1;
-        else if (have_history && use_schur && !opt_mc) {
+        auto decide = [&](uint32_t n_work, bool mc, double& t_est, bool explore) -> int {      // -1: no solve for dense combinations; t_est: modelled seconds
+            const uint32_t nloc = (n_work + world - 1) / world;
+            const uint64_t mt_ = (nloc + sc_bm - 1) / sc_bm;
+            use_schur = opt_schur && nloc && L.n_nonpiv && n_top >= (uint32_t)std::max<int64_t>(1, opt_schur_min_top) &&
+                        (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kp <= (double)opt_schur_max_gb * 1e9 && mt_ * nt_ < (1ull << 31);
+            bool panel_fits = false;
+            if (use_schur && n_top > PANEL_T && n_top <= (uint64_t)opt_panel_max_top && (!mc || PANEL_T <= (uint32_t)BLK_TMAX)) {
+                const uint64_t ntp_ = (n_top + PANEL_T - 1) / PANEL_T, kt_ = ntp_ * PANEL_T;
+                // dense: every At_t at once; block-sparse: one pivot tile's occupied blocks at a time
+                const double at_b = (occ_ < 1.0 || (opt_bsparse && n_top >= 8192) ? (double)nl * PANEL_T * (double)kt_ * occ_ : (double)nl * PANEL_T * PANEL_T * (double)(ntp_ * (ntp_ - 1) / 2))
+                                    + 3.25 * nl * (double)kt_ * PANEL_T;
+                panel_fits = at_b <= (double)opt_panel_max_gb * 1e9 &&
+                             at_b + (double)nl * (mt_ * sc_bm + nt_ * sc_bn) * kt_ + (double)mt_ * sc_bm * PANEL_T * (4 + nl) <= (double)opt_schur_max_gb * 1e9;
+            }
+            const bool block_ok = use_schur && opt_block >= 1;
+            int mode = mc ? -1 : 0;
             double est[3];
-            est[0] = calib[0] * hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
-            est[1] = block_ok && n_top >= 8192 ? calib[1] * model_block(nloc, n_top, last_a, f.small != 0) : 1e30;
+            est[0] = mc ? 1e30 : calib[0] * hitw * model_sparse(nloc, last_density, n_top, last_a, f.small != 0);
+            est[1] = block_ok && (n_top >= 8192 || opt_block >= 2) ? calib[1] * model_block(nloc, n_top, have_history ? last_a : 100.0, f.small != 0) : 1e30;
             est[2] = panel_fits && opt_panel >= 1 ? calib[2] * model_panel((double)(mt_ * sc_bm), n_top, nl, PANEL_T, occ_) : 1e30;
-            mode = est[1] < est[0] ? 1 : 0;
-            if (est[2] < est[mode]) mode = 2;
-            if (++since_explore >= 8) {           // the runner-up, if it is within 1.5x
-                since_explore = 0;
-                int second = -1;
-                for (int m = 0; m < 3; ++m) if (m != mode && est[m] < 1.5 * est[mode] && (second < 0 || est[m] < est[second])) second = m;
-                if (second >= 0) mode = second;
+            t_est = 1e30;
+            if (opt_panel >= 2 && panel_fits) mode = 2;
+            else if (opt_block >= 2 && block_ok) mode = 1;
+            else if (use_schur && (have_history || mc)) {
+                if (mc) { mode = est[1] < est[2] ? 1 : 2; if (est[mode] >= 1e30) mode = -1; }
+                else {
+                    mode = est[1] < est[0] ? 1 : 0;
+                    if (est[2] < est[mode]) mode = 2;
+                }
+                if (explore && mode >= 0 && ++since_explore >= 8) {           // the runner-up, if it is within 1.5x
+                    since_explore = 0;
+                    int second = -1;
+                    for (int m = 0; m < 3; ++m) if (m != mode && est[m] < 1.5 * est[mode] && (second < 0 || est[m] < est[second])) second = m;
+                    if (second >= 0) mode = second;
+                }
+            }
+            if (mode >= 0 && (have_history || mode > 0)) t_est = est[mode];
+            return mode;
+        };
+        // Monte-Carlo combinations: K = predicted rank + margin of them instead of the n_bot rows, when that halves the rows at least
+        mc_plan = 0;
+        if (opt_mc && !(step_flags & GAMBA_CUDA_STEP_FINAL) && n_bot >= 256 && L.n_nonpiv && (opt_mc >= 2 || n_top >= (uint64_t)std::max<int64_t>(1, opt_mc_min_top))) {
+            const int64_t pred = opt_mc_k > 0 ? opt_mc_k : last_rank >= 0 ? last_rank + 32 + last_rank / 8 : opt_mc >= 2 ? 64 : -1;
+            if (pred > 0) {
+                const uint64_t k = ((uint64_t)pred + 7) / 8 * 8;
+                if (k * 2 <= n_bot) mc_plan = (uint32_t)k;
             }
         }
+        // The choice between combinations and rows must be the same on every rank (the all-gather sizes follow from it): it uses
+        // sizes, options and the previous step's rank only - never the calibration factors, which are rank-local timings.
+        double t_mc = 1e30, t_exact = 1e30;
+        int mode = mc_plan ? decide(mc_plan, true, t_mc, true) : -1;
+        if (mode < 0) { mc_plan = 0; mode = decide(n_bot, false, t_exact, true); }
         use_block = mode == 1; use_panel = mode == 2;
         if (use_block) tmax = BLK_TMAX;
         if (use_panel) tmax = PANEL_T;
@@ -503,7 +535,7 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         std::memcpy(&hd, h_hdr.p, sizeof hd);
     }
     const uint32_t n_rows = hd.n_top + hd.n_bot;
-    choose_layout(hd.n_top, hd.n_bot, hd.n_cols);
+    choose_layout(hd.n_top, hd.n_bot, hd.n_cols, hd.flags, hd.nnz);
     flags = hd.flags & ~(GAMBA_CUDA_STEP_DEVICE_INDICES | GAMBA_CUDA_STEP_DEVICE_COLIDX); nnz = hd.nnz;
     if ((uint64_t)n_rows * L.n_tiles + 1 >= (1ull << 32)) throw std::runtime_error("segment table too large");
     if (nnz + 1ull * n_rows * L.n_tiles + 4 >= (1ull << 32)) throw std::runtime_error("step has too many non-zeros for 32-bit entry offsets");
@@ -685,7 +717,8 @@ void gamba_cuda_engine::eliminate() {
     const uint32_t n_work = mc_k ? mc_k : L.n_bot;       // rows of C|D, or random combinations of them
     n_local_max = (n_work + world - 1) / world;
     n_local = n_work > rank ? (n_work - rank + world - 1) / world : 0;
-    n_gather_rows = world > 1 ? n_local_max * world : n_work;
+    n_gather_rows = mc_base + (world > 1 ? n_local_max * world : n_work);
+    if (mc_k && !(use_schur && (use_block || use_panel) && n_local)) throw std::runtime_error("Monte-Carlo combinations need one of the blocked solves");
 
     const uint32_t words_per_col = f.small ? 1u : 2u;
     const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
@@ -712,19 +745,21 @@ void gamba_cuda_engine::eliminate() {
     }
     const uint64_t n_slots = (uint64_t)elim_grid;
 
-    d_dprime.ensure(std::max<uint64_t>((uint64_t)n_gather_rows * L.ld_dprime, 1) * sizeof(uint32_t));
-    d_row_nz.ensure(std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t));
+    const uint32_t cap_rows = std::max(n_gather_rows, mc_k ? mc_cap_rows : 0u);     // a later draw must find the earlier combinations where they are
+    d_dprime.ensure(std::max<uint64_t>((uint64_t)cap_rows * L.ld_dprime, 1) * sizeof(uint32_t));
+    d_row_nz.ensure(std::max<uint32_t>(cap_rows, 1) * sizeof(uint32_t));
     if (!(schur && (block || panel))) {     // the blocked kernel keeps its multipliers in d_mt, the blocked solve needs no lists
         d_list_k.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
         d_list_m.ensure(std::max<uint64_t>(n_slots * L.n_top, 1) * sizeof(uint32_t));
     }
     d_queue_stats.ensure(64);
     GCU_CHECK(cudaMemsetAsync(d_queue_stats.p, 0, 64, stream));
-    GCU_CHECK(cudaMemsetAsync(d_row_nz.p, 0, std::max<uint32_t>(n_gather_rows, 1) * sizeof(uint32_t), stream));
+    if (n_gather_rows > mc_base) GCU_CHECK(cudaMemsetAsync(d_row_nz.as<uint32_t>() + mc_base, 0, (size_t)(n_gather_rows - mc_base) * sizeof(uint32_t), stream));
 
-    // local block of D' sits at its final place inside the gather buffer
-    uint32_t* dloc = d_dprime.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max * L.ld_dprime : 0);
-    uint32_t* nzloc = d_row_nz.as<uint32_t>() + (world > 1 ? (uint64_t)rank * n_local_max : 0);
+    // local block of D' sits at its final place inside the gather buffer (behind the combinations of earlier draws)
+    const uint64_t loc_row0 = (uint64_t)mc_base + (world > 1 ? (uint64_t)rank * n_local_max : 0);
+    uint32_t* dloc = d_dprime.as<uint32_t>() + loc_row0 * L.ld_dprime;
+    uint32_t* nzloc = d_row_nz.as<uint32_t>() + loc_row0;
 
     ElimArgs ea{};
     ea.L = L; ea.f = f;
@@ -740,9 +775,8 @@ void gamba_cuda_engine::eliminate() {
     ea.queue = d_queue_stats.as<uint32_t>();
     ea.stats = reinterpret_cast<unsigned long long*>(d_queue_stats.as<char>() + 16);
     ea.row_ptr = s_row_ptr;
-    ea.mc_rows = mc_k ? L.n_bot : 0;
-    ea.mc_seed = cfg.seed * 0x9e3779b97f4a7c15ull + mc_draw;
-    if (mc_k) { GCU_CHECK(cudaMemcpyAsync(&ea.mc_first, d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); GCU_CHECK(cudaStreamSynchronize(stream)); }
+    uint32_t mc_first = 0;           // smallest pivot column any row to reduce holds: where every combination starts
+    if (mc_k) { GCU_CHECK(cudaMemcpyAsync(&mc_first, d_first.as<uint32_t>() + std::max<uint32_t>(L.n_bot, 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)); GCU_CHECK(cudaStreamSynchronize(stream)); }
     ea.row_begin = rank; ea.row_step = world; ea.n_local = n_local;
     ea.t_lo = 0; ea.t_hi = L.n_tiles;
 
@@ -756,6 +790,30 @@ void gamba_cuda_engine::eliminate() {
     const uint64_t mx_plane = (uint64_t)mp * kp, bt_plane = (uint64_t)np * kp;
     const uint64_t tri_plane = (uint64_t)kt * T;
     GCU_CHECK(cudaEventRecord(ev[2], stream));
+    const uint64_t mc_ldc = (uint64_t)ntp * L.tile_cols;
+    if (mc_k) {
+        // the combinations as dense rows: C half into d_mc_c, D half straight into D' (kernels_mc.cuh)
+        const uint32_t R = f.small ? BlkRows<true>::R : BlkRows<false>::R;
+        McRowsArgs ma{};
+        ma.L = L; ma.f = f; ma.mu32 = ea.mu32; ma.negp = ea.negp; ma.norm_every = ea.norm_every;
+        ma.seg = ea.seg; ma.ent = ea.ent;
+        ma.nbp = (L.n_bot + 31u) / 32u * 32u; ma.n_q = n_local; ma.n_q_pad = (n_local + R - 1) / R * R;
+        ma.q_global0 = mc_base + rank * n_local_max;
+        ma.seed = cfg.seed * 0x9e3779b97f4a7c15ull + 0xd1342543de82ef95ull * mc_draw;
+        d_mc_sel.ensure((uint64_t)ma.n_q_pad * ma.nbp * sizeof(uint32_t));
+        d_mc_c.ensure(std::max<uint64_t>((uint64_t)n_local * mc_ldc, 1) * sizeof(uint32_t));
+        ma.s = d_mc_sel.as<uint32_t>(); ma.dst_c = d_mc_c.as<uint32_t>(); ma.ldc = mc_ldc; ma.dst_d = dloc; ma.ldd = L.ld_dprime;
+        GCU_CHECK(cudaMemsetAsync(dloc, 0, (uint64_t)n_local * L.ld_dprime * sizeof(uint32_t), stream));
+        mc_gen_kernel<<<(uint32_t)(((uint64_t)ma.n_q_pad * ma.nbp + 255) / 256), 256, 0, stream>>>(ma);
+        GCU_CHECK(cudaGetLastError());
+        auto mk = f.small ? mc_rows_kernel<true> : mc_rows_kernel<false>;
+        const size_t msm = (size_t)R * BLK_TS * (f.small ? 1 : 2) * 4;
+        GCU_CHECK(cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+        if (L.tile_cols > (uint32_t)BLK_TMAX) throw std::runtime_error("Monte-Carlo combinations: column tile too wide");
+        mk<<<dim3(ma.n_q_pad / R, L.n_tiles), BLK_THREADS, msm, stream>>>(ma);
+        GCU_CHECK(cudaGetLastError());
+        ctr.kernel_launches += 2;
+    }
     // Block-sparse operands (kernels_schur.cuh, BsArgs): which blocks of 128 pivot rows x bn columns of B (and, for the blocked
     // solve, of A right of a row's own tile) hold an entry at all. The products then skip the empty ones.
     const bool bs = schur && opt_bsparse && L.tile_cols % bn == 0 && L.n_top >= 8192;
@@ -917,15 +975,22 @@ void gamba_cuda_engine::eliminate() {
         const CUtensorMap map_bs = bs ? make_tmap_u8(d_bs_at.p, TC_BK, (uint64_t)nl * (bs_at_plane / 128), TC_BK, bn) : map_cx;
         TriRowsArgs ra{};
         ra.L = L; ra.seg = d_seg.as<uint32_t>(); ra.ent = d_ent.as<uint2>(); ra.row_begin = rank; ra.row_step = world; ra.n_local = n_local;
+        const uint32_t* fpiv = mc_k ? nullptr : d_first.as<uint32_t>();      // combinations all start at mc_first
+        if (mc_k && mp > n_local) GCU_CHECK(cudaMemsetAsync(d_cd.as<uint32_t>() + (uint64_t)n_local * T, 0, (uint64_t)(mp - n_local) * T * sizeof(uint32_t), stream));
         for (uint32_t t = 0; t < ntp; ++t) {
             const uint32_t tw = lay_tile_width(L, t);
-            ra.dst = d_cd.as<uint32_t>(); ra.ld = T; ra.width = T; ra.t_lo = t; ra.t_hi = t + 1; ra.col_base = t * T; ra.n_pad = mp;
-            tri_rows_kernel<<<mp, 128, 0, stream>>>(ra);
-            GCU_CHECK(cudaGetLastError());
+            if (mc_k) {      // C_t of the combinations: a column block of the dense rows
+                GCU_CHECK(cudaMemcpy2DAsync(d_cd.p, (size_t)T * sizeof(uint32_t), d_mc_c.as<uint32_t>() + (uint64_t)t * T, mc_ldc * sizeof(uint32_t),
+                                            (size_t)T * sizeof(uint32_t), n_local, cudaMemcpyDeviceToDevice, stream));
+            } else {
+                ra.dst = d_cd.as<uint32_t>(); ra.ld = T; ra.width = T; ra.t_lo = t; ra.t_hi = t + 1; ra.col_base = t * T; ra.n_pad = mp;
+                tri_rows_kernel<<<mp, 128, 0, stream>>>(ra);
+                GCU_CHECK(cudaGetLastError());
+            }
             TcArgs ta{};
             ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = T; ta.n_rows = n_local; ta.n_cols = tw; ta.ld = T;
             ta.d = d_cd.as<uint32_t>(); ta.m_tiles = mp / TC_BM; ta.n_tiles = T / bn;
-            ta.first_piv = d_first.as<uint32_t>(); ta.row_begin = rank; ta.row_step = world;
+            ta.first_piv = fpiv; ta.k_first = mc_first; ta.row_begin = rank; ta.row_step = world;
             ta.kchunk = kchunk; ta.k_end = t * T;
             ta.o1 = d_cx.as<uint8_t>(); ta.o1_plane = (uint64_t)mp * T; ta.o1_ld = T;
             if (bs) {
@@ -942,7 +1007,7 @@ void gamba_cuda_engine::eliminate() {
             launch_limb_gemm<EPI_RMW_LIMBS>(f.small != 0, map_mx, map_at, ta, 1, stream);
             TcArgs xa{};
             xa.f = f; xa.mp = mp; xa.np = kt; xa.n_rows = n_local; xa.n_cols = tw; xa.m_tiles = mp / TC_BM; xa.n_tiles = (tw + bn - 1) / bn;
-            xa.first_piv = d_first.as<uint32_t>(); xa.row_begin = rank; xa.row_step = world;
+            xa.first_piv = fpiv; xa.k_first = mc_first; xa.row_begin = rank; xa.row_step = world;
             xa.kmin_sub = t * T; xa.skip_hi = (t + 1) * T;
             xa.kchunk = tkc; xa.k_end = (tw + TC_BK - 1) / TC_BK * TC_BK;
             xa.b_row0 = t * T; xa.neg = 1; xa.tri = 2;
@@ -952,7 +1017,7 @@ void gamba_cuda_engine::eliminate() {
             ctr.kernel_launches += 3;
         }
         // 3. D scattered into D' (the product below adds M B)
-        if (L.n_nonpiv) {
+        if (L.n_nonpiv && !mc_k) {
             ra.dst = dloc; ra.ld = L.ld_dprime; ra.width = L.ld_dprime; ra.t_lo = ntp; ra.t_hi = L.n_tiles; ra.col_base = L.n_top; ra.n_pad = n_local;
             tri_rows_kernel<<<n_local, 128, 0, stream>>>(ra);
             GCU_CHECK(cudaGetLastError());
@@ -970,13 +1035,14 @@ void gamba_cuda_engine::eliminate() {
         const uint32_t n_blocks = (n_local + R - 1) / R;
         const int bgrid = std::max(1, std::min<int>(prop.multiProcessorCount * bocc, (int)n_blocks));
         d_mt.ensure((uint64_t)bgrid * std::max(1u, L.n_windows) * R * 32 * sizeof(uint32_t));
-        GCU_CHECK(cudaMemsetAsync(dloc, 0, (uint64_t)n_local * L.ld_dprime * sizeof(uint32_t), stream));
+        if (!mc_k) GCU_CHECK(cudaMemsetAsync(dloc, 0, (uint64_t)n_local * L.ld_dprime * sizeof(uint32_t), stream));
         BlkArgs b{};
         b.L = L; b.f = f; b.mu32 = ea.mu32; b.negp = ea.negp; b.norm_every = ea.norm_every;
         b.seg = ea.seg; b.ent = ea.ent; b.diag = ea.diag; b.dnz = ea.dnz; b.first_piv = ea.first_piv;
         b.dprime = dloc; b.mt = d_mt.as<uint32_t>(); b.queue = ea.queue;
         b.row_begin = rank; b.row_step = world; b.n_local = n_local; b.row_ptr = ea.row_ptr; b.stats = ea.stats;
         b.mx = ea.mx; b.mx_plane = ea.mx_plane; b.mx_kp = ea.mx_kp; b.mx_nl = ea.mx_nl;
+        if (mc_k) { b.dense_c = d_mc_c.as<uint32_t>(); b.dense_ld = mc_ldc; b.mc_first = mc_first; }
         bk<<<bgrid, BLK_THREADS, bsmem, stream>>>(b);
         GCU_CHECK(cudaGetLastError());
         ctr.kernel_launches += 1;
@@ -992,7 +1058,7 @@ void gamba_cuda_engine::eliminate() {
         TcArgs ta{};
         ta.f = f; ta.kp = kp; ta.mp = mp; ta.np = np; ta.n_rows = n_local; ta.n_cols = L.n_nonpiv; ta.ld = L.ld_dprime;
         ta.d = dloc; ta.row_nz = nzloc; ta.m_tiles = mp / TC_BM; ta.n_tiles = np / bn;
-        ta.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); ta.k_first = ea.mc_first; ta.row_begin = rank; ta.row_step = world;
+        ta.first_piv = mc_k ? nullptr : d_first.as<uint32_t>(); ta.k_first = mc_first; ta.row_begin = rank; ta.row_step = world;
         ta.kchunk = kchunk; ta.k_end = k_used;
         const CUtensorMap map_mx = make_tmap_u8(d_mx.p, kp, (uint64_t)nl * mp, TC_BK, TC_BM);
         if (bs) { ta.np = (uint32_t)(bs_plane / 128); ta.klist = d_bs_klist.as<uint32_t>(); ta.kl_base = d_bs_base.as<uint32_t>(); ta.kl_cb0 = n_cb_piv; ta.kl_id0 = (uint32_t)nb_a; }
@@ -1019,10 +1085,12 @@ void gamba_cuda_engine::exchange() {
     if (!gather_fn) throw std::runtime_error("world_size > 1 but no all-gather callback set");
     const size_t bytes_d = (size_t)n_local_max * L.ld_dprime * sizeof(uint32_t);
     const size_t bytes_z = (size_t)n_local_max * sizeof(uint32_t);
-    const char* send_d = d_dprime.as<char>() + (size_t)cfg.rank * bytes_d;
-    const char* send_z = d_row_nz.as<char>() + (size_t)cfg.rank * bytes_z;
-    if (bytes_d && gather_fn(gather_user, send_d, d_dprime.p, bytes_d, stream)) throw std::runtime_error("all-gather of D' failed");
-    if (bytes_z && gather_fn(gather_user, send_z, d_row_nz.p, bytes_z, stream)) throw std::runtime_error("all-gather of row flags failed");
+    char* recv_d = d_dprime.as<char>() + (size_t)mc_base * L.ld_dprime * sizeof(uint32_t);      // behind the combinations of earlier draws
+    char* recv_z = d_row_nz.as<char>() + (size_t)mc_base * sizeof(uint32_t);
+    const char* send_d = recv_d + (size_t)cfg.rank * bytes_d;
+    const char* send_z = recv_z + (size_t)cfg.rank * bytes_z;
+    if (bytes_d && gather_fn(gather_user, send_d, recv_d, bytes_d, stream)) throw std::runtime_error("all-gather of D' failed");
+    if (bytes_z && gather_fn(gather_user, send_z, recv_z, bytes_z, stream)) throw std::runtime_error("all-gather of row flags failed");
 }
 
 void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
@@ -1195,20 +1263,20 @@ void gamba_cuda_engine::echelon(gamba_cuda_step_out* out, uint32_t mc_rows) {
     out->d2h_bytes = (npiv + 1) * 8ull + nnz_new * 8ull + npiv * 4ull + 24;
 }
 
-// Exact mode: every row of C|D is eliminated. Monte-Carlo mode (option "mc"): K random combinations of
-// all the rows are eliminated instead and the result is accepted only if the rank of D' leaves a margin
-// of 32 combinations (K - rank >= 32): K random vectors of a space of dimension rank span it except
-// with probability ~p^-(K-rank) <= 3^-32, so the row space - hence the canonical RREF - is that of the
-// exact computation. Otherwise K is doubled, and beyond n_bot/3 combinations the step runs exactly.
+// Exact mode: every row of C|D is eliminated. Monte-Carlo mode (kernels_mc.cuh, chosen in choose_layout): K random combinations
+// of all the rows are eliminated instead and the result is accepted only if the rank of D' leaves a margin of 32 combinations
+// (K - rank >= 32): K uniform vectors of a space of dimension rank span it except with probability ~p^-(K - rank) <= 3^-32, so
+// the row space - hence the canonical RREF - is that of the exact computation. When the margin is not met the reduced
+// combinations stay where they are in D' (they are rows of the row space whatever the echelon did to them) and as many fresh
+// ones are added behind them (the total doubles); when half the rows would be reached, the step runs exactly.
 void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
-    uint32_t k = 0;
-    if (opt_mc && !(flags & GAMBA_CUDA_STEP_FINAL) && L.n_bot >= 256) {
-        k = opt_mc_k > 0 ? (uint32_t)opt_mc_k : (last_rank < 0 ? 64u : (uint32_t)(last_rank + 32 + last_rank / 8));
-        k = (k + 7) / 8 * 8;
-        if ((uint64_t)k * 3 >= L.n_bot) k = 0;
-    }
+    uint32_t k = mc_plan;
+    const uint32_t world = std::max(1u, cfg.world_size);
+    mc_base = 0;
+    mc_cap_rows = k ? L.n_bot / 2 + 32 * world + 8 : 0;    // the draws stop at n_bot / 2 combinations; each is padded to a multiple of the ranks
     double acc_elim = 0, acc_ech = 0;
     ctr.mc_attempts = 0;
+    uint32_t combos = 0;
     for (;;) {
         mc_k = k; ++mc_draw; ++ctr.mc_attempts;
         double tq = wall_s();
@@ -1234,14 +1302,19 @@ void gamba_cuda_engine::run_reduce(gamba_cuda_step_out* out) {
         mc_ech_k = kk; ctr.mc_ech_combinations = kk;
         dbg_[6] += wall_s() - tq;
         acc_elim += t_elim_dev; acc_ech += t_ech_dev;
-        if (mc_k && out->n_new + 32 > mc_k) {          // margin not met: more combinations, or exact
-            k = mc_k * 2;
-            if ((uint64_t)k * 3 >= L.n_bot) k = 0;
+        if (mc_k) {
+            combos += mc_k;
+            if (out->n_new + 32 <= combos) break;                    // accepted
+            ctr.steps -= 1;
+            const uint64_t next = combos;                            // as many again
+            if ((combos + next) * 2 > L.n_bot) { k = 0; mc_base = 0; combos = 0; }                   // exact
+            else { k = (uint32_t)next; mc_base = n_gather_rows; }
             continue;
         }
         break;
     }
-    ctr.mc_combinations = mc_k;
+    ctr.mc_combinations = combos;
+    mc_base = 0;
     last_rank = out->n_new;
     out->seconds_eliminate = acc_elim; out->seconds_echelon = acc_ech;
     out->seconds_device = t_prep_dev + acc_elim + acc_ech;
@@ -1605,6 +1678,7 @@ int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value) 
         else if (k == "mc_ech") e->opt_mc_ech = value;
         else if (k == "mc") e->opt_mc = value;
         else if (k == "mc_k") e->opt_mc_k = value;
+        else if (k == "mc_min_top") e->opt_mc_min_top = value;
         else if (k == "rank_hint") e->last_rank = value;
         else throw std::runtime_error("unknown option " + k);
     });

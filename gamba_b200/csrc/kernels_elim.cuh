@@ -78,11 +78,6 @@ struct ElimArgs {
     uint32_t* queue;             // atomic row counter
     uint32_t row_begin, row_step, n_local;  // rows r = row_begin + i * row_step, i < n_local
     const uint64_t* row_ptr;     // block-form CSR row pointers (for the fma_top invariant)
-    // Monte-Carlo mode (README.md:5 of the reference, "Monte-Carlo F4"): work item q is not row q of C|D
-    // but the random linear combination sum_r s(q,r) * row_r of ALL mc_rows rows, s = hash(mc_seed, q, r)
-    uint32_t mc_rows;            // 0 = exact mode
-    uint32_t mc_first;           // smallest pivot column present in any row to reduce
-    uint64_t mc_seed;
     unsigned long long* stats;   // [0] pivot rows applied, [1] multiply-adds done, [2] fma_top
     // Schur mode (kernels_schur.cuh): the non-pivot tiles are NOT eliminated here; the multipliers are
     // recorded as u8 limb planes mx[limb][local row][k] and D' = D + M B runs on the tensor cores
@@ -96,15 +91,6 @@ struct ElimArgs {
     const uint32_t* cd;          // NULL outside panel mode (and for the first pivot tile)
     uint32_t cd_ld, panel;
 };
-
-// multiplier of row r in combination q: uniform in [1, p) (splitmix64 finaliser)
-__device__ __forceinline__ uint32_t mc_coeff(uint64_t seed, uint32_t q, uint32_t r, uint32_t p) {
-    uint64_t z = seed + 0x9e3779b97f4a7c15ull * (((uint64_t)q << 32) | r) + 0x632be59bd9b4e019ull;
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    z ^= z >> 31;
-    return 1u + (uint32_t)(z % (p - 1));
-}
 
 // ---- accumulator policies -------------------------------------------------------------------
 
@@ -257,7 +243,7 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
         const uint32_t li = a.n_local - 1 - q;                 // later rows have smaller leads: more work
         const uint32_t r = a.row_begin + li * a.row_step;      // index among the rows to reduce
         const uint32_t grow = L.n_top + r;
-        const uint32_t first = a.mc_rows ? a.mc_first : a.first_piv[r];
+        const uint32_t first = a.first_piv[r];
         const uint32_t t_first = first < L.n_top ? first / L.tile_cols : L.n_tiles_piv;
         uint32_t nlist = 0;
         bool nz = false;
@@ -277,20 +263,11 @@ __global__ void __launch_bounds__(ELIM_CTA_WARPS * 32) elim_kernel(ElimArgs a) {
                 for (uint32_t i = tid; i < tw; i += ELIM_CTA_THREADS) Acc<SMALLP>::set(acc, i, __ldcg(cdr + i));
                 __syncthreads();
                 const uint32_t s = seg_s[grow], e = seg_e[grow];
-                for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::add(acc_sa, en.x, en.y); }
+                for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::add(acc_sa, en.x & 0xffffu, en.y); }
                 absorbed = 2;
-            } else if (a.mc_rows == 0) {   // the row itself
+            } else {   // the row itself
                 const uint32_t s = seg_s[grow], e = seg_e[grow];
-                for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x, en.y); }
-            } else {                // Monte-Carlo: combination number r of all the rows to reduce
-                for (uint32_t base0 = 0; base0 < a.mc_rows; base0 += 32 * ELIM_CTA_WARPS) {
-                    if (absorbed + 32 * ELIM_CTA_WARPS > a.norm_every) { elim_normalise<SMALLP, ELIM_CTA_THREADS>(acc, tw, a); absorbed = 1; }
-                    absorbed += 32 * ELIM_CTA_WARPS;
-                    const uint32_t i = base0 + warp * 32 + lane;
-                    uint32_t s = 0, len = 0, m = 0;
-                    if (i < a.mc_rows) { s = seg_s[L.n_top + i]; len = seg_e[L.n_top + i] - s; m = mc_coeff(a.mc_seed, r, i, p); }
-                    elim_apply_segments<SMALLP>(acc_sa, ring_sa, a, s, len, m, __ballot_sync(0xffffffffu, len != 0), lane);
-                }
+                for (uint32_t k = s + tid; k < e; k += ELIM_CTA_THREADS) { const uint2 en = __ldg(a.ent + k); Acc<SMALLP>::set(acc, en.x & 0xffffu, en.y); }
             }
             __syncthreads();
             // deferred pass over the pivots found in earlier tiles

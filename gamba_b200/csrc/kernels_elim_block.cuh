@@ -58,6 +58,11 @@ struct BlkArgs {
     uint8_t* mx;                 // limb planes of the multipliers for the Schur product
     uint64_t mx_plane;
     uint32_t mx_kp, mx_nl;
+    // Monte-Carlo combinations (kernels_mc.cuh): the rows are dense, row li = dense_c[li * dense_ld + pivot column]; their D half
+    // is already in dprime. NULL: the rows of C|D themselves
+    const uint32_t* dense_c;
+    uint64_t dense_ld;
+    uint32_t mc_first;           // smallest pivot column any row to reduce holds
 };
 
 template <bool SMALLP>
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(BLK_THREADS, BLK_CTAS) elim_block_kernel(BlkAr
         if (q >= n_blocks) break;
         const uint32_t blk = n_blocks - 1 - q;                             // later rows have smaller leads: more work
         const uint32_t li0 = blk * R;
-        if (tid < (uint32_t)R && li0 + tid < a.n_local) atomicMin(&s_first, a.first_piv[a.row_begin + (li0 + tid) * a.row_step]);
+        if (tid < (uint32_t)R && li0 + tid < a.n_local) atomicMin(&s_first, a.dense_c ? a.mc_first : a.first_piv[a.row_begin + (li0 + tid) * a.row_step]);
         for (uint32_t i = tid; i < nww; i += BLK_THREADS) wnz[i] = 0;
         __syncthreads();
         const uint32_t first = s_first;
@@ -160,6 +165,12 @@ __global__ void __launch_bounds__(BLK_THREADS, BLK_CTAS) elim_block_kernel(BlkAr
             for (uint32_t i = tid; i < R * ROWW; i += BLK_THREADS) acc[i] = 0;
             __syncthreads();
             // the rows' own entries (C part) of this tile
+            if (a.dense_c) {
+                for (uint32_t i = tid; i < (uint32_t)R * tw; i += BLK_THREADS) {
+                    const uint32_t r = i / tw, c = i - r * tw;
+                    if (li0 + r < a.n_local) Acc<SMALLP>::set(acc + r * ROWW, c, __ldcs(a.dense_c + (uint64_t)(li0 + r) * a.dense_ld + t0 + c));
+                }
+            } else
             for (uint32_t r = warp; r < (uint32_t)R; r += BLK_WARPS) {
                 const uint32_t li = li0 + r;
                 if (li >= a.n_local) continue;
@@ -273,6 +284,7 @@ __global__ void __launch_bounds__(BLK_THREADS, BLK_CTAS) elim_block_kernel(BlkAr
             }
         }
         // D part: straight into the zeroed D' block
+        if (!a.dense_c)
         for (uint32_t r = warp; r < (uint32_t)R; r += BLK_WARPS) {
             const uint32_t li = li0 + r;
             if (li >= a.n_local) continue;

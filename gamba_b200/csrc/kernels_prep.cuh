@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) prep_fill_kernel(PrepArgs a) {
     uint32_t* cur = sh_cur + warp * nt;
     for (uint32_t b = lane; b < nt; b += 32) cur[b] = a.seg[(uint64_t)b * nr + row];
     __syncwarp();
-    const uint32_t jbits = row < a.L.n_top ? (row % 128u) << 16 : 0u;   // pivot rows: position in their block of 128 rows (low 5 bits: in their window)
+    // position of the row in its block of 128 pivot rows / of 128 rows to reduce (low 5 bits: in its window of 32)
+    const uint32_t jbits = ((row < a.L.n_top ? row : row - a.L.n_top) % 128u) << 16;
     const uint64_t s = a.row_src ? a.row_src[row] : a.row_ptr[row], e = s + (a.row_ptr[row + 1] - a.row_ptr[row]);
     const uint32_t* cf = a.pool + a.coeff_off[a.coeff_id[row]];
     const uint32_t lt = (1u << lane) - 1u;

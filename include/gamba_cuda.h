@@ -168,9 +168,9 @@ typedef struct gamba_cuda_counters {
     uint64_t fma_applied;              /* multiply-adds the elimination kernel did, last step   */
     uint64_t fma_top;                  /* matrix invariant of SURVEY.md §8(d): sum over pivot hits of
                                           nnz(pivot row), this rank's rows, last step              */
-    uint32_t mc_combinations;          /* Monte-Carlo mode: combinations eliminated by the last step (0 = the
-                                          step ran exactly)                                         */
-    uint32_t mc_attempts;              /* ... and how many draws it took to meet the rank margin      */
+    uint32_t mc_combinations;          /* Monte-Carlo combinations eliminated by the last step instead of its rows
+                                          (0 = the step ran on the rows themselves)                 */
+    uint32_t mc_attempts;              /* ... and how many draws it took to meet the rank margin (the exact run counts) */
     double seconds_stage_last;         /* wall time of the last staging: H2D (or broadcast) + staging kernels */
     double seconds_sparse_last;        /* CUDA-event time of elim_kernel alone (the sparse triangular solve), last step */
     double seconds_schur_last;         /* ... of the tensor-core product D' = D + M B (limb planes + schur kernel)     */
@@ -234,8 +234,13 @@ int gamba_cuda_measure_int8_peak(uint32_t device, uint32_t n, double* tmacs_per_
    "mc_ech" (default 1: the echelon runs on K = predicted rank + margin random combinations of the rows of D', formed on the
    tensor cores, and is accepted only if K - rank >= 32 - otherwise it is repeated on the rows themselves; the result is the
    canonical RREF either way; "rank_hint" sets the prediction),
-   "mc" (default 0: exact; 1: Monte-Carlo combinations of the rows to reduce, accepted only with a rank
-   margin of 32 — see DESIGN.md), "mc_k" (combinations, 0 = automatic), "rank_hint" (expected rank of D'). */
+   "mc" (Monte-Carlo combinations of the rows to reduce, the reference's "Monte-Carlo F4" (README.md:5; the seed of
+   linalg_v3{field, seed}, source/f4.hpp:66): K = predicted rank + margin uniform combinations S (C|D) are eliminated
+   instead of the n_bot rows, accepted only if K - rank >= 32, topped up with as many again otherwise, and given up for
+   the rows themselves at n_bot / 2 - the result is the canonical RREF either way, DESIGN.md §5.7. 0 never; 1 (default)
+   on steps with >= "mc_min_top" (default 8192) pivot rows whose predicted K is at most n_bot / 2; 2 on every step a
+   blocked solve runs on), "mc_k" (first draw, 0 = from the prediction), "rank_hint" (expected rank of D'; default: the
+   previous step's). fma_top counts the combinations, not the rows, on steps where mc_combinations > 0. */
 int gamba_cuda_set_option(gamba_cuda_engine* e, const char* key, int64_t value);
 
 #ifdef __cplusplus

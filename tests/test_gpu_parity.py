@@ -207,26 +207,65 @@ def test_full_size_properties(built, p):
     eng.close()
 
 
-def test_monte_carlo_mode_is_bit_exact(step_dirs):
-    """Option "mc": random combinations of the rows to reduce are eliminated instead of the rows themselves
-    (README.md:5 of the reference: "Monte-Carlo F4"); accepted only with a rank margin, so the canonical
-    RREF is the one of the exact computation."""
+def mc_engine(p, mode):
+    """Monte-Carlo combinations need one of the blocked solves: forced here on steps far below the sizes where the cost model picks them."""
     from gamba_b200 import LinalgEngine
-    eng = LinalgEngine(32003)
-    eng.set_option("mc", 1)
-    d = step_dirs("cyclic8-15", ("--dump-min-nnz", "100000"))
-    assert check_dir(d, eng) >= 5
-    used = 0
-    for f in sorted(glob.glob(os.path.join(d, "step_*.bin"))):
+    eng = LinalgEngine(p)
+    eng.set_option("schur_min_top", 1)
+    eng.set_option("mc", 2)
+    if mode == "panel":
+        eng.set_option("panel", 2); eng.set_option("panel_t", 128)
+    else:
+        eng.set_option("panel", 0); eng.set_option("block", 2)
+    return eng
+
+
+@pytest.mark.parametrize("mode", ["panel", "block"])
+@pytest.mark.parametrize("name", ["cyclic8-15", "cyclic8-31", "kat10-15"])
+def test_monte_carlo_combinations_are_bit_exact(step_dirs, name, mode):
+    """Random combinations S (C|D) of the rows to reduce are eliminated instead of the rows themselves (README.md:5 of the
+    reference: "Monte-Carlo F4"; kernels_mc.cuh), accepted only with a rank margin of 32, so the canonical RREF is the one of
+    the exact computation. rank_hint = the true rank: one draw is enough; rank_hint far too small: the margin test must add
+    combinations (top-up behind the first draw) or send the step back to the rows themselves."""
+    d = step_dirs(name, ("--dump-min-nnz", "100000"))
+    files = [f for f in sorted(glob.glob(os.path.join(d, "step_*.bin"))) if not f.endswith("step_final.bin")]
+    eng = mc_engine(load_step(files[0]).p, mode)
+    used = topped_up = exact = 0
+    for f in files:
         s = load_step(f)
-        if f.endswith("step_final.bin") or s.n_bot < 256:
+        want = load_rows(f.replace("step_", "rows_"))
+        if s.n_bot < 256:
             continue
-        eng.set_option("rank_hint", 8)       # far too small: the margin test must force more combinations
-        assert eng.reduce(s).same_as(load_rows(f.replace("step_", "rows_"))), f
-        c = eng.counters()
-        used += c["mc_combinations"] > 0
-        assert c["mc_attempts"] >= 1
-    assert used > 0
+        for hint in (want.n_new, max(8, want.n_new // 3), 8):
+            eng.set_option("rank_hint", hint)
+            assert eng.reduce(s).same_as(want), (f, hint)
+            assert eng.last["zero_reductions"] == s.n_bot - want.n_new
+            c = eng.counters()
+            assert c["solve_mode"] == (2 if mode == "panel" else 1)
+            used += c["mc_combinations"] > 0 and c["mc_attempts"] == 1
+            topped_up += c["mc_combinations"] > 0 and c["mc_attempts"] > 1
+            exact += c["mc_combinations"] == 0
+            if c["mc_combinations"]:
+                assert c["mc_combinations"] >= want.n_new + 32 and c["mc_combinations"] * 2 <= s.n_bot + 64
+    assert used > 0 and topped_up > 0, (used, topped_up, exact)
+    if name.startswith("cyclic8"):       # step 18: 342 rows of rank 80 - from rank_hint 8 the draws reach half the rows: exact
+        assert exact > 0
+    eng.close()
+
+
+def test_monte_carlo_off_and_final_steps_are_exact(step_dirs):
+    """mc = 0 never draws; the final inter-reduction (rank = number of rows) is never drawn either."""
+    d = step_dirs("cyclic8-15", ("--dump-min-nnz", "100000"))
+    eng = mc_engine(32003, "panel")
+    assert check_dir(d, eng) >= 5                      # includes step_final.bin
+    eng.set_option("mc", 0)
+    for f in sorted(glob.glob(os.path.join(d, "step_*.bin")))[:6]:
+        if f.endswith("step_final.bin"):
+            continue
+        s = load_step(f)
+        eng.set_option("rank_hint", 8)
+        assert eng.reduce(s).same_as(load_rows(f.replace("step_", "rows_")))
+        assert eng.counters()["mc_combinations"] == 0
     eng.close()
 
 
@@ -335,13 +374,6 @@ def test_sparse_path_still_matches_oracle(step_dirs, name):
     eng.set_option("schur", 0)
     assert check_dir(d, eng) >= 5
     assert eng.counters()["schur_macs"] == 0
-    eng.close()
-
-
-def test_schur_with_monte_carlo_combinations(step_dirs):
-    eng = schur_engine(32003, mc=1)
-    d = step_dirs("cyclic8-15", ("--dump-min-nnz", "100000"))
-    assert check_dir(d, eng) >= 5
     eng.close()
 
 
