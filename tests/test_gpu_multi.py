@@ -12,9 +12,13 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,opts", [("cyclic7-31", ""), ("cyclic7-31", "schur_min_top=1,block=2"),
-                                       ("cyclic8-15", "schur_min_top=1,block=2"), ("cyclic8-15", "schur_min_top=1,block=0")])
+                                       ("cyclic8-15", "schur_min_top=1,block=2"), ("cyclic8-15", "schur_min_top=1,block=0"),
+                                       ("cyclic8-15", "schur_min_top=1,panel=2,panel_t=128,mc=2"),
+                                       ("cyclic8-31", "schur_min_top=1,panel=0,block=2,mc=2")])
 def test_two_ranks_match_oracle(step_dirs, name, opts):
-    """Default path, and the tensor-core product with the blocked / row-per-CTA sparse solve on sharded rows."""
+    """Default path, and the tensor-core product with the blocked / row-per-CTA sparse solve on sharded rows; mc=2: Monte-Carlo
+    combinations of the rows (each rank forms and eliminates its share of them; draws that miss the rank margin are topped up
+    behind the gathered block of the earlier ones) in front of either blocked solve."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
