@@ -287,7 +287,7 @@ struct gamba_cuda_engine {
     // solve can run on (64 combinations to start with when no rank is known)
     int64_t opt_mc = 1;
     int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
-    int64_t opt_mc_min_top = 65536;  // mc = 1: steps with fewer pivot rows eliminate the rows themselves (launch-bound: nothing to gain)
+    int64_t opt_mc_min_top = 262144; // mc = 1: steps with fewer pivot rows eliminate the rows themselves (launch-bound: nothing to gain)
     int64_t opt_mc_min_rows = 2560;  // mc = 1: ... and so do steps with fewer rows to reduce
     int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
     uint32_t mc_plan = 0;            // combinations the staged step starts with (choose_layout; 0 = the rows themselves)
@@ -445,7 +445,13 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
             if (opt_panel >= 2 && panel_fits) mode = 2;
             else if (opt_block >= 2 && block_ok) mode = 1;
             else if (use_schur && (have_history || mc)) {
-                if (mc) { mode = est[1] < est[2] ? 1 : 2; if (est[mode] >= 1e30) mode = -1; }
+                if (mc) {
+                    // dense rows: the blocked sparse kernel finds no empty window to skip and pays one shared-memory RED per entry of A
+                    // and combination, the products skip the empty blocks of A (kat15-15, 440 k pivot rows, 1480 combinations:
+                    // 324 ms against ~100 ms; 458 k pivot rows, 120 combinations: 518 ms against 166 ms)
+                    mode = est[2] < 1e30 ? 2 : 1;
+                    if (est[mode] >= 1e30) mode = -1;
+                }
                 else {
                     mode = est[1] < est[0] ? 1 : 0;
                     if (est[2] < est[mode]) mode = 2;
@@ -463,14 +469,14 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // Monte-Carlo combinations: K = predicted rank + margin of them instead of the n_bot rows, when that halves the rows at least
         mc_plan = 0;
         // mc = 1: where it was measured to pay (tools/mc_stats.py, kat15-15 without the pair cap: 2.4-2.8x on the steps with 440-460 k pivot
-        // rows; cyclic9-15, <= 50 k pivot rows and <= 2000 rows: the solve is launch-bound and does not get faster with fewer rows):
-        // many pivot rows, more rows than one wave of the blocked kernel, a quarter of them as combinations at most
+        // rows, nothing at 93 k; cyclic9-15, <= 50 k pivot rows and <= 2000 rows: the solve is launch-bound and does not get faster with fewer rows):
+        // many pivot rows, more rows than the pair cap of a default run leaves (2000), half of them as combinations at most
         const bool mc_auto = n_top >= (uint64_t)std::max<int64_t>(1, opt_mc_min_top) && n_bot >= (uint64_t)std::max<int64_t>(256, opt_mc_min_rows);
         if (opt_mc && !(step_flags & GAMBA_CUDA_STEP_FINAL) && n_bot >= 256 && L.n_nonpiv && (opt_mc >= 2 || mc_auto)) {
             const int64_t pred = opt_mc_k > 0 ? opt_mc_k : last_rank >= 0 ? last_rank + 32 + last_rank / 8 : opt_mc >= 2 ? 64 : -1;
             if (pred > 0) {
                 const uint64_t k = ((uint64_t)pred + 7) / 8 * 8;
-                if (k * (opt_mc >= 2 ? 2 : 4) <= n_bot) mc_plan = (uint32_t)k;
+                if (k * 2 <= n_bot) mc_plan = (uint32_t)k;
             }
         }
         // The choice between combinations and rows must be the same on every rank (the all-gather sizes follow from it): it uses

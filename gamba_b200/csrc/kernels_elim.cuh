@@ -100,6 +100,11 @@ __device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t val) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(val) : "memory");
 }
 
+// the same, skipped when val == 0: a predicated instruction, no branch (the blocked kernels issue 16 of these per lane and chunk)
+__device__ __forceinline__ void red_shared_add_nz(uint32_t saddr, uint32_t val, uint32_t nz) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(saddr), "r"(val), "r"(nz) : "memory");
+}
+
 template <> struct Acc<true> {   // p < 2^16: one u32 lane per column
     static constexpr int WORDS = 1;
     // m*v mod p up to one multiple of p: the result is < 2p (the lane is reduced when it is read)
@@ -108,6 +113,7 @@ template <> struct Acc<true> {   // p < 2^16: one u32 lane per column
         return x + __umulhi(x, a.mu32) * a.negp;        // x - q*p, one IMAD
     }
     static __device__ __forceinline__ void add(uint32_t acc_sa, uint32_t c, uint32_t val) { red_shared_add(acc_sa + c * 4, val); }
+    static __device__ __forceinline__ void add_nz(uint32_t acc_sa, uint32_t val) { red_shared_add_nz(acc_sa, val, val); }
     static __device__ __forceinline__ void set(uint32_t* acc, uint32_t c, uint32_t val) { acc[c] = val; }
     static __device__ __forceinline__ uint32_t get(const uint32_t* acc, uint32_t c, const ElimArgs& a) {
         const uint32_t x = acc[c];
@@ -124,6 +130,10 @@ template <> struct Acc<false> {  // p < 2^31: lo/hi pair of u32 lanes per column
     static __device__ __forceinline__ void add(uint32_t acc_sa, uint32_t c, uint32_t val) {
         red_shared_add(acc_sa + c * 8, val & 0xffffu);
         red_shared_add(acc_sa + c * 8 + 4, val >> 16);
+    }
+    static __device__ __forceinline__ void add_nz(uint32_t acc_sa, uint32_t val) {
+        red_shared_add_nz(acc_sa, val & 0xffffu, val);
+        red_shared_add_nz(acc_sa + 4, val >> 16, val);
     }
     static __device__ __forceinline__ void set(uint32_t* acc, uint32_t c, uint32_t val) {
         acc[2 * c] = val & 0xffffu; acc[2 * c + 1] = val >> 16;

@@ -110,8 +110,8 @@ struct BlkStream {
                 for (int r = 0; r < R; ++r) {                                  // no branches: the R chains interleave
                     const uint32_t m0 = __shfl_sync(0xffffffffu, m[r], j0), m1 = __shfl_sync(0xffffffffu, m[r], j1);
                     const uint32_t v0 = Acc<SMALLP>::mulred(m0, cur.y, ea), v1 = Acc<SMALLP>::mulred(m1, cur.w, ea);
-                    if (m0 && cur.y) Acc<SMALLP>::add(a0 + r * ROWB, 0, v0);
-                    if (m1 && cur.w) Acc<SMALLP>::add(a1 + r * ROWB, 0, v1);
+                    Acc<SMALLP>::add_nz(a0 + r * ROWB, v0);                    // m v mod p is zero iff m or v is (padding entries: v = 0)
+                    Acc<SMALLP>::add_nz(a1 + r * ROWB, v1);
                 }
                 done += __popc(rmask);
             }
