@@ -18,6 +18,8 @@ engine makes from the previous step (kernel choice, predicted rank of the Monte-
   roofline  dominant kernel = limb_gemm_tc_kernel (every dense mod-p product of the elimination stage, tcgen05 kind::i8):
             int8 multiply-adds of all its launches / CUDA-event time of the stage without the operand builds / int8 tensor
             peak MEASURED in the same run (gamba_cuda_measure_int8_peak); the survey's algorithmic-bytes figure (§8(d)) beside it
+            (on the steps that run on Monte-Carlo combinations of their rows the products are smaller by n_bot / K: the fraction
+            says how well the launches that remain use the tensor cores, not how much work was avoided)
   cpu_baseline  the CPU oracle (a port: the reference's engine is closed source), single thread, on a bounded sample
   parity_check  untimed: every matrix reduced once more by an independent configuration on rank 0 (N > 1: a world_size = 1
             engine; N = 1: the sparse-kernel path, panel = 0) and compared by checksum
@@ -411,7 +413,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     def collect(gi, si, e):
         c = e.counters()
         per[(gi, si)] = (e.last["seconds_eliminate"], e.last["seconds_echelon"], e.last["seconds_device"], c["fma_top"],
-                         c["dense_macs"], c["seconds_operands_last"], c["solve_mode"], c["seconds_sparse_last"])
+                         c["dense_macs"], c["seconds_operands_last"], c["solve_mode"], c["seconds_sparse_last"], c["mc_combinations"])
     l0 = launches()
     with ClockSampler(local_rank) as clk:
         sync()
@@ -484,7 +486,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if lib.gamba_cuda_measure_int8_peak(local_rank, peak_n, C.byref(pk)):
             raise RuntimeError("gamba_cuda_measure_int8_peak: " + lib.gamba_cuda_last_error().decode())
         int8_peak = pk.value                                         # TMAC/s
-        elim, ech, dev, fma_top, dense, opnd, mode, sparse = (vals[:, i] for i in range(8))
+        elim, ech, dev, fma_top, dense, opnd, mode, sparse, mc_k = (vals[:, i] for i in range(9))
         gemm_s = float(np.sum(np.where(mode == 2, elim - opnd, np.maximum(elim - sparse - opnd, 0.0))))   # the products' share of the stage
         int8_macs = float(np.sum(dense * nl2))
         achieved_tops = 2.0 * int8_macs / max(gemm_s, 1e-12) / 1e12 / world          # per GPU
@@ -501,7 +503,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                        f"NCCL all-gather of D' rows, echelon replicated") if world > 1 else "1 GPU",
                        "matrices_per_step": n_mat, "nnz_per_step": total_nnz,
                        "solve_modes": {"sparse": int(np.sum(mode == 0)), "sparse_blocked": int(np.sum(mode == 1)),
-                                       "tensor_core_blocked_solve": int(np.sum(mode == 2))}},
+                                       "tensor_core_blocked_solve": int(np.sum(mode == 2))},
+                       "monte_carlo": {"matrices": int(np.sum(mc_k > 0)), "combinations": int(np.sum(mc_k)),
+                                       "rows_they_replace": int(sum(s.n_bot for s, k in zip(steps_flat, mc_k) if k > 0)),
+                                       "note": "steps whose rows to reduce were replaced by K = predicted rank + margin random combinations "
+                                               "(kernels_mc.cuh; accepted only with K - rank >= 32, result bit-exact)"}},
             "e2e": {"value": total_nnz * e2e_steps / t_e2e, "unit": "nnz/s", "h2d_bytes_per_step": h2d // e2e_steps,
                     "d2h_bytes_per_step": d2h // e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": n_launch,

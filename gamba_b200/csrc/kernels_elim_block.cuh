@@ -92,6 +92,9 @@ struct BlkStream {
             pos += step;
         }
     }
+    // DENSE: the multipliers are non-zero (Monte-Carlo combinations): every product is added without a test - a zero only costs a RED
+    // of 0 into the column (padding entries: into the sink lane), a test costs a branch around every RED
+    template <bool DENSE = false>
     __device__ __forceinline__ unsigned long long run(uint32_t acc_sa, const ElimArgs& ea, const uint2* ent, const uint32_t (&m)[R],
                                                       uint32_t rmask, uint32_t sink) {
         unsigned long long done = 0;
@@ -110,8 +113,11 @@ struct BlkStream {
                 for (int r = 0; r < R; ++r) {                                  // no branches: the R chains interleave
                     const uint32_t m0 = __shfl_sync(0xffffffffu, m[r], j0), m1 = __shfl_sync(0xffffffffu, m[r], j1);
                     const uint32_t v0 = Acc<SMALLP>::mulred(m0, cur.y, ea), v1 = Acc<SMALLP>::mulred(m1, cur.w, ea);
-                    Acc<SMALLP>::add_nz(a0 + r * ROWB, v0);                    // m v mod p is zero iff m or v is (padding entries: v = 0)
-                    Acc<SMALLP>::add_nz(a1 + r * ROWB, v1);
+                    if (DENSE) { Acc<SMALLP>::add(a0 + r * ROWB, 0, v0); Acc<SMALLP>::add(a1 + r * ROWB, 0, v1); }
+                    else {
+                        Acc<SMALLP>::add_nz(a0 + r * ROWB, v0);                // m v mod p is zero iff m or v is (padding entries: v = 0)
+                        Acc<SMALLP>::add_nz(a1 + r * ROWB, v1);
+                    }
                 }
                 done += __popc(rmask);
             }

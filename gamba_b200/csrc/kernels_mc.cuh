@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(BLK_THREADS, BLK_CTAS) mc_rows_kernel(McRowsAr
             for (int r = 0; r < R; ++r) rmask |= __ballot_sync(0xffffffffu, m[r] != 0) ? 1u << r : 0u;
             BlkStream<SMALLP, R> st;
             st.start(a.ent, s, e, 0, 1, lane, T);
-            st.run(acc_sa, ea, a.ent, m, rmask, T);
+            st.template run<true>(acc_sa, ea, a.ent, m, rmask, T);
         }
         __syncthreads();
         for (uint32_t i = tid; i < (uint32_t)R * tw; i += BLK_THREADS) {
