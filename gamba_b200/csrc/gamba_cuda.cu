@@ -230,7 +230,9 @@ struct gamba_cuda_engine {
     int64_t opt_elim_warps = 0;      // 4 or 8 warps per row to reduce (0 = automatic)
     int elim_warps = 8;
     int64_t opt_coeff_cache = 0;     // keep coefficient arrays on the device across steps (caller: immutable arrays)
-    std::unordered_map<const void*, std::pair<uint64_t, uint32_t>> cache;   // host pointer -> (offset in d_pool, length)
+    struct CacheEntry { uint64_t off; uint32_t len, first, last; };          // offset in d_pool, length, first and last coefficient
+    std::unordered_map<const void*, CacheEntry> cache;                       // keyed by host pointer; an array whose length or end
+                                                                             // coefficients changed (address reused) is uploaded again
     uint64_t cache_used = 0;
     int64_t opt_schur = 1;           // 1: D' = D + M B on the tensor cores when the limb planes fit, 0: sparse path
     int64_t opt_panel = 1;           // 1 (when it is predicted to pay) / 2 (always): blocked triangular solve on the tensor cores
@@ -569,9 +571,15 @@ void gamba_cuda_engine::stage(const gamba_cuda_step_in* in) {
         fresh.reserve(na);
         for (uint32_t i = 0; i < na; ++i) {
             auto it = cache.find(in->coeff_ptr[i]);
-            if (it != cache.end() && it->second.second >= in->coeff_len[i]) { off[i] = it->second.first; continue; }
-            off[i] = cache_used + tot; tot += in->coeff_len[i];
-            cache[in->coeff_ptr[i]] = {off[i], in->coeff_len[i]};
+            const uint32_t n_i = in->coeff_len[i];
+            auto word = [&](uint32_t k) -> uint32_t {
+                return cfg.coeff_bytes == 4 ? ((const uint32_t*)in->coeff_ptr[i])[k] : cfg.coeff_bytes == 2 ? ((const uint16_t*)in->coeff_ptr[i])[k]
+                                                                                                          : ((const uint8_t*)in->coeff_ptr[i])[k];
+            };
+            const uint32_t w0 = n_i ? word(0) : 0u, w1 = n_i ? word(n_i - 1) : 0u;
+            if (it != cache.end() && it->second.len == n_i && it->second.first == w0 && it->second.last == w1) { off[i] = it->second.off; continue; }
+            off[i] = cache_used + tot; tot += n_i;
+            cache[in->coeff_ptr[i]] = CacheEntry{off[i], n_i, w0, w1};
             fresh.push_back(i);
         }
         off[na] = cache_used + tot;
