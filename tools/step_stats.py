@@ -13,7 +13,7 @@ from gamba_b200 import LinalgEngine, load_step  # noqa: E402
 def main():
     system, min_nnz = sys.argv[1], int(sys.argv[2])
     opts = [kv.split("=") for kv in sys.argv[3:]]
-    files = bench.generate_workload(system, min_nnz, 0, 1)
+    files = bench.generate_workload(system, 2000, min_nnz, 0, 1)
     if os.environ.get("STEP_STATS_MAX"):
         files = files[: int(os.environ["STEP_STATS_MAX"])]
     eng = None
