@@ -395,7 +395,11 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
     uint32_t ctas = 4;
     elim_warps = ELIM_CTA_WARPS;
     if (opt_ctas_per_sm > 0) { ctas = (uint32_t)opt_ctas_per_sm; elim_warps = ctas > 8 ? 4 : ELIM_CTA_WARPS; }
-    if (opt_elim_warps == 2 || opt_elim_warps == 4 || opt_elim_warps == 8) elim_warps = (int)opt_elim_warps;
+    // fewer rows than SMs against many pivot rows (kat15-15: 13 rows, 410 k pivots, 88 % of them hit): a row is ONE CTA, and a warp
+    // retires a 64-entry chunk per ~450 cycles of instruction latency whatever is in flight - so 32 warps share the row's stream
+    if (opt_ctas_per_sm <= 0 && (uint64_t)(n_bot + std::max(1u, cfg.world_size) - 1) / std::max(1u, cfg.world_size) * 2 <= (uint64_t)prop.multiProcessorCount && n_top >= 65536)
+        elim_warps = 32;
+    if (opt_elim_warps == 2 || opt_elim_warps == 4 || opt_elim_warps == 8 || opt_elim_warps == 32) elim_warps = (int)opt_elim_warps;
     ctas = std::min<uint32_t>(ctas, 64u / elim_warps);
     const size_t per_cta = std::min<size_t>(((size_t)smem_per_sm / ctas) - 1024 - 64, (size_t)max_smem_optin - 64);
     const uint32_t words_per_col = f.small ? 1u : 2u;   // kernels_elim.cuh: Acc<SMALLP>::WORDS
@@ -484,7 +488,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // The choice between combinations and rows must be the same on every rank (the all-gather sizes follow from it): it uses
         // sizes, options and the previous step's rank only - never the calibration factors, which are rank-local timings.
         double t_mc = 1e30, t_exact = 1e30;
-        int mode = mc_plan ? decide(mc_plan, true, t_mc, true) : -1;
+        int mode = mc_plan ? decide(mc_plan, true, t_mc, false) : -1;      // no runner-up runs on combinations: the sparse solve loses 150-280 ms there
         if (mode < 0) { mc_plan = 0; mode = decide(n_bot, false, t_exact, true); }
         use_block = mode == 1; use_panel = mode == 2;
         if (use_block) tmax = BLK_TMAX;
@@ -743,7 +747,8 @@ void gamba_cuda_engine::eliminate() {
     const size_t acc_words = (((size_t)L.tile_cols + 1) * words_per_col + 3) & ~(size_t)3;
     const size_t smem = (acc_words + (size_t)elim_warps * ELIM_SCRATCH_WORDS) * sizeof(uint32_t);
     const int elim_threads = elim_warps * 32;
-    auto kern = elim_warps == 2 ? (f.small ? elim_kernel<true, 2> : elim_kernel<false, 2>)
+    auto kern = elim_warps == 32 ? (f.small ? elim_kernel<true, 32> : elim_kernel<false, 32>)
+              : elim_warps == 2 ? (f.small ? elim_kernel<true, 2> : elim_kernel<false, 2>)
               : elim_warps == 4 ? (f.small ? elim_kernel<true, 4> : elim_kernel<false, 4>)
                                 : (f.small ? elim_kernel<true, 8> : elim_kernel<false, 8>);
     const uint32_t nl = f.small ? 2u : 4u;

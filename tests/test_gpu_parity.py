@@ -78,6 +78,23 @@ def test_forced_small_tiles_exercise_deferred_passes(step_dirs, tile):
     eng.close()
 
 
+@pytest.mark.parametrize("warps", [2, 4, 32])
+@pytest.mark.parametrize("name", ["cyclic7-15", "cyclic7-31"])
+def test_warps_per_row_of_the_sparse_kernel(step_dirs, name, warps):
+    """elim_kernel with 2 / 4 / 32 warps sharing a row (default 8; 32 is what steps with fewer rows than SMs against >= 65536
+    pivot rows get: one CTA per row, and a warp retires a chunk per ~450 cycles whatever is in flight), with and without the
+    tensor-core product for the B half."""
+    from gamba_b200 import LinalgEngine
+    d = step_dirs(name)
+    p = load_step(sorted(glob.glob(os.path.join(d, "step_*.bin")))[0]).p
+    for schur_min_top in (1, 1 << 30):
+        eng = LinalgEngine(p)
+        eng.set_option("elim_warps", warps); eng.set_option("schur_min_top", schur_min_top); eng.set_option("panel", 0); eng.set_option("block", 0)
+        assert check_dir(d, eng) > 0
+        assert eng.counters()["solve_mode"] == 0
+        eng.close()
+
+
 def test_elimination_order_and_blockelim_steps(step_dirs, engines):
     d = step_dirs("cyclic5-15", ("-e", "2"))
     assert check_dir(d, engines(32003)) > 0
