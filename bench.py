@@ -549,11 +549,14 @@ def cpu_baseline(groups, args):
     from oracle import oracle
     oracle.build()
     name, _, steps = groups[0]
-    cand = [s for s in steps if s.nnz >= 1_000_000] or steps
-    s = min(cand, key=lambda x: x.nnz * x.n_bot)
-    _, fma, sec = oracle.reduce(thin_step(s, 16) if s.n_bot >= 64 else s)
-    every = max(1, int(np.ceil(sec * 16 / args.cpu_seconds))) if s.n_bot >= 64 else 1
-    sample = thin_step(s, every)
+    # the matrix of the first system with the most work (nnz x rows to reduce), thinned so that the sample costs about cpu_seconds:
+    # calibrated on every 64th of its rows (all pivot rows stay: the cost of a row to reduce does not depend on how many others there are)
+    s = max(steps, key=lambda x: x.nnz * x.n_bot)
+    every = 1
+    if s.n_bot >= 128:
+        _, _, sec64 = oracle.reduce(thin_step(s, 64))
+        every = max(1, min(64, int(np.ceil(sec64 * 64 / args.cpu_seconds))))
+    sample = thin_step(s, every) if every > 1 else s
     _, fma, sec = oracle.reduce(sample)
     return {"value": sample_nnz(s, sample) / sec, "unit": "nnz/s", "cores": 1, "kind": "port", "cpu": cpu_model(),
             "sample": f"{name} F4 step {s.n_rows}x{s.n_cols} ({s.nnz} nnz), all pivot rows + every {every}-th of the {s.n_bot} rows to "
