@@ -688,15 +688,25 @@ void F4::export_basis(PolySystem& out) const {
     std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
         return cx_.cmp(bt_.e(G_[a].mon[0]), bt_.e(G_[b].mon[0])) < 0;
     });
-    for (uint32_t i : idx) {
-        const Poly& f = G_[i];
-        out.lens.push_back((uint32_t)f.mon.size());
-        for (size_t k = 0; k < f.mon.size(); ++k) {
-            out.coeffs.push_back(f.cf[k]);
-            const uint16_t* e = bt_.e(f.mon[k]);
-            out.exps.insert(out.exps.end(), e + 2, e + 2 + cx_.nv);
+    // kat15-15: 8 k generators, ~10^8 terms - filled in parallel at precomputed offsets
+    const size_t ng = idx.size(), nv = cx_.nv;
+    std::vector<size_t> off(ng + 1, 0);
+    out.lens.resize(ng);
+    for (size_t g = 0; g < ng; ++g) { out.lens[g] = (uint32_t)G_[idx[g]].mon.size(); off[g + 1] = off[g] + out.lens[g]; }
+    out.coeffs.resize(off[ng]);
+    out.exps.resize(off[ng] * nv);
+    pool_->parallel_for(ng, 1, [&](size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; ++g) {
+            const Poly& f = G_[idx[g]];
+            uint32_t* cf = out.coeffs.data() + off[g];
+            uint16_t* ex = out.exps.data() + off[g] * nv;
+            for (size_t k = 0; k < f.mon.size(); ++k) {
+                cf[k] = f.cf[k];
+                const uint16_t* e = bt_.e(f.mon[k]);
+                std::copy(e + 2, e + 2 + nv, ex + k * nv);
+            }
         }
-    }
+    });
 }
 
 }  // namespace gb

@@ -1,5 +1,9 @@
 #include "io.hpp"
 
+#include <atomic>
+#include <charconv>
+#include <thread>
+
 #include <algorithm>
 #include <cctype>
 #include <istream>
@@ -187,36 +191,71 @@ void PolySystem::read(std::istream& in) {
     }
 }
 
+// One generator as text (source/io.cpp:375-449: terms joined by '+', coefficient 1 left out, exponent 1 left out).
+static void format_generator(std::string& buf, const PolySystem& s, size_t off, size_t len, bool last) {
+    const size_t nv = s.vars.size();
+    char num[16];
+    auto put = [&](uint32_t v) { auto r = std::to_chars(num, num + sizeof num, v); buf.append(num, r.ptr); };
+    for (size_t j = 0; j < len; ++j) {
+        const uint32_t cf = s.coeffs[off + j];
+        if (cf == 0) continue;
+        bool star = false;
+        if (cf != 1) { put(cf); star = true; }
+        bool any = false;
+        const uint16_t* ex = s.exps.data() + (off + j) * nv;
+        for (size_t k = 0; k < nv; ++k) {
+            const uint16_t e = ex[k];
+            if (!e) continue;
+            if (star || any) buf += '*';
+            buf += s.vars[k];
+            if (e > 1) { buf += '^'; put(e); }
+            any = true;
+        }
+        if (!any && cf == 1) buf += '1';
+        if (j + 1 != len && s.coeffs[off + j + 1] > 0) buf += '+';
+    }
+    if (!last) buf += ',';
+    buf += '\n';
+}
+
+// The basis of kat15-15 is 1.5 GB of text: generators are formatted by all host threads into per-chunk buffers (chunks of
+// about equal numbers of terms, handed out dynamically) and written in order; a small system takes the serial path.
 void PolySystem::write(std::ostream& out) const {
     for (auto const& v : vars) out << v << ",";
     out << "\n" << p << "\n";
-    const size_t nv = vars.size(), ng = lens.size();
-    size_t off = 0;
-    std::string buf;
-    for (size_t g = 0; g < ng; ++g) {
-        buf.clear();
-        for (size_t j = 0; j < lens[g]; ++j) {
-            uint32_t cf = coeffs[off + j];
-            if (cf == 0) continue;
-            bool star = false;
-            if (cf != 1) { buf += std::to_string(cf); star = true; }
-            bool any = false;
-            for (size_t k = 0; k < nv; ++k) {
-                uint16_t e = exps[(off + j) * nv + k];
-                if (!e) continue;
-                if (star || any) buf += '*';
-                buf += vars[k];
-                if (e > 1) { buf += '^'; buf += std::to_string(e); }
-                any = true;
-            }
-            if (!any && cf == 1) buf += '1';
-            if (j + 1 != lens[g] && coeffs[off + j + 1] > 0) buf += '+';
-        }
-        if (g + 1 != ng) buf += ',';
-        buf += '\n';
-        out << buf;
-        off += lens[g];
+    const size_t ng = lens.size();
+    std::vector<size_t> off(ng + 1, 0);
+    for (size_t g = 0; g < ng; ++g) off[g + 1] = off[g] + lens[g];
+    const size_t terms = off[ng];
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (terms < 200000 || hw == 1) {
+        std::string buf;
+        for (size_t g = 0; g < ng; ++g) { buf.clear(); format_generator(buf, *this, off[g], lens[g], g + 1 == ng); out << buf; }
+        out.flush();
+        return;
     }
+    // chunk boundaries: ~8 chunks per thread, cut at generator boundaries
+    const size_t n_chunks = std::min<size_t>(ng, (size_t)hw * 8), per = (terms + n_chunks - 1) / n_chunks;
+    std::vector<size_t> cut{0};
+    for (size_t g = 0; g < ng; ++g)
+        if (off[g + 1] >= cut.size() * per || g + 1 == ng) cut.push_back(g + 1);
+    const size_t nc = cut.size() - 1;
+    std::vector<std::string> bufs(nc);
+    std::atomic<size_t> next{0};
+    auto worker = [&] {
+        for (;;) {
+            const size_t c = next.fetch_add(1);
+            if (c >= nc) break;
+            std::string& b = bufs[c];
+            b.reserve((off[cut[c + 1]] - off[cut[c]]) * 20 + 64);
+            for (size_t g = cut[c]; g < cut[c + 1]; ++g) format_generator(b, *this, off[g], lens[g], g + 1 == ng);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < hw; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    for (size_t c = 0; c < nc; ++c) { out.write(bufs[c].data(), (std::streamsize)bufs[c].size()); std::string().swap(bufs[c]); }
     out.flush();
 }
 
