@@ -290,7 +290,8 @@ struct gamba_cuda_engine {
     int64_t opt_mc = 1;
     int64_t opt_mc_k = 0;            // number of combinations (0 = automatic)
     int64_t opt_mc_min_top = 262144; // mc = 1: steps with fewer pivot rows eliminate the rows themselves (launch-bound: nothing to gain)
-    int64_t opt_mc_min_rows = 2560;  // mc = 1: ... and so do steps with fewer rows to reduce
+    int64_t opt_mc_min_rows = 256;   // mc = 1: ... and so do steps with fewer rows to reduce (with >= 262144 pivot rows the solve has a floor of
+                                     // ~0.7 ms per pivot tile whatever the rows: 1013 rows of rank 13 against 453 k pivots took 728 ms in elim_kernel)
     int64_t last_rank = -1;          // rank of D' of the previous step (predictor for the number of combinations)
     uint32_t mc_plan = 0;            // combinations the staged step starts with (choose_layout; 0 = the rows themselves)
     uint32_t mc_k = 0;               // combinations the current elimination works on (0 = exact)
@@ -476,7 +477,7 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         mc_plan = 0;
         // mc = 1: where it was measured to pay (tools/mc_stats.py, kat15-15 without the pair cap: 2.4-2.8x on the steps with 440-460 k pivot
         // rows, nothing at 93 k; cyclic9-15, <= 50 k pivot rows and <= 2000 rows: the solve is launch-bound and does not get faster with fewer rows):
-        // many pivot rows, more rows than the pair cap of a default run leaves (2000), half of them as combinations at most
+        // many pivot rows, half of the rows as combinations at most
         const bool mc_auto = n_top >= (uint64_t)std::max<int64_t>(1, opt_mc_min_top) && n_bot >= (uint64_t)std::max<int64_t>(256, opt_mc_min_rows);
         if (opt_mc && !(step_flags & GAMBA_CUDA_STEP_FINAL) && n_bot >= 256 && L.n_nonpiv && (opt_mc >= 2 || mc_auto)) {
             const int64_t pred = opt_mc_k > 0 ? opt_mc_k : last_rank >= 0 ? last_rank + 32 + last_rank / 8 : opt_mc >= 2 ? 64 : -1;

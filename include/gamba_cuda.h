@@ -238,7 +238,7 @@ int gamba_cuda_measure_int8_peak(uint32_t device, uint32_t n, double* tmacs_per_
    linalg_v3{field, seed}, source/f4.hpp:66): K = predicted rank + margin uniform combinations S (C|D) are eliminated
    instead of the n_bot rows, accepted only if K - rank >= 32, topped up with as many again otherwise, and given up for
    the rows themselves at n_bot / 2 - the result is the canonical RREF either way, DESIGN.md §5.7. 0 never; 1 (default)
-   on steps with >= "mc_min_top" (default 262144) pivot rows and >= "mc_min_rows" (default 2560) rows to reduce whose
+   on steps with >= "mc_min_top" (default 262144) pivot rows and >= "mc_min_rows" (default 256) rows to reduce whose
    predicted K is at most n_bot / 2; 2 on every step with K <= n_bot / 2 that a
    blocked solve runs on), "mc_k" (first draw, 0 = from the prediction), "rank_hint" (expected rank of D'; default: the
    previous step's).
