@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cstdlib>
 #include <istream>
 #include <numeric>
 #include <ostream>
@@ -227,7 +228,8 @@ void PolySystem::write(std::ostream& out) const {
     std::vector<size_t> off(ng + 1, 0);
     for (size_t g = 0; g < ng; ++g) off[g + 1] = off[g] + lens[g];
     const size_t terms = off[ng];
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* wt = std::getenv("GAMBA_WRITE_THREADS")) hw = (unsigned)std::max(1, std::atoi(wt));     // 1 = the serial path (tests)
     if (terms < 200000 || hw == 1) {
         std::string buf;
         for (size_t g = 0; g < ng; ++g) { buf.clear(); format_generator(buf, *this, off[g], lens[g], g + 1 == ng); out << buf; }

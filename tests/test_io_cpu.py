@@ -70,3 +70,19 @@ def test_zero_and_one_ideal(drv, tmp_path):
     assert r.returncode == 0 and out == "x,y,\n7\n"
     r, out = run(drv, "x,y\n7\nx,\nx-1\n", tmp_path)
     assert r.returncode == 0 and out == "x,y,\n7\n1\n"
+
+
+def test_parallel_writer_equals_the_serial_one(drv, tmp_path):
+    """A basis of more than 200 k terms (kat11-15: 383 k) is formatted by all host threads into per-chunk buffers
+    (gamba_b200/host/io.cpp); GAMBA_WRITE_THREADS=1 takes the serial path. Same bytes."""
+    import os
+    from gamba_b200 import systems
+    inp = systems.write_system("kat11-15", str(tmp_path / "kat11.txt"))
+    outs = []
+    for threads in ("1", "5"):
+        out = tmp_path / f"out{threads}.txt"
+        r = subprocess.run([drv, "-i", inp, "-o", str(out), "-v", "0"], capture_output=True, text=True,
+                           env=dict(os.environ, GAMBA_WRITE_THREADS=threads, GAMBA_ORACLE_THREADS="8"))
+        assert r.returncode == 0, r.stderr
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] and outs[0].count(b"+") + outs[0].count(b",") > 200000
