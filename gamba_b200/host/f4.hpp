@@ -98,6 +98,7 @@ private:
 
     void import_generators();
     void update(uint32_t h);
+    void update_batch(size_t from);
     void update_all(size_t from);
     long select_pairs(int32_t& deg);
     void clear_step();
