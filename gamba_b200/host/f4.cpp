@@ -720,18 +720,30 @@ void F4::insert_new_rows() {
     // monomial enters the basis table once, the terms index that map
     constexpr uint32_t UNSET = 0xffffffffu;
     std::vector<uint32_t> col2bt(nonpiv_col_.size(), UNSET);
-    for (uint32_t r = 0; r < R_.n_new; ++r) {
-        Poly f;
-        uint64_t a = R_.row_ptr[r], b = R_.row_ptr[r + 1];
-        f.mon.resize(b - a); f.cf.assign(R_.val.begin() + a, R_.val.begin() + b);
-        for (uint64_t k = a; k < b; ++k) {
-            const uint32_t c = R_.col[k], h = order_[nonpiv_col_[c]];
-            if (col2bt[c] == UNSET) col2bt[c] = bt_.insert(st_.e(h), st_.hv[h]);
-            f.mon[k - a] = col2bt[c];
-            f.deg = std::max<uint32_t>(f.deg, st_.e(h)[0]);
+    std::vector<uint8_t> used(nonpiv_col_.size(), 0);
+    pool_->parallel_for(R_.n_new, 1, [&](size_t r0, size_t r1) {
+        for (uint64_t k = R_.row_ptr[r0]; k < R_.row_ptr[r1]; ++k) __atomic_store_n(&used[R_.col[k]], (uint8_t)1, __ATOMIC_RELAXED);
+    });
+    for (size_t c = 0; c < used.size(); ++c)
+        if (used[c]) { const uint32_t h = order_[nonpiv_col_[c]]; col2bt[c] = bt_.insert(st_.e(h), st_.hv[h]); }
+    // the polynomials themselves (up to 10^8 terms in a step of kat15-15) are filled by all threads
+    std::vector<Poly> fs(R_.n_new);
+    pool_->parallel_for(R_.n_new, 1, [&](size_t r0, size_t r1) {
+        for (size_t r = r0; r < r1; ++r) {
+            Poly& f = fs[r];
+            const uint64_t a = R_.row_ptr[r], b = R_.row_ptr[r + 1];
+            f.mon.resize(b - a); f.cf.assign(R_.val.begin() + a, R_.val.begin() + b);
+            for (uint64_t k = a; k < b; ++k) {
+                const uint32_t c = R_.col[k];
+                f.mon[k - a] = col2bt[c];
+                f.deg = std::max<uint32_t>(f.deg, st_.e(order_[nonpiv_col_[c]])[0]);
+            }
+            if (b > a) f.lm_mask = cx_.divmask(bt_.e(f.mon[0]));
         }
-        if (f.cf[0] != 1) throw std::logic_error("engine returned a non-monic row");
-        f.lm_mask = cx_.divmask(bt_.e(f.mon[0]));
+    });
+    for (uint32_t r = 0; r < R_.n_new; ++r) {
+        Poly& f = fs[r];
+        if (f.cf.empty() || f.cf[0] != 1) throw std::logic_error("engine returned a non-monic row");
         if (bt_.e(f.mon[0])[0] == 0) { make_trivial(); break; }
         G_.push_back(std::move(f));
     }

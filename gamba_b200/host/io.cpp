@@ -242,7 +242,11 @@ void PolySystem::write(std::ostream& out) const {
     for (size_t g = 0; g < ng; ++g)
         if (off[g + 1] >= cut.size() * per || g + 1 == ng) cut.push_back(g + 1);
     const size_t nc = cut.size() - 1;
+    // workers take the chunks in order; this thread writes every chunk as soon as it is complete (formatting and the write of
+    // the 2 GB file overlap), then frees it
     std::vector<std::string> bufs(nc);
+    std::vector<std::atomic<int>> ready(nc);
+    for (auto& r : ready) r.store(0, std::memory_order_relaxed);
     std::atomic<size_t> next{0};
     auto worker = [&] {
         for (;;) {
@@ -251,13 +255,17 @@ void PolySystem::write(std::ostream& out) const {
             std::string& b = bufs[c];
             b.reserve((off[cut[c + 1]] - off[cut[c]]) * 20 + 64);
             for (size_t g = cut[c]; g < cut[c + 1]; ++g) format_generator(b, *this, off[g], lens[g], g + 1 == ng);
+            ready[c].store(1, std::memory_order_release);
         }
     };
     std::vector<std::thread> th;
-    for (unsigned t = 1; t < hw; ++t) th.emplace_back(worker);
-    worker();
+    for (unsigned t = 0; t + 1 < hw; ++t) th.emplace_back(worker);
+    for (size_t c = 0; c < nc; ++c) {
+        while (!ready[c].load(std::memory_order_acquire)) std::this_thread::yield();
+        out.write(bufs[c].data(), (std::streamsize)bufs[c].size());
+        std::string().swap(bufs[c]);
+    }
     for (auto& t : th) t.join();
-    for (size_t c = 0; c < nc; ++c) { out.write(bufs[c].data(), (std::streamsize)bufs[c].size()); std::string().swap(bufs[c]); }
     out.flush();
 }
 
