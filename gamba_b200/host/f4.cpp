@@ -355,7 +355,8 @@ void F4::update_batch(size_t from) {
 void F4::update_all(size_t from) {
     double t0 = now_s();
     // a few new generators: one at a time, each with all threads; a batch of them: all at once, one thread each
-    if (G_.size() - from >= 8 && nthreads_ > 1) update_batch(from);
+    static const bool batch = [] { const char* e = std::getenv("GAMBA_UPDATE_BATCH"); return !e || std::atoi(e) != 0; }();     // 0: tests
+    if (batch && G_.size() - from >= 8 && nthreads_ > 1) update_batch(from);
     else for (size_t h = from; h < G_.size(); ++h) update((uint32_t)h);
     stats.t_update += now_s() - t0;
 }

@@ -57,3 +57,24 @@ def test_large_synthetic_matches_oracle_rank(built):
     s = synthetic_step_large(2500, 4000, 0.01, 32003, seed=5)
     rows, fma_top, _ = oracle.reduce(s)
     assert rows.n_new == min(s.n_bot, s.n_nonpiv) and fma_top > 0      # random rows: full rank
+
+
+@pytest.mark.parametrize("name,extra", [("cyclic7-15", ()), ("kat10-15", ("--max-spairs", "0")), ("eco10-31", ())])
+def test_batched_pair_update_equals_one_at_a_time(built, tmp_path, name, extra):
+    """F4::update_batch installs a step's new generators as one batch over all host threads (Gebauer-Moeller criteria,
+    reference source/update.hpp:29-269); GAMBA_UPDATE_BATCH=0 installs them one at a time. Same queue: same steps, pairs,
+    criteria counts and basis."""
+    import os
+    import re
+    import subprocess
+    from conftest import GOLD_IN
+    from oracle import oracle
+    res = []
+    for batch in ("0", "1"):
+        out = tmp_path / f"out{batch}.txt"
+        r = subprocess.run([oracle.DRIVER, "-i", os.path.join(GOLD_IN, name + ".txt"), "-o", str(out), "-v", "1", "-t", "4", *extra],
+                           capture_output=True, text=True, env=dict(os.environ, GAMBA_UPDATE_BATCH=batch, GAMBA_ORACLE_THREADS="4"))
+        assert r.returncode == 0, r.stderr
+        m = re.search(r"steps (\d+)  pairs (\d+)  gm-removed (\d+)  rows-reduced (\d+)  zero-reductions (\d+)", r.stdout)
+        res.append((m.groups(), out.read_bytes()))
+    assert res[0] == res[1]
