@@ -56,7 +56,9 @@
 namespace gcu {
 
 constexpr int ELIM_CTA_WARPS = 8;         // warps per row to reduce (template parameter WARPS: 8, or 4 when many rows
-                                          // must be resident per SM - the walk over the windows is latency-bound)
+                                          // must be resident per SM - the walk over the windows is latency-bound; 32 when a
+                                          // step has fewer rows than SMs against >= 65536 pivot rows: a row is ONE CTA, and
+                                          // the rate of its deferred passes is warps x one chunk per ~450 cycles)
 constexpr int ELIM_DEPTH = 4;             // cp.async ring slots per warp (512 B each)
 constexpr int ELIM_SCRATCH_WORDS = ELIM_DEPTH * 128;   // per warp: the ring
 
