@@ -4,7 +4,7 @@ dictionary on the host: same monomial sets, rows that decode to the same monomia
 monomial; their order inside a batch is whatever the device's atomics made it - nothing depends on it), table growth
 (rehash) and several batches per step. The end-to-end check is that the product driver, which
 generates every row this way, reproduces the goldens (tests/test_gpu_e2e.py) and the oracle driver's bases
-(tests/test_gpu_named.py)."""
+(tests/test_gpu_zz_named.py)."""
 import ctypes as C
 
 import numpy as np

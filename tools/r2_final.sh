@@ -2,7 +2,7 @@
 # last checks of the round on one B200: Monte-Carlo parity cases, the uncapped kat15-15 run against the oracle driver's md5, default bench
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
 t0=$SECONDS
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_named.py -x -q -k "monte_carlo or (config4 and kat15 and extra1) or config2" > gpurun_out/r2_final_pytest.log 2>&1; echo "pytest rc=$? ($((SECONDS-t0)) s)"; tail -4 gpurun_out/r2_final_pytest.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zz_named.py -x -q -k "monte_carlo or (config4 and kat15 and extra1) or config2" > gpurun_out/r2_final_pytest.log 2>&1; echo "pytest rc=$? ($((SECONDS-t0)) s)"; tail -4 gpurun_out/r2_final_pytest.log
 t0=$SECONDS
 GAMBA_BENCH_VERBOSE=1 timeout 900 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err; echo "bench rc=$? ($((SECONDS-t0)) s)"
 grep -v "cyclic9-15\[" gpurun_out/r2_final_bench.err | tail -c 1500
