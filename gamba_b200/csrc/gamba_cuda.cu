@@ -490,6 +490,12 @@ void gamba_cuda_engine::choose_layout(uint32_t n_top, uint32_t n_bot, uint32_t n
         // sizes, options and the previous step's rank only - never the calibration factors, which are rank-local timings.
         double t_mc = 1e30, t_exact = 1e30;
         int mode = mc_plan ? decide(mc_plan, true, t_mc, false) : -1;      // no runner-up runs on combinations: the sparse solve loses 150-280 ms there
+        if (mode >= 0) {
+            // a draw that misses the margin all the way falls back to the rows themselves ON THIS LAYOUT: their multiplier and
+            // operand planes must fit the same budget, or the step is planned for the rows from the start
+            const uint64_t mt_x = ((uint64_t)(n_bot + world - 1) / world + sc_bm - 1) / sc_bm;
+            if ((double)nl * (mt_x * sc_bm + nt_ * sc_bn) * ((double)kp + PANEL_T) > (double)opt_schur_max_gb * 1e9) mode = -1;
+        }
         if (mode < 0) { mc_plan = 0; mode = decide(n_bot, false, t_exact, true); }
         use_block = mode == 1; use_panel = mode == 2;
         if (use_block) tmax = BLK_TMAX;
